@@ -1,0 +1,532 @@
+"""CPU oracle for the fingerprint + marginal-Wasserstein misfit hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.  The product path
+(``waveform_ot_b200``) never imports, links or executes anything under
+``oracle/``.
+
+It is a plain NumPy FP64 restatement of the algorithm in the reference
+(msambridge/waveform-ot, pure Python + NumPy), function by function, each
+citing the reference ``file:line`` it follows.  Where the reference's exact
+floating-point *operation order* matters for index parity (normalisation,
+point-to-segment distance, first-minimum argmin) the same order of elementary
+operations is kept.
+
+Parity is PINNED: ``tests/test_oracle_golden.py`` checks this file against
+(1) the reference notebooks' printed known answers and
+(2) fixtures produced by running the unmodified reference in the build
+container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``).
+"""
+from __future__ import annotations
+
+import bisect
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# Exceptions (names follow libs/OTlib.py:34-75, libs/FingerprintLib.py:33-46)
+# --------------------------------------------------------------------------
+
+
+class PDFSignError(Exception):
+    pass
+
+
+class PDFShapeError(Exception):
+    pass
+
+
+class TargetSourceCDFError(Exception):
+    pass
+
+
+class TargetSource2DShapeError(Exception):
+    pass
+
+
+class MarginalWassersteinError(Exception):
+    pass
+
+
+class UnknownOTDistanceTypeError(Exception):
+    pass
+
+
+class FingerprintMethodError(Exception):
+    pass
+
+
+# --------------------------------------------------------------------------
+# Fingerprint: normalisation  (libs/FingerprintLib.py:53-115)
+# --------------------------------------------------------------------------
+
+
+@dataclass
+class Window:
+    """State of one waveform window; field names follow the reference's
+    ``waveformFP`` attributes (libs/FingerprintLib.py:84-115, 265-269, 385)."""
+    nt: int
+    ntg: int
+    nug: int
+    tlim: tuple
+    ulim: tuple
+    tant: float
+    theta: float
+    tlimn: tuple
+    tlimnfp: tuple
+    ulimnfp: tuple
+    pn: np.ndarray        # (nt,2) normalised sample coordinates
+    delta_n: np.ndarray   # (S,2) segment vectors
+    lsq_n: np.ndarray     # (S,)  squared segment lengths
+    lam: float = 0.04
+    q: object = None
+    dfield: np.ndarray | None = None
+    irays: np.ndarray | None = None
+    lrays: np.ndarray | None = None
+    xrays: np.ndarray | None = None
+    pos: np.ndarray | None = None
+    pdf: np.ndarray | None = None
+    dddy: np.ndarray | None = None
+    extra: dict = field(default_factory=dict)
+
+
+def resolve_theta(theta=45.0, tantheta=1.0):
+    """theta / tan(theta) precedence, libs/FingerprintLib.py:77-82."""
+    if tantheta != 1.0:
+        theta = np.arctan(tantheta) * 180.0 / np.pi
+    elif theta != 45.0:
+        tantheta = np.tan(np.pi * theta / 180.0)
+    else:
+        tantheta = 1.0
+    return theta, tantheta
+
+
+def make_window(t, w, grid, fpgrid=None, theta=45.0, tantheta=1.0) -> Window:
+    """Non-dimensionalise one waveform into the unit box
+    (libs/FingerprintLib.py:75-113)."""
+    t = np.asarray(t, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    t0, t1, u0, u1, nug, ntg = grid
+    theta, tantheta = resolve_theta(theta, tantheta)
+    delt = tantheta * (t1 - t0)                                   # :90
+    tlimn = ((t[0] - t0) / delt, (t[-1] - t0) / delt)             # :91
+    if fpgrid is None:                                            # :95-100
+        tlimnfp = tlimn
+        ulimnfp = (0.0, 1.0)
+    else:                                                         # :101-106
+        f0, f1, g0, g1 = fpgrid[0:4]
+        tlimnfp = ((f0 - t0) / delt, (f1 - t0) / delt)
+        ulimnfp = ((g0 - u0) / (u1 - u0), (g1 - u0) / (u1 - u0))
+    pn = np.empty((len(t), 2))
+    pn[:, 0] = (t - t0) / delt                                    # :110
+    pn[:, 1] = (w - u0) / (u1 - u0)
+    delta_n = pn[1:] - pn[:-1]                                    # :112
+    lsq_n = delta_n[:, 0] * delta_n[:, 0] + delta_n[:, 1] * delta_n[:, 1]  # :113
+    return Window(nt=len(t), ntg=int(ntg), nug=int(nug), tlim=(t0, t1),
+                  ulim=(u0, u1), tant=tantheta, theta=theta, tlimn=tlimn,
+                  tlimnfp=tlimnfp, ulimnfp=ulimnfp, pn=pn, delta_n=delta_n,
+                  lsq_n=lsq_n)
+
+
+def grid_axes(win: Window):
+    """Pixel coordinate axes, libs/FingerprintLib.py:254 (np.linspace)."""
+    T = np.linspace(win.tlimnfp[0], win.tlimnfp[1], win.ntg)
+    U = np.linspace(win.ulimnfp[0], win.ulimnfp[1], win.nug)
+    return T, U
+
+
+# --------------------------------------------------------------------------
+# Fingerprint: nearest distance / nearest segment (libs/FingerprintLib.py:230-269)
+# --------------------------------------------------------------------------
+
+
+def wdist(win: Window, chunk: int = 8192) -> Window:
+    """Brute-force point-to-polyline distance for every pixel.
+
+    Same elementary operations, in the same order, as
+    libs/FingerprintLib.py:256-263; evaluated in pixel chunks so the
+    (Npix x Nseg) temporaries stay small (the reference allocates them whole).
+    Pixel flat index k = iu*Nt + it (meshgrid 'xy', :254-255)."""
+    T, U = grid_axes(win)
+    nump = win.ntg * win.nug
+    px = np.tile(T, win.nug)
+    py = np.repeat(U, win.ntg)
+    x0 = win.pn[:-1]
+    c = win.delta_n
+    lsq = win.lsq_n
+    irays = np.empty(nump, dtype=np.int64)
+    lrays = np.empty(nump)
+    dsqmin = np.empty(nump)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for a in range(0, nump, chunk):
+            b = min(nump, a + chunk)
+            bx = px[a:b, None] - x0[None, :, 0]                   # :256
+            by = py[a:b, None] - x0[None, :, 1]
+            lam = np.clip((bx * c[None, :, 0] + by * c[None, :, 1]) / lsq[None, :],
+                          0.0, 1.0)                               # :257
+            dsx = bx - c[None, :, 0] * lam                        # :258
+            dsy = by - c[None, :, 1] * lam
+            dsq = dsx * dsx + dsy * dsy                           # :259
+            ic = np.argmin(dsq, axis=1)                           # :260 first minimum
+            ar = np.arange(b - a)
+            irays[a:b] = ic
+            lrays[a:b] = lam[ar, ic]                              # :261
+            dsqmin[a:b] = dsq[ar, ic]
+    xrays = x0[irays] + lrays[:, None] * c[irays]                 # :262
+    win.dfield = np.sqrt(dsqmin).reshape(win.nug, win.ntg)        # :263,265
+    win.irays = irays
+    win.lrays = lrays
+    win.xrays = xrays
+    Xn, Yn = np.meshgrid(T, U)
+    win.pos = np.dstack((Xn, Yn))                                 # :269
+    return win
+
+
+def wdistderiv(win: Window) -> Window:
+    """d(distance)/d(un-normalised amplitude of the two end samples of the
+    nearest segment); libs/FingerprintLib.py:349-385, term by term."""
+    T, U = grid_axes(win)
+    px = np.tile(T, win.nug)
+    py = np.repeat(U, win.ntg)
+    p = np.stack((px, py), axis=1)
+    dis = win.dfield.reshape(-1, 1)
+    ey = np.array([0.0, 1.0])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dddx = (win.xrays - p) / dis                              # :355
+        x0 = win.pn[:-1][win.irays]                               # :357
+        c = win.delta_n[win.irays]                                # :358
+        lsq = win.lsq_n[win.irays]
+        l = win.lrays
+        dlamdy0 = (2 * c[:, 1] * l + np.sum((p - ey) * c - (p - x0) * ey, axis=1)) / lsq   # :362
+        dlamdy0[l == 0] = 0.0                                     # :363-364
+        dlamdy0[l == 1] = 0.0
+        dxdy0 = ey + dlamdy0[:, None] * c - l[:, None] * ey       # :365
+        dlamdy1 = (-2 * c[:, 1] * l + np.sum(p * c + (p - x0) * ey, axis=1)) / lsq         # :367
+        dlamdy1[l == 0] = 0.0                                     # :368-369
+        dlamdy1[l == 1] = 0.0
+        dxdy1 = dlamdy1[:, None] * c + l[:, None] * ey            # :371
+        dddy0 = np.sum(dddx * dxdy0, axis=1)                      # :373
+        dddy1 = np.sum(dddx * dxdy1, axis=1)                      # :374
+    du = win.ulim[1] - win.ulim[0]                                # :376-378
+    win.dddy = np.stack((dddy0 / du, dddy1 / du), axis=1)         # :385
+    return win
+
+
+def calcpdf(win: Window, q=None, lambdav=0.04, deriv=False, method="Enumerate",
+            chunk: int = 8192) -> Window:
+    """Distance field -> density; libs/FingerprintLib.py:117-177
+    (method 'Enumerate' only, the one every notebook uses)."""
+    if method != "Enumerate":
+        raise FingerprintMethodError(method)
+    win.lam = lambdav
+    wdist(win, chunk=chunk)
+    if deriv:
+        wdistderiv(win)
+    win.q = q
+    if q is None:
+        win.pdf = np.exp(-np.abs(win.dfield) / win.lam)           # :174
+    elif q == 2:
+        win.pdf = np.exp(-win.dfield ** q / win.lam)              # :176
+    return win
+
+
+def pdfderiv(win: Window, chain) -> np.ndarray:
+    """Chain rule pixel -> waveform sample for ONE chain field;
+    libs/FingerprintLib.py:188-203.  The reference loops over samples with
+    boolean masks; the two bincounts below add the same terms per bin."""
+    row = win.pdf.reshape(-1) * np.asarray(chain).reshape(-1) if chain is not None \
+        else win.pdf.reshape(-1).copy()                           # :188-191
+    if win.q is not None and win.q == 2:
+        row = 2 * row * np.abs(win.dfield.reshape(-1))            # :193-194
+    s = np.bincount(win.irays, weights=win.dddy[:, 0] * row, minlength=win.nt)[:win.nt]
+    s = s + np.bincount(win.irays + 1, weights=win.dddy[:, 1] * row, minlength=win.nt)[:win.nt]
+    return -s / win.lam                                           # :203
+
+
+def pdfderiv_marg(win: Window, chains) -> list:
+    """libs/FingerprintLib.py:205-228: one gradient per marginal."""
+    return [pdfderiv(win, chains[0]), pdfderiv(win, chains[1])]
+
+
+# --------------------------------------------------------------------------
+# OTpdf  (libs/OTlib.py:82-117, 146-163)
+# --------------------------------------------------------------------------
+
+
+@dataclass
+class Pdf:
+    amp: float
+    pdf: np.ndarray
+    x: np.ndarray
+    cdf: np.ndarray
+    n: int
+    type: str
+    nx: int = 0
+    ny: int = 0
+    marg: list | None = None
+
+
+def otpdf(pdf, x) -> Pdf:
+    """Normalise + CDF; libs/OTlib.py:90-117."""
+    pdf = np.asarray(pdf, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    if np.min(pdf) < 0.0:                                         # :91
+        raise PDFSignError()
+    amp = np.sum(pdf)                                             # :92
+    p = pdf / amp                                                 # :93
+    if p.ndim == 2:                                               # :97-105
+        if p.shape != x.shape[:2]:
+            raise PDFShapeError()
+        nx, ny = x.shape[0], x.shape[1]
+        n, typ = nx * ny, "2D"
+    else:                                                         # :106-110
+        if len(pdf) != len(x):
+            raise PDFShapeError()
+        nx = ny = 0
+        n, typ = len(pdf), "1D"
+    cdf = np.cumsum(p)                                            # :112
+    cdf = cdf / cdf[-1]                                           # :113
+    return Pdf(amp=amp, pdf=p, x=x.copy(), cdf=cdf, n=n, type=typ, nx=nx, ny=ny)
+
+
+def set_marginals(P: Pdf) -> Pdf:
+    """libs/OTlib.py:146-163: marg[0] = time marginal (sum over amplitude
+    rows), marg[1] = amplitude marginal; each re-normalised as a 1-D Pdf."""
+    if P.type != "2D":
+        raise TargetSource2DShapeError()
+    f0 = np.sum(P.pdf, axis=0)                                    # :155
+    f1 = np.sum(P.pdf, axis=1)                                    # :156
+    P.marg = [otpdf(f0, P.x[0, :, 0]), otpdf(f1, P.x[:, 0, 1])]    # :157-160
+    return P
+
+
+# --------------------------------------------------------------------------
+# 1-D Wasserstein  (libs/OTlib.py:596-706)
+# --------------------------------------------------------------------------
+
+
+def merge_cdfs(cf, cg):
+    """Knot set, merged order and quantile ranks; libs/OTlib.py:668-673."""
+    a = np.append(cf[:-1], cg)                                    # :668
+    tkarg = np.argsort(a)                                         # :669
+    tk = a[tkarg]                                                 # :670
+    indf = np.array([bisect.bisect_left(cf, v) for v in tk], dtype=np.int64)   # :671
+    indg = np.array([bisect.bisect_left(cg, v) for v in tk], dtype=np.int64)   # :672
+    dtk = np.insert(tk[1:] - tk[:-1], 0, tk[0])                   # :673
+    return tkarg, tk, indf, indg, dtk
+
+
+def wasser(source: Pdf, target: Pdf, distfunc="W12", derivatives=False,
+           checkCommonCDF=False, ignoreCommonCDFerror=False, return_merge=False):
+    """W_p^p (p=1,2), d/d(un-normalised source amplitudes), d/d(translation);
+    libs/OTlib.py:643-706.  Output list order as the reference's (:688-706)."""
+    if not isinstance(distfunc, str):
+        raise UnknownOTDistanceTypeError()
+    calcW2 = distfunc in ("W2", "W12")                            # :170-174
+    calcW1 = distfunc in ("W1", "W12")
+    cf, cg, n = source.cdf, target.cdf, source.n
+    if derivatives or checkCommonCDF:                             # :663-666
+        cset = np.intersect1d(cg[:-1], cf[:-1])
+        if len(cset) != 0 and not ignoreCommonCDFerror:
+            raise TargetSourceCDFError(str(cset))
+    tkarg, tk, indf, indg, dtk = merge_cdfs(cf, cg)
+    xft = source.x[indf]                                          # :676-678
+    xgt = target.x[indg]
+    dxft = np.abs(xft - xgt)
+    if derivatives:                                               # :681-686
+        B = np.triu(np.ones((n, target.n)))
+        C = (B - cf) / source.amp
+        D = np.hstack((C[:, :-1], np.zeros((n, target.n))))
+        Difftk = D[:, tkarg]
+        Diffdtk = np.hstack((Difftk[:, 0:1], Difftk[:, 1:] - Difftk[:, :-1]))
+    out = []
+    if calcW1:                                                    # :689-696
+        out.append(np.dot(dxft, dtk))
+        if derivatives:
+            out.append(np.dot(Diffdtk, dxft))
+            out.append(np.dot(np.sign(xft - xgt), dtk))
+    if calcW2:                                                    # :698-706
+        dsq = dxft * dxft
+        out.append(np.dot(dsq, dtk))
+        if derivatives:
+            out.append(np.dot(Diffdtk, dsq))
+            out.append(np.dot(2.0 * (xft - xgt), dtk))
+    if return_merge:
+        return out, (tkarg, indf, indg)
+    return out
+
+
+def wasser_linear(source: Pdf, target: Pdf, distfunc="W12"):
+    """O(n+m) restatement of :681-706's derivative;
+    used by tests to cross-check the dense form and by large-size checks.
+    With c_k = |dx_k|^p, e_k = c_k - c_{k+1} (c past the end = 0) and E_j = e at
+    the merged position of source knot F_j (j <= n-2; E_{n-1} = 0):
+    dW/df_i = (sum_{j>=i} E_j - sum_j F_j E_j) / amp."""
+    cf, cg, n = source.cdf, target.cdf, source.n
+    tkarg, tk, indf, indg, dtk = merge_cdfs(cf, cg)
+    dx = source.x[indf] - target.x[indg]
+    res = []
+    for p in ((1,) if distfunc == "W1" else (2,) if distfunc == "W2" else (1, 2)):
+        c = np.abs(dx) ** p
+        e = c - np.append(c[1:], 0.0)
+        E = np.zeros(n)
+        pos_of = np.empty(len(tkarg), dtype=np.int64)
+        pos_of[tkarg] = np.arange(len(tkarg))
+        E[: n - 1] = e[pos_of[: n - 1]]
+        suffix = np.cumsum(E[::-1])[::-1]
+        dW = (suffix - np.dot(cf, E)) / source.amp
+        dpos = np.dot(np.sign(dx), dtk) if p == 1 else np.dot(2.0 * dx, dtk)
+        res += [np.dot(c, dtk), dW, dpos]
+    return res
+
+
+# --------------------------------------------------------------------------
+# Marginal Wasserstein on 2-D densities  (libs/OTlib.py:1055-1154)
+# --------------------------------------------------------------------------
+
+
+def marg_wasserstein(source: Pdf, target: Pdf, distfunc="W2", derivatives=False,
+                     returnmargW=False):
+    if source.type != "2D" or target.type != "2D":                # :1088-1089
+        raise TargetSource2DShapeError()
+    if isinstance(distfunc, str) and distfunc == "W12":           # :1090-1091
+        raise MarginalWassersteinError("W12")
+    if source.marg is None:                                       # :1093-1094
+        set_marginals(source)
+    if target.marg is None:
+        set_marginals(target)
+    nx, ny = source.nx, source.ny
+    if derivatives:
+        dwp = np.zeros((nx, ny))
+        dwpX = np.zeros((nx, ny))
+        dwpY = np.zeros((nx, ny))
+    wpm = np.zeros(2)
+    dwgm = [0.0, 0.0]
+    dwg = 0.0
+    for i in range(2):                                            # :1106-1132
+        wout = wasser(source.marg[i], target.marg[i], distfunc=distfunc,
+                      derivatives=derivatives, checkCommonCDF=True)
+        wpm[i] = wout[0]
+        if derivatives:
+            dw = wout[1]
+            if i == 0:
+                dwp[:] += dw                                      # :1120 broadcast over rows
+                dwg = wout[2]                                     # :1121
+                dwgm[0] = dwg
+                dwpX = dwp.copy()                                 # :1123
+            else:
+                dwp.T[:] += dw                                    # :1126
+                dwpY.T[:] += dw                                   # :1127
+    wp = wpm[0] + wpm[1]
+    if not derivatives:
+        return [[wpm[0], wpm[1]]] if returnmargW else [wp / 2]    # :1136-1138,1153
+    pflat = source.pdf.reshape(-1)
+    dwp = (dwp - np.dot(dwp.reshape(-1), pflat)) / source.amp     # :1141-1142
+    if returnmargW:                                               # :1143-1149
+        dwpX = (dwpX - np.dot(dwpX.reshape(-1), pflat)) / source.amp
+        dwpY = (dwpY - np.dot(dwpY.reshape(-1), pflat)) / source.amp
+        return [[wpm[0], wpm[1]], [dwpX, dwpY], dwgm]
+    return [wp / 2, dwp / 2, dwg / 2]                             # :1150-1151
+
+
+# --------------------------------------------------------------------------
+# Adapter tails (libs/ricker_util.py:204-339, libs/loc_cmt_util.py:430-587)
+# --------------------------------------------------------------------------
+
+
+def arctan_trans(u, u0, u1, deriv=False):
+    """libs/ricker_util.py:270-275 == libs/loc_cmt_util.py:583-585."""
+    up = ((u - u0) + (u - u1)) / (u1 - u0)
+    un = 0.5 + np.arctan(up) / np.pi
+    if deriv:
+        return un, 2 / ((u1 - u0) * np.pi * (1 + up * up))
+    return un
+
+
+def build_fingerprint_window(t, wave):
+    """Window rule of libs/loc_cmt_util.py:435-445 for one trace."""
+    du = np.max(wave) - np.min(wave)
+    return [np.min(t), np.max(t), np.min(wave) - 0.3 * du, np.max(wave) + 0.3 * du,
+            int(1.3 * len(wave)), len(wave)]
+
+
+def build_ot_from_waveform(t, wave, grid, lambdav=0.04, deriv=False, transform=False,
+                           theta=45.0, q=None, chunk=8192):
+    """libs/ricker_util.py:241-268 (also the per-window body of
+    libs/loc_cmt_util.py:508-519, whose ``pos`` is the same grid)."""
+    t0, t1, u0, u1, Nu, Nt = grid
+    if transform:                                                 # :241-244
+        wave = arctan_trans(np.asarray(wave, dtype=np.float64), u0, u1)
+        u0, u1 = 0.0, 1.0
+    win = make_window(t, wave, (t0, t1, u0, u1, Nu, Nt), theta=theta)
+    calcpdf(win, q=q, lambdav=lambdav, deriv=deriv, chunk=chunk)
+    return win, otpdf(win.pdf, win.pos)                           # :261-268
+
+
+def calc_wasser_waveform(src: Pdf, tgt: Pdf, win: Window, distfunc="W2", deriv=False,
+                         returnmarg=False, adapter="ricker"):
+    """libs/ricker_util.py:321-339 (adapter='ricker': origin-time derivative
+    divided by tan(theta)*(t1-t0)) and libs/loc_cmt_util.py:557-574
+    (adapter='cmt': divided by (t1-t0))."""
+    if not deriv:
+        out = marg_wasserstein(src, tgt, distfunc=distfunc, returnmargW=returnmarg)
+        return out if returnmarg else out[0]
+    w, dw, dwg = marg_wasserstein(src, tgt, distfunc=distfunc, derivatives=True,
+                                  returnmargW=returnmarg)
+    scale = win.tlim[1] - win.tlim[0]
+    if adapter == "ricker":
+        scale = win.tant * scale
+    if returnmarg:
+        return w, pdfderiv_marg(win, dw), [dwg[0] / scale, dwg[1] / scale]
+    return w, pdfderiv(win, dw), dwg / scale
+
+
+def misfit_grad_window(t, w, grid, target: Pdf, lambdav=0.04, distfunc="W2",
+                       theta=45.0, transform=False, q=None, adapter="ricker",
+                       chunk=8192):
+    """One 'evaluation' in the BASELINE.json sense: predicted window ->
+    fingerprint -> marginals -> W_p^p per marginal -> dW/dw (nt,) per marginal
+    and dW/dt_origin.  Composition of ru.optfunc's middle
+    (libs/ricker_util.py:386-388)."""
+    win, src = build_ot_from_waveform(t, w, grid, lambdav=lambdav, deriv=True,
+                                      transform=transform, theta=theta, q=q, chunk=chunk)
+    W, dr, dg = calc_wasser_waveform(src, target, win, distfunc=distfunc, deriv=True,
+                                     returnmarg=True, adapter=adapter)
+    if transform:                                                 # :393-397
+        _, dundu = arctan_trans(np.asarray(w, dtype=np.float64), grid[2], grid[3], deriv=True)
+        dr = [dr[0] * dundu, dr[1] * dundu]
+    return W, dr, dg, win, src
+
+
+# --------------------------------------------------------------------------
+# Synthetic inputs shared by tests and bench (host side, not part of the path)
+# --------------------------------------------------------------------------
+
+
+def ricker(f, length=0.128, dt=0.001):
+    """libs/ricker_util.py:22-30 (no derivative)."""
+    t = np.arange(-length / 2, (length - dt) / 2, dt)
+    a = 1.0 - 2.0 * (np.pi ** 2) * (f ** 2) * (t ** 2)
+    return t, a * np.exp(-(np.pi ** 2) * (f ** 2) * (t ** 2))
+
+
+def rickerwavelet(tpert, amp, f, trange=(-2.0, 2.0)):
+    """Noise-free double Ricker wavelet, libs/ricker_util.py:62-70,89."""
+    _, w = ricker(f * 25 * 4 / 128, length=4, dt=4 / 128)
+    wp = amp * np.concatenate((w, w))
+    tp = np.linspace(trange[0], trange[1], len(wp))
+    return tp + tpert, wp
+
+
+def random_walk_windows(B, nt, seed=5, dtype=np.float32):
+    """cfg5 input rule: cumulative-sum random walk,
+    moving average 8, scaled to max|w| = 1."""
+    rng = np.random.default_rng(seed)
+    x = np.cumsum(rng.standard_normal((B, nt + 7)), axis=1)
+    k = np.ones(8) / 8.0
+    y = np.stack([np.convolve(r, k, mode="valid") for r in x])
+    y -= y.mean(axis=1, keepdims=True)
+    y /= np.max(np.abs(y), axis=1, keepdims=True)
+    return y.astype(dtype)

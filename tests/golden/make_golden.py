@@ -1,0 +1,135 @@
+"""Generate golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  The fixtures pin ``oracle/wfot_oracle.py`` and,
+through it, the CUDA path.  Inputs are generated from fixed seeds and stored in
+the fixture next to the outputs, so tests never need the reference.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _refimport import import_reference  # noqa: E402
+
+fp, OT, ru = import_reference()
+
+
+def run_window(t, w, grid, lam, q=None, fpgrid=None, theta=45.0, tantheta=1.0):
+    wf = fp.waveformFP(t, w, grid, fpgrid=fpgrid, theta=theta, tantheta=tantheta)
+    wf.calcpdf(q=q, lambdav=lam, deriv=True)
+    return wf
+
+
+def full_pair(tag, tp, wp, to, wo, grid, lam, distfunc, q=None, fpgrid=None, theta=45.0,
+              sub=None):
+    """pred (tp,wp) vs obs (to,wo) on a common grid through the reference's
+    own calls: waveformFP -> calcpdf -> OTpdf -> MargWasserstein -> PDFderivMarg."""
+    wf = run_window(tp, wp, grid, lam, q=q, fpgrid=fpgrid, theta=theta)
+    wo_ = run_window(to, wo, grid, lam, q=q, fpgrid=fpgrid, theta=theta)
+    src = OT.OTpdf((wf.pdf, wf.pos))
+    tgt = OT.OTpdf((wo_.pdf, wo_.pos))
+    W, dW, dwg = OT.MargWasserstein(src, tgt, distfunc=distfunc, derivatives=True, returnmargW=True)
+    wf.PDFderivMarg(dW)
+    Wavg, dWavg, dwgavg = OT.MargWasserstein(src, tgt, distfunc=distfunc, derivatives=True)
+    wf.PDFderiv(chainmatrix=dWavg)
+    d = dict(
+        tp=tp, wp=wp, to=to, wo=wo, grid=np.array(grid, dtype=np.float64), lam=lam,
+        distfunc=distfunc, q=-1 if q is None else q,
+        fpgrid=np.array(fpgrid if fpgrid is not None else [], dtype=np.float64), theta=theta,
+        pn=wf.pn, lsq_n=wf.lsq_n, tlimn=np.array(wf.tlimn),
+        amp=src.amp, marg_t=src.marg[0].pdf, marg_u=src.marg[1].pdf,
+        cdf_t=src.marg[0].cdf, cdf_u=src.marg[1].cdf, x_t=src.marg[0].x, x_u=src.marg[1].x,
+        tgt_amp=tgt.amp, tgt_cdf_t=tgt.marg[0].cdf, tgt_cdf_u=tgt.marg[1].cdf,
+        tgt_x_t=tgt.marg[0].x, tgt_x_u=tgt.marg[1].x,
+        W=np.array(W), dwg=np.array(dwg, dtype=np.float64),
+        pdfdMarg0=wf.pdfdMarg[0], pdfdMarg1=wf.pdfdMarg[1],
+        Wavg=Wavg, dwgavg=dwgavg, pdfd=wf.pdfd,
+        sum_dfield=wf.dfield.sum(), sum_pdf=wf.pdf.sum(), sum_irays=int(wf.irays.sum()),
+        sum_lrays=wf.lrays.sum(),
+    )
+    if sub is None:
+        d.update(dfield=wf.dfield, irays=wf.irays.astype(np.int32), lrays=wf.lrays,
+                 xrays=wf.xrays, pdf=wf.pdf, dddy=wf.dddy, dWt=dW[0], dWu=dW[1])
+    else:  # strided subsample of the per-pixel fields (keeps the fixture small)
+        k = np.arange(0, wf.irays.size, sub)
+        d.update(sub=sub, dfield_sub=wf.dfield.reshape(-1)[k], irays_sub=wf.irays[k].astype(np.int32),
+                 lrays_sub=wf.lrays[k], pdf_sub=wf.pdf.reshape(-1)[k], dddy_sub=wf.dddy[k],
+                 irays_all=wf.irays.astype(np.int16),
+                 dWt_row0=dW[0][0, :], dWu_col0=dW[1][:, 0])
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **d)
+    print(tag, "W", W, "dwg", dwg)
+
+
+def main():
+    # ---- (1) point masses: Point_mass_demo_Fig_5.ipynb cells 3/11/13 ------
+    fx = np.linspace(3, 14, 6)
+    gx = np.linspace(7, 18, 6)
+    f = np.array([.2, .01, .18, .21, .2, .2])
+    g = np.array([.18, .07, .2, .05, .27, .23])
+    s, t = OT.OTpdf((f, fx)), OT.OTpdf((g, gx))
+    out = OT.wasser(s, t, 'W12', derivatives=True)
+    np.savez(os.path.join(HERE, "pointmass.npz"), f=f, g=g, fx=fx, gx=gx,
+             W1=out[0], dW1=out[1], dW1pos=out[2], W2=out[3], dW2=out[4], dW2pos=out[5],
+             cdf_f=s.cdf, cdf_g=t.cdf)
+
+    # ---- (2) 1-D random OT, n == m with derivatives, n != m without -------
+    rng = np.random.default_rng(20221)
+    n = 96
+    f = rng.random(n) + 1e-3
+    g = rng.random(n) + 1e-3
+    x = np.linspace(0, 1, n)
+    xg = np.sort(rng.random(n)) * 1.5 - 0.2
+    s, t = OT.OTpdf((f, x)), OT.OTpdf((g, xg))
+    out = OT.wasser(s, t, 'W12', derivatives=True)
+    f2 = rng.random(50) + 1e-3
+    g2 = rng.random(70) + 1e-3
+    x2f, x2g = np.linspace(0, 1, 50), np.linspace(-0.1, 1.3, 70)
+    s2, t2 = OT.OTpdf((f2, x2f)), OT.OTpdf((g2, x2g))
+    out2 = OT.wasser(s2, t2, 'W12')
+    np.savez(os.path.join(HERE, "ot1d_random.npz"), f=f, g=g, xf=x, xg=xg,
+             W1=out[0], dW1=out[1], dW1pos=out[2], W2=out[3], dW2=out[4], dW2pos=out[5],
+             f2=f2, g2=g2, x2f=x2f, x2g=x2g, W1_2=out2[0], W2_2=out2[1])
+
+    # ---- (3) Ricker cfg1 shape, noise-free: Ricker_waveform_derivatives.ipynb cells 7/12/14
+    tp, wp = ru.rickerwavelet(5.0, 3.0, 0.5, trange=[-2, 2])
+    to, wo = ru.rickerwavelet(0.0, 1.6, 1.0, trange=[-2, 2])
+    full_pair("ricker_cfg1", tp, wp, to, wo, (-2, 2, -2.0, 3.5, 80, 512), 0.03, "W2", sub=97)
+    full_pair("ricker_cfg1_w1", tp, wp, to, wo, (-2, 2, -2.0, 3.5, 80, 512), 0.03, "W1", sub=97)
+
+    # ---- (4) small random windows, all per-pixel fields kept --------------
+    rng = np.random.default_rng(7)
+    nt = 24
+    t = np.sort(rng.random(nt)) * 3.0 + 0.5          # non-uniform sampling
+    t[0], t[-1] = 0.5, 3.5
+    wp = rng.standard_normal(nt).cumsum() * 0.3
+    wo = wp + 0.25 * rng.standard_normal(nt)
+    full_pair("small_q1", t, wp, t + 0.2, wo, (0.0, 4.0, -2.5, 2.5, 20, 16), 0.05, "W2")
+    full_pair("small_q2", t, wp, t + 0.2, wo, (0.0, 4.0, -2.5, 2.5, 20, 16), 0.05, "W2", q=2)
+    full_pair("small_theta", t, wp, t + 0.2, wo, (0.0, 4.0, -2.5, 2.5, 20, 16), 0.05, "W1", theta=60.0)
+    full_pair("small_fpgrid", t, wp, t + 0.2, wo, (0.0, 4.0, -2.5, 2.5, 20, 16), 0.05, "W2",
+              fpgrid=(0.2, 3.9, -2.0, 2.2))
+
+    # ---- (5) cmt-shaped window: nt=61 -> 79x61, arctan transform, lambda=0.04
+    rng = np.random.default_rng(11)
+    t = np.arange(61.0)
+    pulse = np.exp(-0.5 * ((t - 25.0) / 4.0) ** 2) * np.sin(0.5 * (t - 25.0))
+    wp = 1e-3 * (pulse + 0.02 * rng.standard_normal(61))
+    wo = 1e-3 * (np.roll(pulse, 3) * 1.2 + 0.03 * rng.standard_normal(61))
+    du = wo.max() - wo.min()
+    u0, u1 = wo.min() - 0.3 * du, wo.max() + 0.3 * du
+    unp = ru.arctan_trans(wp, u0, u1)
+    uno = ru.arctan_trans(wo, u0, u1)
+    full_pair("cmt_window", t, unp, t, uno, (0.0, 60.0, 0.0, 1.0, 79, 61), 0.04, "W2")
+    d = dict(np.load(os.path.join(HERE, "cmt_window.npz")))
+    d.update(raw_wp=wp, raw_wo=wo, u0=u0, u1=u1)
+    np.savez_compressed(os.path.join(HERE, "cmt_window.npz"), **d)
+
+
+if __name__ == "__main__":
+    main()
