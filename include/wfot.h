@@ -1,0 +1,186 @@
+/*
+ * wfot.h -- C ABI of libwfot.so: the B200 (sm_100a) implementation of
+ * waveform-ot's fingerprint + marginal-Wasserstein misfit hot path.
+ *
+ * The reference (msambridge/waveform-ot) has no FFI: its boundary is the
+ * Python module surface libs/FingerprintLib.py + libs/OTlib.py.  Each entry
+ * point below names the reference function(s) it replaces; the Python shim
+ * (waveform_ot_b200/FingerprintLib.py, OTlib.py) binds them with ctypes and
+ * re-creates the reference's classes/attributes on top.  INTEGRATION.md shows
+ * the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; every array pointer is a DEVICE pointer unless the
+ *    function name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *  - the caller owns every buffer, including the scratch workspace whose size
+ *    the matching *_workspace_bytes() call reports.  The library keeps no
+ *    global state and never allocates persistent device memory.
+ *  - calls are asynchronous on `stream`; return value 0 = launched OK,
+ *    negative = wfot_status (see wfot_strerror).  Data-dependent conditions the
+ *    reference reports as Python exceptions (negative density, common CDF
+ *    values, zero distance in a derivative) are counted into the `status`
+ *    device array (WFOT_STAT_* slots, int32 each, per call, accumulated with
+ *    atomics) and mapped back to the reference's exception classes by the shim.
+ *  - window b of a batch reads t + b*t_stride and w + b*nt (t_stride = 0
+ *    shares one time axis); grids[n_grids==1 ? 0 : b].
+ *  - pixel flat index k = iu*ntg + it (row-major (nug, ntg), the reference's
+ *    meshgrid 'xy' order, libs/FingerprintLib.py:254-255).
+ */
+#ifndef WFOT_H
+#define WFOT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFOT_VERSION 100
+
+/* ---- status codes ------------------------------------------------------ */
+enum wfot_status {
+    WFOT_OK = 0,
+    WFOT_ERR_INVALID_ARG = -1,
+    WFOT_ERR_CUDA = -2,
+    WFOT_ERR_UNSUPPORTED = -3,  /* e.g. not an sm_100 device, window too large for smem */
+    WFOT_ERR_WORKSPACE = -4
+};
+
+/* slots of the per-call `status` device array (int32[WFOT_STAT_SLOTS]) */
+enum wfot_stat_slot {
+    WFOT_STAT_NEG_PDF = 0,        /* OTpdf: min(pdf) < 0        (libs/OTlib.py:91)      */
+    WFOT_STAT_COMMON_CDF = 1,     /* wasser: cf[:-1] n cg[:-1]  (libs/OTlib.py:663-666) */
+    WFOT_STAT_ZERO_DIST = 2,      /* wdistderiv: d == 0 -> NaN  (libs/FingerprintLib.py:355) */
+    WFOT_STAT_DEGENERATE_SEG = 3, /* zero-length segment        (libs/FingerprintLib.py:257, 0/0) */
+    WFOT_STAT_SLOW_PIXELS = 4,    /* pixels resolved by the full FP64 rescan (diagnostic) */
+    WFOT_STAT_SLOTS = 8
+};
+
+enum wfot_dtype { WFOT_F32 = 0, WFOT_F64 = 1 };
+
+/* p-mask for the Wasserstein order: the reference's distfunc strings */
+enum wfot_pmask { WFOT_W1 = 1, WFOT_W2 = 2, WFOT_W12 = 3 };
+
+/* The reference's `grid` tuple (t0,t1,u0,u1,Nu,Nt) plus optional fpgrid and
+ * tan(theta): libs/FingerprintLib.py:53,75-106.  Nu/Nt are per call. */
+typedef struct wfot_grid {
+    double t0, t1, u0, u1;             /* non-dimensionalisation box            */
+    double fp_t0, fp_t1, fp_u0, fp_u1; /* fingerprint box, used iff has_fpgrid  */
+    double tantheta;                   /* metric weighting, 1.0 for theta = 45  */
+    int32_t has_fpgrid;
+    int32_t reserved;
+} wfot_grid;
+
+/* ---- library ------------------------------------------------------------ */
+int wfot_version(void);
+const char* wfot_strerror(int status);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char* wfot_last_cuda_error(void);
+/* SM count / compute capability of the current device; < 0 on error */
+int wfot_device_sm_count(void);
+int wfot_device_cc(void);
+
+/* ---- fingerprint (materialising path) ------------------------------------
+ * Replaces waveformFP.__init__ + calcpdf(method='Enumerate') + wdist +
+ * wdistderiv: libs/FingerprintLib.py:53-115, 117-177, 230-269, 333-385.
+ * FP32 brute-force argmin over all segments, exact FP64 re-evaluation (in the
+ * reference's operation order) of every near-minimal candidate, so `iray`
+ * equals the reference's np.argmin first-minimum index.
+ * Any output pointer may be NULL (not materialised).  Outputs are FP64:
+ *   pn     (B, nt, 2)   normalised sample coordinates            (:110)
+ *   dfield (B, nug, ntg) nearest distance                        (:265)
+ *   iray   (B, nug*ntg) int32 nearest segment                    (:266)
+ *   lray   (B, nug*ntg) clipped segment parameter                (:268)
+ *   xray   (B, nug*ntg, 2) nearest point on the waveform         (:267)
+ *   pdf    (B, nug, ntg) exp(-|d|/lambda) (q=0) or exp(-d^2/lambda) (q=2)  (:174,176)
+ *   dddy   (B, nug*ntg, 2) d(d)/d(raw amplitude of the segment's end samples) (:385)
+ */
+size_t wfot_fingerprint_workspace_bytes(int B, int nt, int nug, int ntg);
+int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
+                           const wfot_grid* grids, int n_grids, int B, int nug, int ntg,
+                           double lambda, int q,
+                           double* pn, double* dfield, int32_t* iray, double* lray, double* xray,
+                           double* pdf, double* dddy,
+                           void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
+/* ---- marginals ------------------------------------------------------------
+ * Replaces OTpdf.__init__ (2-D) + setMarginals: libs/OTlib.py:90-117, 146-163.
+ * pdf (B, nug, ntg) FP64 un-normalised ->
+ *   amp (B,), marg_t (B, ntg) = sum over rows / amp, marg_u (B, nug) = sum over
+ *   columns / amp  (i.e. the marginals of the normalised 2-D density).
+ * Vectorised, coalesced, deterministic (fixed-order) reductions. */
+int wfot_marginals_batch(const double* pdf, int B, int nug, int ntg,
+                         double* amp, double* marg_t, double* marg_u,
+                         int32_t* status, void* stream);
+
+/* ---- 1-D optimal transport -------------------------------------------------
+ * Replaces OTpdf.__init__ (1-D) + wasser(distfunc in {'W1','W2','W12'},
+ * derivatives=...): libs/OTlib.py:90-117, 596-706.
+ * f (B, n) un-normalised source amplitudes, g (B, m) target; *_stride in
+ * elements (0 = shared by the whole batch).  Prefix-scan CDFs (FP64), stable
+ * merge of cf[:-1] and cg (source first on ties), bisect_left quantile ranks.
+ * Outputs (any may be NULL): W (B, 2) = [W1, W2^2] (slot unused by pmask left
+ * untouched), dW1/dW2 (B, n) d/d(un-normalised f), dpos (B, 2) d/d(translation
+ * of the source), amp_f (B,), cdf_f (B, n), cdf_g (B, m),
+ * merge_order (B, n+m-1) int32 = the reference's `tkarg` (:669).
+ * WFOT_STAT_COMMON_CDF counts exact cf/cg coincidences (:663-666). */
+int wfot_ot1d_batch(const void* f, const void* g, int in_dtype,
+                    const double* xf, const double* xg,
+                    long long f_stride, long long g_stride, long long xf_stride, long long xg_stride,
+                    int n, int m, int B, int pmask, int derivatives,
+                    double* W, double* dW1, double* dW2, double* dpos,
+                    double* amp_f, double* cdf_f, double* cdf_g, int32_t* merge_order,
+                    int32_t* status, void* stream);
+
+/* ---- gradient assembly (materialising path) --------------------------------
+ * Replaces waveformFP.PDFderiv / PDFderivMarg: libs/FingerprintLib.py:182-228.
+ * out (B, nchain, nt) = -1/lambda * segmented sum over pixels keyed by iray of
+ * dddy * pdf * chain (* 2|d| if q == 2).  chain (B, nchain, nug*ntg) or NULL
+ * (chain == 1, nchain must be 1). */
+int wfot_pdfderiv_batch(const double* pdf, const double* dfield, const int32_t* iray,
+                        const double* dddy, const double* chain, int nchain,
+                        int B, int npix, int nt, double lambda, int q,
+                        double* out, void* stream);
+
+/* ---- fused misfit + gradient (throughput path) -------------------------------
+ * One "evaluation" per window: fingerprint -> marginals -> W_p^p per marginal ->
+ * d/d(waveform amplitudes) per marginal and d/d(window position), nothing but
+ * the waveform read from and the (2 + 2*nt + 1) results written to HBM.
+ * Replaces the chain ru.BuildOTobjfromWaveform -> OT.MargWasserstein(derivatives
+ * =True, returnmargW=True) -> wf.PDFderivMarg: libs/ricker_util.py:204-268,
+ * 321-337; libs/OTlib.py:1055-1154; libs/FingerprintLib.py:205-228.
+ * Target (observed) marginals are given as their CDFs + bin positions:
+ *   tgt_cdf_t/tgt_x_t (Bt, ntg), tgt_cdf_u/tgt_x_u (Bt, nug), window b uses
+ *   row (tgt_stride_windows ? b : 0).
+ * Outputs: W (B, 2) = [W^t, W^u]; grad (B, 2, nt) = [dW^t/dw, dW^u/dw] (NULL =
+ * misfit only); dwg (B,) = dW^t/d(translation) in normalised time units
+ * (divide by tan(theta)*(t1-t0) as libs/ricker_util.py:333).
+ * pmask is WFOT_W1 or WFOT_W2.  If transform != 0 the arctan amplitude
+ * transform of libs/ricker_util.py:270-275 is applied in-kernel with each
+ * grid's (u0,u1) and the gradient is multiplied by d(un)/du (:393-397). */
+size_t wfot_misfit_grad_workspace_bytes(int B, int nt, int nug, int ntg);
+int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
+                           const wfot_grid* grids, int n_grids, int B, int nug, int ntg,
+                           double lambda, int q, int pmask, int transform,
+                           const double* tgt_cdf_t, const double* tgt_x_t,
+                           const double* tgt_cdf_u, const double* tgt_x_u, int tgt_per_window,
+                           double* W, double* grad, double* dwg,
+                           void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
+/* ---- chain to model parameters ----------------------------------------------
+ * Replaces `dw.dot(dr)` / `d.dot(dr.flatten())`: libs/ricker_util.py:399-400,
+ * libs/loc_cmt_util.py:283-296.  out (M, P) = J (M, P, L) . dr (M, L);
+ * J_stride_models = 0 shares one Jacobian. */
+int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M,
+                     long long J_stride_models, double* out, void* stream);
+
+/* ---- microbenchmark used by bench.py to measure the FP32-pipe peak -----------
+ * Runs `iters` dependent-free FFMA2 (packed) or FFMA (scalar) bundles on every
+ * SM; returns executed FMA lane-operations through *fma_ops (host pointer). */
+int wfot_fp32_peak_probe(int packed, int iters, float* sink, double* fma_ops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFOT_H */

@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+reference-generated golden fixtures.  Run on the B200 box: pytest -m gpu.
+
+Stated tolerances (FP64 reference):
+  * nearest-segment indices, segment parameters, distances, nearest points: BIT-EXACT
+    (the kernel re-evaluates near-minimal candidates in FP64 in the reference's order);
+  * densities: 4 ulp (CUDA exp vs glibc exp);
+  * marginals, CDFs, W_p^p, gradients: rtol 1e-9 (well inside the 1e-5 the spec allows).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import wfot_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def B():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from waveform_ot_b200 import batch
+    return batch
+
+
+def _grid(g):
+    return tuple(g["grid"][:4]) + (int(g["grid"][4]), int(g["grid"][5]))
+
+
+def _case(g):
+    q = None if int(g["q"]) < 0 else int(g["q"])
+    fpgrid = tuple(g["fpgrid"]) if g["fpgrid"].size else None
+    theta = float(g["theta"])
+    _, tant = O.resolve_theta(theta, 1.0)
+    return q, fpgrid, theta, tant, float(g["lam"]), str(g["distfunc"])
+
+
+def _oracle_window(t, w, grid, lam, q=None, fpgrid=None, theta=45.0, deriv=True):
+    win = O.make_window(t, w, grid, fpgrid=fpgrid, theta=theta)
+    O.calcpdf(win, q=q, lambdav=lam, deriv=deriv)
+    return win
+
+
+def _check_fields(out, win, b=0):
+    np.testing.assert_array_equal(out["pn"][b].cpu().numpy(), win.pn)
+    np.testing.assert_array_equal(out["iray"][b].cpu().numpy().astype(np.int64), win.irays)
+    np.testing.assert_array_equal(out["lray"][b].cpu().numpy(), win.lrays)
+    np.testing.assert_array_equal(out["dfield"][b].cpu().numpy(), win.dfield)
+    np.testing.assert_array_equal(out["xray"][b].cpu().numpy(), win.xrays)
+    np.testing.assert_allclose(out["pdf"][b].cpu().numpy(), win.pdf, rtol=1e-15 * 4, atol=0)
+    if win.dddy is not None and "dddy" in out:
+        np.testing.assert_allclose(out["dddy"][b].cpu().numpy(), win.dddy, rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("case", ["small_q1", "small_q2", "small_theta", "small_fpgrid", "cmt_window"])
+def test_fingerprint_vs_golden(B, golden, case):
+    g = golden(case)
+    q, fpgrid, theta, tant, lam, _ = _case(g)
+    grid = _grid(g)
+    out = B.fingerprint_batch(g["tp"], g["wp"], grid, grid[4], grid[5], lam, q=q, tantheta=tant,
+                              fpgrids=fpgrid, deriv=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out["pn"][0].cpu().numpy(), g["pn"])
+    np.testing.assert_array_equal(out["iray"][0].cpu().numpy(), g["irays"])
+    np.testing.assert_array_equal(out["lray"][0].cpu().numpy(), g["lrays"])
+    np.testing.assert_array_equal(out["dfield"][0].cpu().numpy(), g["dfield"])
+    np.testing.assert_array_equal(out["xray"][0].cpu().numpy(), g["xrays"])
+    np.testing.assert_allclose(out["pdf"][0].cpu().numpy(), g["pdf"], rtol=4e-15)
+    np.testing.assert_allclose(out["dddy"][0].cpu().numpy(), g["dddy"], rtol=1e-9, atol=1e-13)
+
+
+def test_fingerprint_ricker_cfg1_golden(B, golden):
+    g = golden("ricker_cfg1")
+    grid = _grid(g)
+    out = B.fingerprint_batch(g["tp"], g["wp"], grid, 80, 512, 0.03, deriv=True)
+    torch.cuda.synchronize()
+    k = np.arange(0, 80 * 512, int(g["sub"]))
+    np.testing.assert_array_equal(out["iray"][0].cpu().numpy(), g["irays_all"].astype(np.int32))
+    np.testing.assert_array_equal(out["dfield"][0].cpu().numpy().reshape(-1)[k], g["dfield_sub"])
+    np.testing.assert_array_equal(out["lray"][0].cpu().numpy()[k], g["lrays_sub"])
+    np.testing.assert_allclose(out["pdf"][0].cpu().numpy().reshape(-1)[k], g["pdf_sub"], rtol=4e-15)
+    np.testing.assert_allclose(out["dddy"][0].cpu().numpy()[k], g["dddy_sub"], rtol=1e-9, atol=1e-13)
+    # notebook known answers (Ricker_waveform_derivatives.ipynb cells 23-24)
+    d = out["dfield"][0].cpu().numpy()
+    np.testing.assert_allclose(d[0, :3], [0.17128621, 0.16994805, 0.16862197], atol=5e-9)
+    assert abs(float(out["pdf"][0].sum()) - float(g["sum_pdf"])) < 1e-9 * float(g["sum_pdf"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fingerprint_random_batch_vs_oracle(B, dtype):
+    """Ragged-ish random batch: per-window grids, non-uniform time axes, float32 and float64 input."""
+    rng = np.random.default_rng(3)
+    nb, nt, nug, ntg = 6, 150, 37, 53          # odd sizes: exercises the tile / pair padding
+    t = np.sort(rng.random((nb, nt)), axis=1).astype(dtype) * 10.0
+    w = (rng.standard_normal((nb, nt)).cumsum(axis=1) * 0.2).astype(dtype)
+    grids = [(float(t[b, 0]) - 0.1 * b, float(t[b, -1]) + 0.3, float(w[b].min()) - 0.4, float(w[b].max()) + 0.2, nug, ntg)
+             for b in range(nb)]
+    out = B.fingerprint_batch(t, w, grids, nug, ntg, 0.04, deriv=True)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        win = _oracle_window(t[b].astype(np.float64), w[b].astype(np.float64), grids[b], 0.04)
+        _check_fields(out, win, b)
+
+
+def test_fingerprint_symmetric_ties(B):
+    """Exact far-apart ties (mirror-symmetric waveform, pixel column on the symmetry axis) and
+    vertex ties on every column (Nt == nt): first-minimum rule must hold bit-exactly."""
+    nt = 65
+    t = np.linspace(0.0, 1.0, nt)
+    w = np.abs(np.sin(6 * np.pi * t)) * np.cos(2 * np.pi * t) ** 2
+    w = 0.5 * (w + w[::-1])
+    grid = (0.0, 1.0, -0.5, 1.5, 41, 65)
+    out = B.fingerprint_batch(t, w, grid, 41, 65, 0.04, deriv=False)
+    torch.cuda.synchronize()
+    win = _oracle_window(t, w, grid, 0.04, deriv=False)
+    _check_fields(out, win)
+    assert int(out["status"].read()[4]) > 0      # some pixels went through the full FP64 rescan
+
+
+def test_marginals_and_ot1d_vs_oracle(B, golden):
+    g = golden("small_q1")
+    pdf = g["pdf"]
+    m = B.marginals_batch(pdf)
+    P = O.set_marginals(O.otpdf(pdf, np.zeros(pdf.shape + (2,))))
+    assert float(m["amp"][0]) == pytest.approx(P.amp, rel=1e-15)
+    np.testing.assert_allclose(m["marg_t"][0].cpu().numpy(), P.pdf.sum(axis=0), rtol=1e-14)
+    np.testing.assert_allclose(m["marg_u"][0].cpu().numpy(), P.pdf.sum(axis=1), rtol=1e-14)
+
+
+def test_ot1d_pointmass_golden(B, golden):
+    g = golden("pointmass")
+    r = B.ot1d_batch(g["f"], g["g"], g["fx"], g["gx"], "W12", derivatives=True, want_cdf=True)
+    torch.cuda.synchronize()
+    W = r["W"][0].cpu().numpy()
+    assert W[0] == pytest.approx(4.11, abs=1e-12) and W[1] == pytest.approx(18.09, abs=1e-12)
+    np.testing.assert_allclose(r["dW1"][0].cpu().numpy(), g["dW1"], atol=1e-12)
+    np.testing.assert_allclose(r["dW2"][0].cpu().numpy(), g["dW2"], atol=1e-11)
+    np.testing.assert_allclose(r["dpos"][0].cpu().numpy(), [g["dW1pos"], g["dW2pos"]], atol=1e-12)
+    np.testing.assert_allclose(r["cdf_f"][0].cpu().numpy(), g["cdf_f"], rtol=1e-15)
+
+
+def test_ot1d_random_batch_vs_oracle(B):
+    rng = np.random.default_rng(0)
+    nb, n = 40, 128
+    f = rng.random((nb, n), dtype=np.float32) + 1e-3
+    gq = rng.random((nb, n), dtype=np.float32) + 1e-3
+    x = np.linspace(0, 1, n)
+    r = B.ot1d_batch(f, gq, x, x, "W12", derivatives=True, want_cdf=True, want_merge=True)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        s, t = O.otpdf(f[b].astype(np.float64), x), O.otpdf(gq[b].astype(np.float64), x)
+        out, (tkarg, indf, indg) = O.wasser(s, t, "W12", derivatives=True, ignoreCommonCDFerror=True,
+                                            return_merge=True)
+        np.testing.assert_allclose(r["cdf_f"][b].cpu().numpy(), s.cdf, rtol=1e-14)
+        np.testing.assert_array_equal(r["merge_order"][b].cpu().numpy(), tkarg)   # CDF-merge order, exact
+        np.testing.assert_allclose(r["W"][b].cpu().numpy(), [out[0], out[3]], rtol=1e-11)
+        np.testing.assert_allclose(r["dW1"][b].cpu().numpy(), out[1], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(r["dW2"][b].cpu().numpy(), out[4], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(r["dpos"][b].cpu().numpy(), [out[2], out[5]], rtol=1e-10, atol=1e-13)
+
+
+def test_ot1d_unequal_lengths_and_common_cdf(B, golden):
+    g = golden("ot1d_random")
+    r = B.ot1d_batch(g["f2"], g["g2"], g["x2f"], g["x2g"], "W12")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(r["W"][0].cpu().numpy(), [g["W1_2"], g["W2_2"]], rtol=1e-12)
+    same = np.ones(8)
+    x = np.linspace(0, 1, 8)
+    r = B.ot1d_batch(same, same, x, x, "W2", derivatives=True)
+    assert int(r["status"].read()[1]) == 7          # cf[:-1] == cg[:-1]: TargetSourceCDFError condition
+    r = B.ot1d_batch(np.array([0.2, -0.1, 0.5]), np.ones(3), x[:3], x[:3], "W1")
+    assert int(r["status"].read()[0]) >= 1          # PDFSignError condition
+
+
+@pytest.mark.parametrize("case", ["small_q1", "small_q2", "cmt_window"])
+def test_pdfderiv_vs_golden(B, golden, case):
+    g = golden(case)
+    q, fpgrid, theta, tant, lam, _ = _case(g)
+    chain = np.stack([g["dWt"].reshape(-1), g["dWu"].reshape(-1)])[None]
+    out = B.pdfderiv_batch(g["pdf"][None], g["dfield"][None], torch.from_numpy(g["irays"][None]),
+                           g["dddy"][None], chain, len(g["tp"]), lam, q=q)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out[0, 0].cpu().numpy(), g["pdfdMarg0"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(out[0, 1].cpu().numpy(), g["pdfdMarg1"], rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("case", ["small_q1", "small_q2", "small_theta", "small_fpgrid", "cmt_window",
+                                  "ricker_cfg1", "ricker_cfg1_w1"])
+def test_fused_misfit_grad_vs_golden(B, golden, case):
+    g = golden(case)
+    q, fpgrid, theta, tant, lam, distfunc = _case(g)
+    grid = _grid(g)
+    tg = B.Target.from_waveform(g["to"], g["wo"], grid, grid[4], grid[5], lam, q=q, tantheta=tant, fpgrids=fpgrid)
+    np.testing.assert_allclose(tg.cdf_t[0].cpu().numpy(), g["tgt_cdf_t"], rtol=1e-13)
+    np.testing.assert_allclose(tg.cdf_u[0].cpu().numpy(), g["tgt_cdf_u"], rtol=1e-13)
+    np.testing.assert_array_equal(tg.x_t[0].cpu().numpy(), g["tgt_x_t"])
+    r = B.misfit_grad_batch(g["tp"], g["wp"], grid, grid[4], grid[5], lam, tg, distfunc=distfunc, q=q,
+                            tantheta=tant, fpgrids=fpgrid)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(r["W"][0].cpu().numpy(), g["W"], rtol=1e-10)
+    np.testing.assert_allclose(r["dwg"][0].cpu().numpy(), g["dwg"][0], rtol=1e-10, atol=1e-14)
+    scale = np.abs(g["pdfdMarg0"]).max()
+    np.testing.assert_allclose(r["grad"][0, 0].cpu().numpy(), g["pdfdMarg0"], rtol=1e-8, atol=1e-10 * scale)
+    scale = np.abs(g["pdfdMarg1"]).max()
+    np.testing.assert_allclose(r["grad"][0, 1].cpu().numpy(), g["pdfdMarg1"], rtol=1e-8, atol=1e-10 * scale)
+
+
+def test_fused_batch_vs_oracle_and_unfused(B):
+    """Batch of random-walk windows (cfg5 rule at reduced size) against the oracle, and the fused
+    kernel against the composition of the materialising kernels."""
+    nb, nt, nug, ntg, lam = 5, 200, 48, 64, 0.04
+    w = O.random_walk_windows(nb + 1, nt, seed=5).astype(np.float64)
+    t = np.linspace(0, 1, nt)
+    grid = (0.0, 1.0, -1.3, 1.3, nug, ntg)
+    tg = B.Target.from_waveform(t, w[0], grid, nug, ntg, lam)
+    r = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg, distfunc="W2")
+    torch.cuda.synchronize()
+    wino, tgt = O.build_ot_from_waveform(t, w[0], grid, lambdav=lam)
+    for b in range(nb):
+        Wd, dr, dg, win, src = O.misfit_grad_window(t, w[1 + b], grid, tgt, lambdav=lam, distfunc="W2")
+        np.testing.assert_allclose(r["W"][b].cpu().numpy(), Wd, rtol=1e-10)
+        np.testing.assert_allclose(r["dwg"][b].item() / (1.0 * (grid[1] - grid[0])), dg[0], rtol=1e-10)
+        for i in range(2):
+            np.testing.assert_allclose(r["grad"][b, i].cpu().numpy(), dr[i], rtol=1e-8,
+                                       atol=1e-10 * np.abs(dr[i]).max())
+
+
+def test_fused_transform_vs_oracle(B):
+    """In-kernel arctan amplitude transform (libs/ricker_util.py:241-244, 393-397)."""
+    nt, nug, ntg, lam = 61, 79, 61, 0.04
+    rng = np.random.default_rng(4)
+    t = np.arange(float(nt))
+    wo = np.exp(-0.5 * ((t - 25) / 4.0) ** 2) * np.sin(0.5 * (t - 25)) * 1e-3
+    wp = np.roll(wo, 2) * 1.1 + 2e-5 * rng.standard_normal(nt)
+    du = wo.max() - wo.min()
+    grid = (0.0, 60.0, wo.min() - 0.3 * du, wo.max() + 0.3 * du, nug, ntg)
+    uo = O.arctan_trans(wo, grid[2], grid[3])
+    tg = B.Target.from_waveform(t, uo, (0.0, 60.0, 0.0, 1.0, nug, ntg), nug, ntg, lam)
+    r = B.misfit_grad_batch(t, wp, grid, nug, ntg, lam, tg, distfunc="W2", transform=True)
+    torch.cuda.synchronize()
+    _, tgt = O.build_ot_from_waveform(t, wo, grid, lambdav=lam, transform=True)
+    Wd, dr, dg, _, _ = O.misfit_grad_window(t, wp, grid, tgt, lambdav=lam, transform=True, adapter="cmt")
+    np.testing.assert_allclose(r["W"][0].cpu().numpy(), Wd, rtol=1e-7)
+    for i in range(2):
+        np.testing.assert_allclose(r["grad"][0, i].cpu().numpy(), dr[i], rtol=1e-5, atol=1e-7 * np.abs(dr[i]).max())
+
+
+def test_chain_batch(B):
+    rng = np.random.default_rng(2)
+    J = rng.standard_normal((7, 9, 1830))
+    dr = rng.standard_normal((7, 1830))
+    out = B.chain_batch(J, dr).cpu().numpy()
+    np.testing.assert_allclose(out, np.einsum("mpl,ml->mp", J, dr), rtol=1e-12, atol=1e-12)
+    out = B.chain_batch(J[0], dr).cpu().numpy()
+    np.testing.assert_allclose(out, dr @ J[0].T, rtol=1e-12, atol=1e-12)
+
+
+def test_full_size_cfg5_properties(B):
+    """BASELINE cfg5 shape (nt=1024 -> 256x256): one window against the chunked oracle, plus
+    size-independent properties on a batch: fused == unfused composition, translation of the time
+    axis leaves W^u unchanged and shifts dW^t/dx0 consistently, batch order independence."""
+    nt, nug, ntg, lam = 1024, 256, 256, 0.04
+    w = O.random_walk_windows(9, nt, seed=5)           # float32 inputs as in cfg5
+    t = np.linspace(0, 1, nt).astype(np.float32)
+    grid = (0.0, 1.0, -1.3, 1.3, nug, ntg)
+    tg = B.Target.from_waveform(t, w[0], grid, nug, ntg, lam)
+    r = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg, distfunc="W2")
+    torch.cuda.synchronize()
+    # (a) oracle on one full-size window (about 10 s of CPU)
+    t64, w64 = t.astype(np.float64), w.astype(np.float64)
+    _, tgt = O.build_ot_from_waveform(t64, w64[0], grid, lambdav=lam, chunk=2048)
+    Wd, dr, dg, win, _ = O.misfit_grad_window(t64, w64[1], grid, tgt, lambdav=lam, chunk=2048)
+    np.testing.assert_allclose(r["W"][0].cpu().numpy(), Wd, rtol=1e-10)
+    for i in range(2):
+        np.testing.assert_allclose(r["grad"][0, i].cpu().numpy(), dr[i], rtol=1e-7, atol=1e-10 * np.abs(dr[i]).max())
+    fp = B.fingerprint_batch(t, w[1:2], grid, nug, ntg, lam, fields=("iray", "dfield"))
+    np.testing.assert_array_equal(fp["iray"][0].cpu().numpy().astype(np.int64), win.irays)
+    np.testing.assert_array_equal(fp["dfield"][0].cpu().numpy(), win.dfield)
+    # (b) batch order independence (bit-exact: every reduction has a fixed order except the
+    #     shared-memory gradient bins, which are FP64 atomics)
+    perm = np.array([3, 0, 7, 1, 6, 2, 5, 4])
+    r2 = B.misfit_grad_batch(t, w[1:][perm], grid, nug, ntg, lam, tg, distfunc="W2")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(r2["W"].cpu().numpy(), r["W"].cpu().numpy()[perm])
+    np.testing.assert_allclose(r2["grad"].cpu().numpy(), r["grad"].cpu().numpy()[perm], rtol=1e-12, atol=1e-18)
+    # (c) gradient vs finite difference of the fused misfit itself (oracle-independent)
+    b, j, h = 2, 500, 1e-4
+    wp = w64[1 + b].copy(); wm = wp.copy()
+    wp[j] += h; wm[j] -= h
+    rp = B.misfit_grad_batch(t64, np.stack([wp, wm]), grid, nug, ntg, lam, tg, distfunc="W2", want_grad=False)
+    fd = (rp["W"][0] - rp["W"][1]).cpu().numpy() / (2 * h)
+    an = r["grad"][b, :, j].cpu().numpy()
+    np.testing.assert_allclose(an, fd, rtol=2e-2, atol=2e-3 * np.abs(r["grad"][b].cpu().numpy()).max())

@@ -1,0 +1,285 @@
+"""Batched drivers over the C ABI (include/wfot.h).
+
+These are the entry points the reference's per-window Python loops map onto
+(libs/loc_cmt_util.py:256-271, 503-519 loop over stations x components;
+notebook sweeps loop over trial models).  torch is used only to own device
+memory and streams; every computation happens inside libwfot.so.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi as C
+
+GRID_DTYPE = np.dtype([("t0", "f8"), ("t1", "f8"), ("u0", "f8"), ("u1", "f8"),
+                       ("fp_t0", "f8"), ("fp_t1", "f8"), ("fp_u0", "f8"), ("fp_u1", "f8"),
+                       ("tantheta", "f8"), ("has_fpgrid", "i4"), ("reserved", "i4")])
+assert GRID_DTYPE.itemsize == ctypes.sizeof(C.wfot_grid)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("waveform_ot_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def pack_grids(grids, tantheta=1.0, fpgrids=None):
+    """grids: one (t0,t1,u0,u1,...) tuple or a sequence of them -> (n, 80-byte) device tensor."""
+    if np.isscalar(grids[0]):
+        grids = [grids]
+    n = len(grids)
+    tan = np.broadcast_to(np.asarray(tantheta, dtype=np.float64), (n,))
+    arr = np.zeros(n, dtype=GRID_DTYPE)
+    for i, g in enumerate(grids):
+        arr[i]["t0"], arr[i]["t1"], arr[i]["u0"], arr[i]["u1"] = g[0], g[1], g[2], g[3]
+        arr[i]["tantheta"] = tan[i]
+        fg = None if fpgrids is None else (fpgrids if np.isscalar(fpgrids[0]) else fpgrids[i])
+        if fg is not None:
+            arr[i]["fp_t0"], arr[i]["fp_t1"], arr[i]["fp_u0"], arr[i]["fp_u1"] = fg[0], fg[1], fg[2], fg[3]
+            arr[i]["has_fpgrid"] = 1
+    return torch.from_numpy(arr.view(np.uint8).reshape(n, GRID_DTYPE.itemsize).copy()).to(_device())
+
+
+def _as_device(x, dtype=None):
+    """numpy / torch (host or device) -> contiguous device tensor; float32/float64 kept."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        a = np.ascontiguousarray(x)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        t = torch.from_numpy(a)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(_device(), non_blocking=True).contiguous()
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return C.F32
+    if t.dtype == torch.float64:
+        return C.F64
+    raise TypeError("waveform arrays must be float32 or float64")
+
+
+class Status:
+    """Per-call data-dependent condition counters (WFOT_STAT_* slots)."""
+
+    def __init__(self):
+        self.t = torch.zeros(C.STAT_SLOTS, dtype=torch.int32, device=_device())
+
+    def read(self):
+        return self.t.cpu().numpy()
+
+
+def fingerprint_batch(t, w, grids, nug, ntg, lambdav, q=None, tantheta=1.0, fpgrids=None,
+                      deriv=False, fields=("dfield", "iray", "lray", "xray", "pdf", "pn"), status=None):
+    """waveformFP(...).calcpdf(...) for B windows.  t: (nt,) shared or (B, nt); w: (B, nt).
+    Returns dict of device tensors (FP64; iray int32)."""
+    dev = _device()
+    w = _as_device(w)
+    if w.dim() == 1:
+        w = w[None, :]
+    B, nt = w.shape
+    t = _as_device(t, w.dtype)
+    t_stride = 0 if t.dim() == 1 else nt
+    g = grids if isinstance(grids, torch.Tensor) else pack_grids(grids, tantheta, fpgrids)
+    npix = nug * ntg
+    out = {}
+    f64 = dict(dtype=torch.float64, device=dev)
+    want = set(fields) | ({"dddy"} if deriv else set())
+    if "pn" in want: out["pn"] = torch.empty((B, nt, 2), **f64)
+    if "dfield" in want: out["dfield"] = torch.empty((B, nug, ntg), **f64)
+    if "iray" in want: out["iray"] = torch.empty((B, npix), dtype=torch.int32, device=dev)
+    if "lray" in want: out["lray"] = torch.empty((B, npix), **f64)
+    if "xray" in want: out["xray"] = torch.empty((B, npix, 2), **f64)
+    if "pdf" in want: out["pdf"] = torch.empty((B, nug, ntg), **f64)
+    if "dddy" in want: out["dddy"] = torch.empty((B, npix, 2), **f64)
+    wsb = C.lib.wfot_fingerprint_workspace_bytes(B, nt, nug, ntg)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    st = status or Status()
+    C.check(C.lib.wfot_fingerprint_batch(
+        C.ptr(t), C.ptr(w), _dt(w), t_stride, nt, C.ptr(g), g.shape[0], B, nug, ntg,
+        float(lambdav), 0 if q is None else int(q),
+        C.ptr(out.get("pn")), C.ptr(out.get("dfield")), C.ptr(out.get("iray")), C.ptr(out.get("lray")),
+        C.ptr(out.get("xray")), C.ptr(out.get("pdf")), C.ptr(out.get("dddy")),
+        C.ptr(ws), wsb, C.ptr(st.t), _stream()), "wfot_fingerprint_batch")
+    out["status"] = st
+    out["_keepalive"] = (t, w, g, ws)
+    return out
+
+
+def marginals_batch(pdf, status=None):
+    """OTpdf (2-D) + setMarginals for B densities (B, nug, ntg) -> amp, marg_t, marg_u."""
+    dev = _device()
+    pdf = _as_device(pdf, torch.float64)
+    if pdf.dim() == 2:
+        pdf = pdf[None]
+    B, nug, ntg = pdf.shape
+    amp = torch.empty(B, dtype=torch.float64, device=dev)
+    mt = torch.empty((B, ntg), dtype=torch.float64, device=dev)
+    mu = torch.empty((B, nug), dtype=torch.float64, device=dev)
+    st = status or Status()
+    C.check(C.lib.wfot_marginals_batch(C.ptr(pdf), B, nug, ntg, C.ptr(amp), C.ptr(mt), C.ptr(mu),
+                                       C.ptr(st.t), _stream()), "wfot_marginals_batch")
+    return dict(amp=amp, marg_t=mt, marg_u=mu, status=st)
+
+
+def ot1d_batch(f, g, xf, xg, distfunc="W12", derivatives=False, want_cdf=False, want_merge=False,
+               status=None):
+    """OTpdf (1-D) + wasser for B pairs.  f (B,n) or (n,); g (B,m) or (m,) shared; x likewise."""
+    dev = _device()
+    f = _as_device(f)
+    g = _as_device(g, f.dtype)
+    if f.dim() == 1:
+        f = f[None]
+    B, n = f.shape
+    m = g.shape[-1]
+    xf = _as_device(xf, torch.float64)
+    xg = _as_device(xg, torch.float64)
+    pmask = {"W1": C.W1, "W2": C.W2, "W12": C.W12}[distfunc]
+    f64 = dict(dtype=torch.float64, device=dev)
+    W = torch.zeros((B, 2), **f64)
+    dpos = torch.zeros((B, 2), **f64) if derivatives else None
+    dW1 = torch.empty((B, n), **f64) if derivatives and pmask & 1 else None
+    dW2 = torch.empty((B, n), **f64) if derivatives and pmask & 2 else None
+    amp = torch.empty(B, **f64)
+    cdf_f = torch.empty((B, n), **f64) if want_cdf else None
+    cdf_g = torch.empty((B, m), **f64) if want_cdf else None
+    merge = torch.empty((B, n + m - 1), dtype=torch.int32, device=dev) if want_merge else None
+    st = status or Status()
+    C.check(C.lib.wfot_ot1d_batch(
+        C.ptr(f), C.ptr(g), _dt(f), C.ptr(xf), C.ptr(xg),
+        n, 0 if g.dim() == 1 else m, 0 if xf.dim() == 1 else n, 0 if xg.dim() == 1 else m,
+        n, m, B, pmask, int(bool(derivatives)),
+        C.ptr(W), C.ptr(dW1), C.ptr(dW2), C.ptr(dpos), C.ptr(amp), C.ptr(cdf_f), C.ptr(cdf_g),
+        C.ptr(merge), C.ptr(st.t), _stream()), "wfot_ot1d_batch")
+    return dict(W=W, dW1=dW1, dW2=dW2, dpos=dpos, amp=amp, cdf_f=cdf_f, cdf_g=cdf_g, merge_order=merge,
+                status=st, _keepalive=(f, g, xf, xg))
+
+
+def pdfderiv_batch(pdf, dfield, iray, dddy, chain, nt, lambdav, q=None):
+    """PDFderiv / PDFderivMarg for B windows.  chain: None, (B,npix) or (B,nchain,npix)."""
+    dev = _device()
+    pdf = _as_device(pdf, torch.float64)
+    B = pdf.shape[0]
+    npix = pdf[0].numel()
+    dfield = _as_device(dfield, torch.float64) if dfield is not None else None
+    iray = iray.to(dev).to(torch.int32).contiguous()
+    dddy = _as_device(dddy, torch.float64)
+    nchain = 1
+    if chain is not None:
+        chain = _as_device(chain, torch.float64).reshape(B, -1, npix)
+        nchain = chain.shape[1]
+    out = torch.empty((B, nchain, nt), dtype=torch.float64, device=dev)
+    C.check(C.lib.wfot_pdfderiv_batch(C.ptr(pdf), C.ptr(dfield), C.ptr(iray), C.ptr(dddy), C.ptr(chain),
+                                      nchain, B, npix, nt, float(lambdav), 0 if q is None else int(q),
+                                      C.ptr(out), _stream()), "wfot_pdfderiv_batch")
+    return out
+
+
+class Target:
+    """Observed-window marginals in the form the fused kernel consumes: CDF + bin
+    positions of the time and amplitude marginals (what `wfobs_target.marg[i].cdf/.x`
+    hold in the reference, libs/OTlib.py:112-114,157-160)."""
+
+    def __init__(self, cdf_t, x_t, cdf_u, x_u):
+        self.cdf_t, self.x_t, self.cdf_u, self.x_u = cdf_t, x_t, cdf_u, x_u
+        self.per_window = cdf_t.dim() == 2 and cdf_t.shape[0] > 1
+
+    @staticmethod
+    def from_waveform(t, w, grids, nug, ntg, lambdav, q=None, tantheta=1.0, fpgrids=None):
+        """Fingerprint the observed window(s) and keep their marginal CDFs."""
+        fp = fingerprint_batch(t, w, grids, nug, ntg, lambdav, q=q, tantheta=tantheta, fpgrids=fpgrids,
+                               fields=("pdf", "pn"))
+        mg = marginals_batch(fp["pdf"])
+        Bt = mg["marg_t"].shape[0]
+        dev = _device()
+        # bin positions = pixel axes (libs/OTlib.py:157-158 on wf.pos)
+        pn = fp["pn"]
+        g = grids if isinstance(grids, torch.Tensor) else pack_grids(grids, tantheta, fpgrids)
+        x_t, x_u = pixel_axes(pn, g, nug, ntg)
+        ones = torch.ones(1, dtype=torch.float64, device=dev)
+        ct = ot1d_batch(mg["marg_t"], ones.expand(2).contiguous(), x_t, torch.zeros(2, dtype=torch.float64, device=dev),
+                        distfunc="W1", want_cdf=True)["cdf_f"]
+        cu = ot1d_batch(mg["marg_u"], ones.expand(2).contiguous(), x_u, torch.zeros(2, dtype=torch.float64, device=dev),
+                        distfunc="W1", want_cdf=True)["cdf_f"]
+        tg = Target(ct, x_t, cu, x_u)
+        tg.per_window = Bt > 1
+        return tg
+
+
+def pixel_axes(pn, grids_dev, nug, ntg):
+    """FP64 pixel axes exactly as np.linspace builds them (libs/FingerprintLib.py:254):
+    i*step + start, last element = stop.  pn: (B, nt, 2) device tensor."""
+    B = pn.shape[0]
+    gr = grids_dev.cpu().numpy().view(GRID_DTYPE).reshape(-1)
+    pnh = pn[:, [0, -1], 0].cpu().numpy()
+    xt = np.empty((B, ntg))
+    xu = np.empty((B, nug))
+    for b in range(B):
+        g = gr[0 if len(gr) == 1 else b]
+        if g["has_fpgrid"]:
+            delt = g["tantheta"] * (g["t1"] - g["t0"])
+            a0, a1 = (g["fp_t0"] - g["t0"]) / delt, (g["fp_t1"] - g["t0"]) / delt
+            du = g["u1"] - g["u0"]
+            c0, c1 = (g["fp_u0"] - g["u0"]) / du, (g["fp_u1"] - g["u0"]) / du
+        else:
+            a0, a1, c0, c1 = pnh[b, 0], pnh[b, 1], 0.0, 1.0
+        xt[b] = np.linspace(a0, a1, ntg)
+        xu[b] = np.linspace(c0, c1, nug)
+    return torch.from_numpy(xt).to(pn.device), torch.from_numpy(xu).to(pn.device)
+
+
+def misfit_grad_batch(t, w, grids, nug, ntg, lambdav, target: Target, distfunc="W2", q=None,
+                      tantheta=1.0, fpgrids=None, transform=False, want_grad=True, status=None,
+                      workspace=None):
+    """Fused evaluation of B windows: returns W (B,2) [W^t, W^u], grad (B,2,nt), dwg (B,)
+    (dW^t/d(translation) in normalised time units).  Inputs may already be device tensors."""
+    dev = _device()
+    w = _as_device(w)
+    if w.dim() == 1:
+        w = w[None, :]
+    B, nt = w.shape
+    t = _as_device(t, w.dtype)
+    t_stride = 0 if t.dim() == 1 else nt
+    g = grids if isinstance(grids, torch.Tensor) else pack_grids(grids, tantheta, fpgrids)
+    pmask = {"W1": C.W1, "W2": C.W2}[distfunc]
+    f64 = dict(dtype=torch.float64, device=dev)
+    W = torch.empty((B, 2), **f64)
+    grad = torch.empty((B, 2, nt), **f64) if want_grad else None
+    dwg = torch.empty(B, **f64)
+    wsb = C.lib.wfot_misfit_grad_workspace_bytes(B, nt, nug, ntg)
+    ws = workspace if workspace is not None and workspace.numel() >= wsb else \
+        torch.empty(wsb, dtype=torch.uint8, device=dev)
+    st = status or Status()
+    C.check(C.lib.wfot_misfit_grad_batch(
+        C.ptr(t), C.ptr(w), _dt(w), t_stride, nt, C.ptr(g), g.shape[0], B, nug, ntg,
+        float(lambdav), 0 if q is None else int(q), pmask, int(bool(transform)),
+        C.ptr(target.cdf_t), C.ptr(target.x_t), C.ptr(target.cdf_u), C.ptr(target.x_u),
+        int(target.per_window), C.ptr(W), C.ptr(grad), C.ptr(dwg), C.ptr(ws), ws.numel(),
+        C.ptr(st.t), _stream()), "wfot_misfit_grad_batch")
+    return dict(W=W, grad=grad, dwg=dwg, status=st, _keepalive=(t, w, g, ws))
+
+
+def chain_batch(J, dr):
+    """g_m = J_m . dr_m  (libs/ricker_util.py:399-400, libs/loc_cmt_util.py:283-296).
+    J (M,P,L) or (P,L) shared; dr (M,L)."""
+    dev = _device()
+    J = _as_device(J, torch.float64)
+    dr = _as_device(dr, torch.float64)
+    if dr.dim() == 1:
+        dr = dr[None]
+    M, L = dr.shape
+    P = J.shape[-2]
+    out = torch.empty((M, P), dtype=torch.float64, device=dev)
+    C.check(C.lib.wfot_chain_batch(C.ptr(J), C.ptr(dr), P, L, M, 0 if J.dim() == 2 else P * L,
+                                   C.ptr(out), _stream()), "wfot_chain_batch")
+    return out

@@ -1,0 +1,395 @@
+// wfot_device.cuh -- device-side building blocks shared by the materialising
+// fingerprint kernel and the fused misfit+gradient kernel (sm_100a).
+//
+// Layout of the work:
+//   * prep_window(): FP64 non-dimensionalisation in the reference's operation
+//     order (libs/FingerprintLib.py:90-113) -> pn64; then an FP32 "rotated
+//     frame" segment table in window-local, power-of-two-scaled coordinates.
+//   * scan_block<R>(): the hot loop.  A thread owns 2 pixel columns x R rows and
+//     walks every segment; per (pixel, segment) pair it spends 5 FP32 lane
+//     operations (4 of them issued as packed FFMA2/FMUL2) and half an FMNMX3:
+//         along = (p - mid).e      perp = (p - mid).n
+//         D     = perp^2 + sat(|along| - h)^2          (h = half segment length)
+//     which is the clamped point-to-segment distance of
+//     libs/FingerprintLib.py:256-259 written in the segment's own frame.
+//     Only the running minimum per tile of kTile segments is kept.
+//   * resolve_pixel(): re-walks the winning tile, and evaluates every segment
+//     whose FP32 distance is within the rounding tolerance of the minimum in
+//     FP64 with exactly the reference's sequence of elementary operations, so
+//     the selected index is np.argmin's (first minimum) on the FP64 field.
+//     A pixel whose second-best *tile* is also within tolerance is resolved by
+//     a full-segment cooperative rescan (resolve_pixel_warp).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/wfot.h"
+
+namespace wfot {
+
+constexpr int kTile = 32;          // segments per argmin tile
+constexpr float kBig = 3.0e38f;    // "no distance yet"
+constexpr float kPadD = 5.0f;      // squared distance produced by padding segments (> any real one)
+
+// ------------------------------------------------------------------ packed FP32
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// ------------------------------------------------------------------ per-window header
+struct WinHdr {
+    double T0, Tstep, Tlast;   // pixel time axis:      np.linspace(tlimnfp[0], tlimnfp[1], ntg)
+    double U0, Ustep, Ulast;   // pixel amplitude axis: np.linspace(ulimnfp[0], ulimnfp[1], nug)
+    double ccx, ccy;           // origin of the window-local FP32 frame (normalised units)
+    double sigma;              // power-of-two scale of the FP32 frame
+    double du;                 // u1 - u0 (raw amplitude box)
+    double u0raw, u1raw;       // raw amplitude box before an arctan transform
+    int degenerate;            // number of zero-length segments
+    int pad;
+};
+
+// FP32 segment table in the rotated frame (shared or global memory)
+struct SegTable {
+    const float4* A;   // {ex, ex, ey, ey}
+    const float4* B;   // {-am, -am, -bm, -bm}   am = mid.e, bm = mid x e (scaled)
+    const float* H;    // half length (scaled)
+    int S;             // real segments
+    int Spad;          // padded to a multiple of kTile
+};
+
+__device__ __forceinline__ double lin_axis(double a0, double step, double alast, int i, int n) {
+    // numpy.linspace: y = arange(n)*step + start ; y[-1] = stop
+    if (i == n - 1 && n > 1) return alast;
+    return __dadd_rn(__dmul_rn((double)i, step), a0);
+}
+
+// ------------------------------------------------------------------ FP32 pair kernel (scalar form)
+__device__ __forceinline__ float eval32(const SegTable& tb, int s, float px, float py) {
+    const float4 a = tb.A[s];
+    const float4 b = tb.B[s];
+    const float h = tb.H[s];
+    const float P = __fmaf_rn(px, a.x, b.x);
+    const float Q = __fmaf_rn(px, a.z, b.z);
+    const float al = __fmaf_rn(py, a.z, P);
+    const float pe = __fmaf_rn(-py, a.x, Q);
+    const float tm = __saturatef(__fadd_rn(fabsf(al), -h));
+    return __fmaf_rn(tm, tm, __fmul_rn(pe, pe));
+}
+
+// rounding tolerance of the FP32 squared distance (scaled frame, |coords| <= 0.5, D < 1);
+// derivation in DESIGN.md section 3.3
+__device__ __forceinline__ float tau32(float d2) {
+    return 2.5e-6f * sqrtf(d2) + 3.0e-7f * d2 + 1.0e-12f;
+}
+
+// ------------------------------------------------------------------ FP64 reference-order evaluation
+// libs/FingerprintLib.py:256-259 for one (pixel, segment): the same elementary
+// operations in the same order, no FMA contraction.
+__device__ __forceinline__ void eval64(const double2* __restrict__ pn, int s, double px, double py,
+                                       double& D, double& lam) {
+    const double2 a = pn[s];
+    const double2 b = pn[s + 1];
+    const double cx = __dsub_rn(b.x, a.x);                     // delta_n (:112)
+    const double cy = __dsub_rn(b.y, a.y);
+    const double L = __dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy));   // lsq_n (:113)
+    const double bx = __dsub_rn(px, a.x);                      // b = p - x0 (:256)
+    const double by = __dsub_rn(py, a.y);
+    double l = __ddiv_rn(__dadd_rn(__dmul_rn(bx, cx), __dmul_rn(by, cy)), L);   // (:257)
+    l = fmin(fmax(l, 0.0), 1.0);                               // np.clip
+    const double dx = __dsub_rn(bx, __dmul_rn(cx, l));         // ds = b - c*lam (:258)
+    const double dy = __dsub_rn(by, __dmul_rn(cy, l));
+    D = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));       // (:259)
+    lam = l;
+}
+
+struct PixelHit {
+    double D;     // FP64 squared distance of the selected segment
+    double lam;   // clipped segment parameter
+    int s;        // selected segment (np.argmin first-minimum)
+};
+
+// Walk tile t1 (+1 segment either side: vertex ties straddle tile boundaries).
+__device__ __forceinline__ void resolve_pixel(const SegTable& tb, const double2* __restrict__ pn,
+                                              float pxl, float pyl, double px, double py,
+                                              float b1, int t1, PixelHit& hit) {
+    const float thr = b1 + tau32(b1);
+    const int lo = max(t1 * kTile - 1, 0);
+    const int hi = min(t1 * kTile + kTile, tb.S - 1);
+    hit.D = CUDART_INF;
+    hit.lam = 0.0;
+    hit.s = lo;
+    for (int s = lo; s <= hi; ++s) {
+        const float d32 = eval32(tb, s, pxl, pyl);
+        if (d32 <= thr) {
+            double D, l;
+            eval64(pn, s, px, py, D, l);
+            if (D < hit.D) { hit.D = D; hit.lam = l; hit.s = s; }
+        }
+    }
+}
+
+// Full rescan of every segment by one thread (queue-overflow fallback).
+static __device__ __noinline__ void resolve_pixel_full(const SegTable& tb, const double2* __restrict__ pn,
+                                                float pxl, float pyl, double px, double py,
+                                                float b1, PixelHit& hit) {
+    const float thr = b1 + tau32(b1);
+    hit.D = CUDART_INF; hit.lam = 0.0; hit.s = 0;
+    for (int s = 0; s < tb.S; ++s) {
+        const float d32 = eval32(tb, s, pxl, pyl);
+        if (d32 <= thr) {
+            double D, l;
+            eval64(pn, s, px, py, D, l);
+            if (D < hit.D) { hit.D = D; hit.lam = l; hit.s = s; }
+        }
+    }
+}
+
+// Full rescan by a whole warp (lanes stride over segments); result valid in every lane.
+__device__ __forceinline__ void resolve_pixel_warp(const SegTable& tb, const double2* __restrict__ pn,
+                                                   float pxl, float pyl, double px, double py,
+                                                   float b1, PixelHit& hit) {
+    const int lane = threadIdx.x & 31;
+    const float thr = b1 + tau32(b1);
+    double bD = CUDART_INF, bl = 0.0;
+    int bs = 0x7fffffff;
+    for (int s = lane; s < tb.S; s += 32) {
+        const float d32 = eval32(tb, s, pxl, pyl);
+        if (d32 <= thr) {
+            double D, l;
+            eval64(pn, s, px, py, D, l);
+            if (D < bD) { bD = D; bl = l; bs = s; }   // ascending s per lane: first minimum
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double oD = __shfl_xor_sync(0xffffffffu, bD, off);
+        const double ol = __shfl_xor_sync(0xffffffffu, bl, off);
+        const int os = __shfl_xor_sync(0xffffffffu, bs, off);
+        if (oD < bD || (oD == bD && os < bs)) { bD = oD; bl = ol; bs = os; }
+    }
+    hit.D = bD; hit.lam = bl; hit.s = (bs == 0x7fffffff) ? 0 : bs;
+}
+
+// ------------------------------------------------------------------ the hot loop
+// Thread-owned pixel block: columns (px0, px1) x rows py[0..R).  Slot k = 2*r + c.
+// On return b1[k] = min_s D, t1[k] = tile holding it, b2[k] = second-smallest tile minimum.
+template <int R>
+__device__ __forceinline__ void scan_block(const SegTable& tb, float px0, float px1,
+                                           const float (&py)[R],
+                                           float (&b1)[2 * R], int (&t1)[2 * R], float (&b2)[2 * R]) {
+    const uint64_t px2 = pack2(px0, px1);
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) { b1[k] = kBig; b2[k] = kBig; t1[k] = 0; }
+    const int ntiles = tb.Spad / kTile;
+    for (int tile = 0; tile < ntiles; ++tile) {
+        float tm[2 * R];
+#pragma unroll
+        for (int k = 0; k < 2 * R; ++k) tm[k] = kBig;
+        const float4* __restrict__ A = tb.A + tile * kTile;
+        const float4* __restrict__ B = tb.B + tile * kTile;
+        const float* __restrict__ H = tb.H + tile * kTile;
+#pragma unroll 2
+        for (int j = 0; j < kTile; j += 2) {
+            const float4 a0 = A[j], c0 = B[j];
+            const float4 a1 = A[j + 1], c1 = B[j + 1];
+            const float h0 = H[j], h1 = H[j + 1];
+            const uint64_t ex0 = pack2(a0.x, a0.y), ey0 = pack2(a0.z, a0.w);
+            const uint64_t ex1 = pack2(a1.x, a1.y), ey1 = pack2(a1.z, a1.w);
+            const uint64_t P0 = ffma2(px2, ex0, pack2(c0.x, c0.y));
+            const uint64_t Q0 = ffma2(px2, ey0, pack2(c0.z, c0.w));
+            const uint64_t P1 = ffma2(px2, ex1, pack2(c1.x, c1.y));
+            const uint64_t Q1 = ffma2(px2, ey1, pack2(c1.z, c1.w));
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint64_t y2 = pack2(py[r], py[r]);
+                const uint64_t ny2 = pack2(-py[r], -py[r]);
+                float al0, al1, bl0, bl1;
+                unpack2(ffma2(y2, ey0, P0), al0, al1);
+                unpack2(ffma2(y2, ey1, P1), bl0, bl1);
+                const uint64_t pe0 = ffma2(ny2, ex0, Q0);
+                const uint64_t pe1 = ffma2(ny2, ex1, Q1);
+                const float u0 = __saturatef(__fadd_rn(fabsf(al0), -h0));
+                const float u1 = __saturatef(__fadd_rn(fabsf(al1), -h0));
+                const float v0 = __saturatef(__fadd_rn(fabsf(bl0), -h1));
+                const float v1 = __saturatef(__fadd_rn(fabsf(bl1), -h1));
+                const uint64_t u2 = pack2(u0, u1), v2 = pack2(v0, v1);
+                float d00, d01, d10, d11;
+                unpack2(ffma2(u2, u2, fmul2(pe0, pe0)), d00, d01);
+                unpack2(ffma2(v2, v2, fmul2(pe1, pe1)), d10, d11);
+                tm[2 * r] = fminf(tm[2 * r], fminf(d00, d10));
+                tm[2 * r + 1] = fminf(tm[2 * r + 1], fminf(d01, d11));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * R; ++k) {
+            const bool better = tm[k] < b1[k];
+            b2[k] = fminf(b2[k], fmaxf(tm[k], b1[k]));
+            t1[k] = better ? tile : t1[k];
+            b1[k] = fminf(b1[k], tm[k]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ window preparation
+// Input sample loader (FP32 or FP64 waveform / time arrays).
+__device__ __forceinline__ double load_sample(const void* p, int dtype, long long i) {
+    return dtype == WFOT_F64 ? reinterpret_cast<const double*>(p)[i]
+                             : (double)reinterpret_cast<const float*>(p)[i];
+}
+
+__device__ __forceinline__ double block_reduce_minmax(double v, bool is_max, double* red) {
+    // red: >= 32 doubles of shared memory; all threads of the block participate
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, v, off);
+        v = is_max ? fmax(v, o) : fmin(v, o);
+    }
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double r = red[0];
+    for (int i = 1; i < nw; ++i) r = is_max ? fmax(r, red[i]) : fmin(r, red[i]);
+    return r;
+}
+
+// Destination buffers may live in shared or global memory.
+struct PrepOut {
+    double2* pn;    // [nt]
+    float4* A;      // [Spad]
+    float4* B;      // [Spad]
+    float* H;       // [Spad]
+    float* pxs;     // [ntg]  scaled local pixel time coordinates
+    float* pys;     // [nug]
+    WinHdr* hdr;    // [1]
+};
+
+// One block prepares one window.  `red` = 64 doubles of shared scratch.
+// transform != 0: arctan amplitude transform (libs/ricker_util.py:270-275) with the
+// grid's (u0,u1); the amplitude box becomes (0,1) (libs/ricker_util.py:241-244).
+__device__ __forceinline__ void prep_window(const void* t, const void* w, int dtype, long long toff,
+                                            long long woff, int nt, const wfot_grid& g, int nug,
+                                            int ntg, int transform, const PrepOut& o, double* red,
+                                            double* pn_out /* nullable global (nt,2) */) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    double u0 = g.u0, u1 = g.u1;
+    const double u0raw = g.u0, u1raw = g.u1;
+    if (transform) { u0 = 0.0; u1 = 1.0; }
+    const double delt = __dmul_rn(g.tantheta, __dsub_rn(g.t1, g.t0));      // :90
+    const double du = __dsub_rn(u1, u0);
+    double mnx = CUDART_INF, mxx = -CUDART_INF, mny = CUDART_INF, mxy = -CUDART_INF;
+    for (int j = tid; j < nt; j += nth) {
+        const double tj = load_sample(t, dtype, toff + j);
+        double wj = load_sample(w, dtype, woff + j);
+        if (transform) {   // un = 0.5 + arctan(((u-u0)+(u-u1))/(u1-u0))/pi
+            const double up = __ddiv_rn(__dadd_rn(__dsub_rn(wj, u0raw), __dsub_rn(wj, u1raw)),
+                                        __dsub_rn(u1raw, u0raw));
+            wj = __dadd_rn(0.5, __ddiv_rn(atan(up), CUDART_PI));
+        }
+        double2 p;
+        p.x = __ddiv_rn(__dsub_rn(tj, g.t0), delt);                        // :110
+        p.y = __ddiv_rn(__dsub_rn(wj, u0), du);
+        o.pn[j] = p;
+        if (pn_out) { pn_out[2 * j] = p.x; pn_out[2 * j + 1] = p.y; }
+        mnx = fmin(mnx, p.x); mxx = fmax(mxx, p.x);
+        mny = fmin(mny, p.y); mxy = fmax(mxy, p.y);
+    }
+    mnx = block_reduce_minmax(mnx, false, red);
+    mxx = block_reduce_minmax(mxx, true, red);
+    mny = block_reduce_minmax(mny, false, red);
+    mxy = block_reduce_minmax(mxy, true, red);   // contains __syncthreads: o.pn visible below
+    // pixel axes (:91, 95-106)
+    double T0, Tl, U0, Ul;
+    if (g.has_fpgrid) {
+        T0 = __ddiv_rn(__dsub_rn(g.fp_t0, g.t0), delt);
+        Tl = __ddiv_rn(__dsub_rn(g.fp_t1, g.t0), delt);
+        U0 = __ddiv_rn(__dsub_rn(g.fp_u0, u0), du);
+        Ul = __ddiv_rn(__dsub_rn(g.fp_u1, u0), du);
+    } else {
+        T0 = o.pn[0].x; Tl = o.pn[nt - 1].x; U0 = 0.0; Ul = 1.0;
+    }
+    const double Ts = ntg > 1 ? __ddiv_rn(__dsub_rn(Tl, T0), (double)(ntg - 1)) : 0.0;
+    const double Us = nug > 1 ? __ddiv_rn(__dsub_rn(Ul, U0), (double)(nug - 1)) : 0.0;
+    // FP32 frame: origin at the centre of the bounding box of samples and pixels,
+    // scaled by a power of two so that every distance in the box is < 1.
+    const double bx0 = fmin(mnx, fmin(T0, Tl)), bx1 = fmax(mxx, fmax(T0, Tl));
+    const double by0 = fmin(mny, fmin(U0, Ul)), by1 = fmax(mxy, fmax(U0, Ul));
+    const double ccx = 0.5 * (bx0 + bx1), ccy = 0.5 * (by0 + by1);
+    const double diag = sqrt((bx1 - bx0) * (bx1 - bx0) + (by1 - by0) * (by1 - by0));
+    int ex = 0;
+    frexp(diag > 0.0 ? diag : 1.0, &ex);           // diag = m * 2^ex, m in [0.5, 1)
+    const double sigma = ldexp(1.0, -ex);
+    const int S = nt - 1;
+    const int Spad = ((S + kTile - 1) / kTile) * kTile;
+    int degen = 0;
+    for (int s = tid; s < Spad; s += nth) {
+        float4 A, B;
+        float h;
+        if (s < S) {
+            const double2 a = o.pn[s], b = o.pn[s + 1];
+            const double cx = b.x - a.x, cy = b.y - a.y;
+            const double len = sqrt(cx * cx + cy * cy);
+            double exd = 1.0, eyd = 0.0;
+            if (len > 0.0) { exd = cx / len; eyd = cy / len; } else { degen++; }
+            const double mx = (a.x + 0.5 * cx - ccx) * sigma, my = (a.y + 0.5 * cy - ccy) * sigma;
+            const float fex = (float)exd, fey = (float)eyd;
+            const float am = (float)(mx * exd + my * eyd);     // mid . e
+            const float bm = (float)(mx * eyd - my * exd);     // perp' = px*ey - py*ex - bm
+            A = make_float4(fex, fex, fey, fey);
+            B = make_float4(-am, -am, -bm, -bm);
+            h = (float)(0.5 * len * sigma);
+        } else {   // padding: along = -4 -> sat -> 1, perp = 2 -> D = kPadD
+            A = make_float4(0.f, 0.f, 0.f, 0.f);
+            B = make_float4(-4.f, -4.f, 2.f, 2.f);
+            h = 0.f;
+        }
+        o.A[s] = A; o.B[s] = B; o.H[s] = h;
+    }
+    for (int i = tid; i < ntg; i += nth)
+        o.pxs[i] = (float)((lin_axis(T0, Ts, Tl, i, ntg) - ccx) * sigma);
+    for (int i = tid; i < nug; i += nth)
+        o.pys[i] = (float)((lin_axis(U0, Us, Ul, i, nug) - ccy) * sigma);
+    if (degen) atomicAdd(&o.hdr->degenerate, degen);   // zeroed by the caller before prep_window
+    if (tid == 0) {
+        WinHdr* h = o.hdr;
+        h->T0 = T0; h->Tstep = Ts; h->Tlast = Tl; h->U0 = U0; h->Ustep = Us; h->Ulast = Ul;
+        h->ccx = ccx; h->ccy = ccy; h->sigma = sigma; h->du = du; h->u0raw = u0raw; h->u1raw = u1raw;
+        h->pad = 0;
+    }
+}
+
+// ------------------------------------------------------------------ per-pixel epilogue values
+struct PixelVals {
+    double d, pdf, xcx, xcy, g;   // g = (xc_y - p_y)/d   (dddx_y, libs/FingerprintLib.py:355)
+};
+
+__device__ __forceinline__ PixelVals pixel_values(const double2* __restrict__ pn, const PixelHit& hit,
+                                                  double py, double lambda, int q) {
+    PixelVals v;
+    const double2 a = pn[hit.s], b = pn[hit.s + 1];
+    const double cx = __dsub_rn(b.x, a.x), cy = __dsub_rn(b.y, a.y);
+    v.xcx = __dadd_rn(a.x, __dmul_rn(hit.lam, cx));            // xclose (:262)
+    v.xcy = __dadd_rn(a.y, __dmul_rn(hit.lam, cy));
+    v.d = __dsqrt_rn(hit.D);                                   // (:263)
+    v.pdf = (q == 2) ? exp(-(v.d * v.d) / lambda) : exp(-fabs(v.d) / lambda);   // (:174,176)
+    v.g = (v.xcy - py) / v.d;
+    return v;
+}
+
+}  // namespace wfot

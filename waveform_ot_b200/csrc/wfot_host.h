@@ -1,0 +1,52 @@
+// wfot_host.h -- host-side helpers shared by the translation units of libwfot.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "wfot_device.cuh"
+
+namespace wfot {
+
+constexpr int kFpChunk = 2048;   // windows prepared + scanned per launch pair (materialising path)
+
+// Per-chunk scratch of the materialising fingerprint path (device memory).
+struct FpWorkspace {
+    WinHdr* hdr;     // [chunk]
+    double2* pn;     // [chunk][nt]
+    float4* A;       // [chunk][Spad]
+    float4* B;       // [chunk][Spad]
+    float* H;        // [chunk][Spad]
+    float* pxs;      // [chunk][ntg_pad]
+    float* pys;      // [chunk][nug_pad]
+    int Spad, ntg_pad, nug_pad;
+};
+
+inline int seg_pad(int nt) { return ((nt - 1 + kTile - 1) / kTile) * kTile; }
+inline int pad4(int n) { return (n + 3) & ~3; }
+
+inline size_t fp_workspace_per_window(int nt, int nug, int ntg) {
+    const size_t Spad = (size_t)seg_pad(nt);
+    return 128 + (size_t)nt * 16 + Spad * 36 + (size_t)(pad4(ntg) + pad4(nug)) * 4;
+}
+
+inline FpWorkspace fp_workspace_carve(void* base, int chunk, int nt, int nug, int ntg) {
+    FpWorkspace ws;
+    ws.Spad = seg_pad(nt);
+    ws.ntg_pad = pad4(ntg);
+    ws.nug_pad = pad4(nug);
+    unsigned char* p = (unsigned char*)base;
+    ws.hdr = (WinHdr*)p;   p += (size_t)chunk * 128;
+    ws.pn = (double2*)p;   p += (size_t)chunk * nt * 16;
+    ws.A = (float4*)p;     p += (size_t)chunk * ws.Spad * 16;
+    ws.B = (float4*)p;     p += (size_t)chunk * ws.Spad * 16;
+    ws.H = (float*)p;      p += (size_t)chunk * ws.Spad * 4;
+    ws.pxs = (float*)p;    p += (size_t)chunk * ws.ntg_pad * 4;
+    ws.pys = (float*)p;
+    return ws;
+}
+
+extern thread_local char g_cuda_err[512];
+int cuda_fail(cudaError_t e, const char* what);
+
+}  // namespace wfot

@@ -1,0 +1,534 @@
+// wfot_kernels.cu -- materialising kernels + C ABI of libwfot.so (sm_100a).
+//   k_prep           window normalisation + FP32 segment table   (FingerprintLib.py:53-115)
+//   k_fingerprint    nearest segment / distance / density / d(d)/dw (FingerprintLib.py:230-385)
+//   k_marginals      2-D normalisation + time/amplitude marginals (OTlib.py:90-93,146-160)
+//   k_ot1d           batched 1-D W1/W2 + derivatives              (OTlib.py:596-706)
+//   k_pdfderiv       pixel -> sample segmented reduction          (FingerprintLib.py:182-228)
+//   k_chain          J . dr batched                               (ricker_util.py:399-400)
+// The fused throughput kernel lives in wfot_fused.cu.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "wfot_device.cuh"
+#include "wfot_host.h"
+#include "wfot_ot.cuh"
+
+namespace wfot {
+
+thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return WFOT_ERR_CUDA;
+}
+
+// ============================================================ k_prep
+struct PrepArgs {
+    const void* t; const void* w; int dtype; long long t_stride; int nt;
+    const wfot_grid* grids; int n_grids; long long b0; int nug, ntg; int transform;
+    FpWorkspace ws; double* pn_out; int32_t* status;
+};
+
+__global__ void __launch_bounds__(256) k_prep(PrepArgs a) {
+    __shared__ double red[64];
+    const int wl = blockIdx.x;
+    const long long b = a.b0 + wl;
+    const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
+    PrepOut o;
+    o.pn = a.ws.pn + (size_t)wl * a.nt;
+    o.A = a.ws.A + (size_t)wl * a.ws.Spad;
+    o.B = a.ws.B + (size_t)wl * a.ws.Spad;
+    o.H = a.ws.H + (size_t)wl * a.ws.Spad;
+    o.pxs = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
+    o.pys = a.ws.pys + (size_t)wl * a.ws.nug_pad;
+    o.hdr = a.ws.hdr + wl;
+    if (threadIdx.x == 0) o.hdr->degenerate = 0;
+    __syncthreads();
+    prep_window(a.t, a.w, a.dtype, b * a.t_stride, b * (long long)a.nt, a.nt, g, a.nug, a.ntg,
+                a.transform, o, red, a.pn_out ? a.pn_out + (size_t)b * a.nt * 2 : nullptr);
+    __syncthreads();
+    if (threadIdx.x == 0 && o.hdr->degenerate && a.status)
+        atomicAdd(a.status + WFOT_STAT_DEGENERATE_SEG, o.hdr->degenerate);
+}
+
+// ============================================================ k_fingerprint
+constexpr int kQCap = 1024;
+
+struct FpArgs {
+    FpWorkspace ws; int nt; long long b0; int nug, ntg; double lambda; int q;
+    double* dfield; int32_t* iray; double* lray; double* xray; double* pdf; double* dddy;
+    int32_t* status;
+};
+
+struct QEntry { int slot_it; int iu; float b1; float pad; };
+
+__device__ __forceinline__ void emit_pixel(const FpArgs& a, const double2* pn, const WinHdr& h,
+                                           long long b, int it, int iu, const PixelHit& hit,
+                                           double py, int& zero_dist) {
+    const size_t npix = (size_t)a.nug * a.ntg;
+    const size_t k = (size_t)b * npix + (size_t)iu * a.ntg + it;
+    const PixelVals v = pixel_values(pn, hit, py, a.lambda, a.q);
+    if (a.dfield) a.dfield[k] = v.d;
+    if (a.iray) a.iray[k] = hit.s;
+    if (a.lray) a.lray[k] = hit.lam;
+    if (a.xray) { a.xray[2 * k] = v.xcx; a.xray[2 * k + 1] = v.xcy; }
+    if (a.pdf) a.pdf[k] = v.pdf;
+    if (a.dddy) {
+        a.dddy[2 * k] = ((1.0 - hit.lam) * v.g) / h.du;      // libs/FingerprintLib.py:365,373,377
+        a.dddy[2 * k + 1] = (hit.lam * v.g) / h.du;          // :371,374,378
+        zero_dist += (v.d == 0.0);
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wl = blockIdx.y;
+    const long long b = a.b0 + wl;
+    const int Spad = a.ws.Spad, S = a.nt - 1;
+    float4* sA = reinterpret_cast<float4*>(smem_raw);
+    float4* sB = sA + Spad;
+    float* sH = reinterpret_cast<float*>(sB + Spad);
+    float* sPx = sH + Spad;
+    float* sPy = sPx + a.ws.ntg_pad;
+    QEntry* queue = reinterpret_cast<QEntry*>(sPy + a.ws.nug_pad);
+    __shared__ int qcount;
+    __shared__ WinHdr hdr;
+    const int tid = threadIdx.x;
+    {   // stage the window's segment table (contiguous, 16-byte vector copies)
+        const float4* gA = a.ws.A + (size_t)wl * Spad;
+        const float4* gB = a.ws.B + (size_t)wl * Spad;
+        const float* gH = a.ws.H + (size_t)wl * Spad;
+        for (int i = tid; i < Spad; i += 256) { sA[i] = gA[i]; sB[i] = gB[i]; sH[i] = gH[i]; }
+        const float* gx = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
+        const float* gy = a.ws.pys + (size_t)wl * a.ws.nug_pad;
+        for (int i = tid; i < a.ntg; i += 256) sPx[i] = gx[i];
+        for (int i = tid; i < a.nug; i += 256) sPy[i] = gy[i];
+        if (tid == 0) { qcount = 0; hdr = a.ws.hdr[wl]; }
+    }
+    __syncthreads();
+    const double2* pn = a.ws.pn + (size_t)wl * a.nt;
+    SegTable tb{sA, sB, sH, S, Spad};
+    const int ncp = (a.ntg + 1) >> 1, nrg = (a.nug + R - 1) / R;
+    const int blk = blockIdx.x * 256 + tid;
+    int zero_dist = 0, slow = 0;
+    if (blk < ncp * nrg) {
+        const int cp = blk % ncp, rg = blk / ncp;
+        const int it0 = 2 * cp, it1 = min(2 * cp + 1, a.ntg - 1);
+        float py[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) py[r] = sPy[min(rg * R + r, a.nug - 1)];
+        float b1[2 * R], b2[2 * R];
+        int t1[2 * R];
+        scan_block<R>(tb, sPx[it0], sPx[it1], py, b1, t1, b2);
+        // The epilogue is deliberately NOT unrolled (FP64 division/exp per pixel would
+        // multiply the code size by 2R); the scan results move to local arrays first.
+        float lb1[2 * R], lb2[2 * R];
+        int lt1[2 * R];
+#pragma unroll
+        for (int k = 0; k < 2 * R; ++k) { lb1[k] = b1[k]; lb2[k] = b2[k]; lt1[k] = t1[k]; }
+#pragma unroll 1
+        for (int k = 0; k < 2 * R; ++k) {
+            const int it = 2 * cp + (k & 1), iu = rg * R + (k >> 1);
+            if (it >= a.ntg || iu >= a.nug) continue;
+            const float kb1 = lb1[k];
+            const double px = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, it, a.ntg);
+            const double pyd = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, iu, a.nug);
+            PixelHit hit;
+            if (lb2[k] <= kb1 + tau32(kb1)) {   // another tile within rounding distance
+                const int qi = atomicAdd(&qcount, 1);
+                if (qi < kQCap) { queue[qi] = QEntry{it, iu, kb1, 0.f}; continue; }
+                ++slow;
+                resolve_pixel_full(tb, pn, sPx[it], sPy[iu], px, pyd, kb1, hit);
+            } else {
+                resolve_pixel(tb, pn, sPx[it], sPy[iu], px, pyd, kb1, lt1[k], hit);
+            }
+            emit_pixel(a, pn, hdr, b, it, iu, hit, pyd, zero_dist);
+        }
+    }
+    __syncthreads();
+    {   // ambiguous pixels: one warp each, all segments
+        const int nq = min(qcount, kQCap), warp = tid >> 5, lane = tid & 31;
+        for (int e = warp; e < nq; e += 8) {
+            const QEntry qe = queue[e];
+            const double px = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, qe.slot_it, a.ntg);
+            const double pyd = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, qe.iu, a.nug);
+            PixelHit hit;
+            resolve_pixel_warp(tb, pn, sPx[qe.slot_it], sPy[qe.iu], px, pyd, qe.b1, hit);
+            if (lane == 0) { emit_pixel(a, pn, hdr, b, qe.slot_it, qe.iu, hit, pyd, zero_dist); ++slow; }
+        }
+    }
+    if (a.status) {
+        if (zero_dist) atomicAdd(a.status + WFOT_STAT_ZERO_DIST, zero_dist);
+        if (slow) atomicAdd(a.status + WFOT_STAT_SLOW_PIXELS, slow);
+    }
+}
+
+// ============================================================ k_marginals
+// One block per window.  Column sums: a thread owns column pairs and walks the rows
+// (16-byte loads, fixed order).  Row sums: one warp per row, 16-byte loads, shuffle tree.
+__global__ void __launch_bounds__(256) k_marginals(const double* __restrict__ pdf, int nug, int ntg,
+                                                   double* amp, double* marg_t, double* marg_u,
+                                                   int32_t* status) {
+    __shared__ double red[33];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* colsum = reinterpret_cast<double*>(smem_raw);   // [ntg]
+    const long long b = blockIdx.x;
+    const double* P = pdf + (size_t)b * nug * ntg;
+    const int tid = threadIdx.x;
+    int neg = 0;
+    double part = 0.0;
+    const bool vec = (ntg % 2 == 0);
+    if (vec) {
+        for (int cp = tid; cp < ntg / 2; cp += 256) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int iu = 0; iu < nug; ++iu) {
+                const double2 v = *reinterpret_cast<const double2*>(P + (size_t)iu * ntg + 2 * cp);
+                s0 += v.x; s1 += v.y;
+                neg += (v.x < 0.0) + (v.y < 0.0);
+            }
+            colsum[2 * cp] = s0; colsum[2 * cp + 1] = s1;
+            part += s0 + s1;
+        }
+    } else {
+        for (int c = tid; c < ntg; c += 256) {
+            double s0 = 0.0;
+            for (int iu = 0; iu < nug; ++iu) { const double v = P[(size_t)iu * ntg + c]; s0 += v; neg += (v < 0.0); }
+            colsum[c] = s0;
+            part += s0;
+        }
+    }
+    const double A = block_sum(part, red);                       // OTpdf.amp (libs/OTlib.py:92)
+    for (int c = tid; c < ntg; c += 256) marg_t[(size_t)b * ntg + c] = colsum[c] / A;   // :93,155
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int iu = warp; iu < nug; iu += 8) {
+        double s = 0.0;
+        const double* row = P + (size_t)iu * ntg;
+        if (vec) {
+            for (int c = lane; c < ntg / 2; c += 32) {
+                const double2 v = *reinterpret_cast<const double2*>(row + 2 * c);
+                s += v.x + v.y;
+            }
+        } else {
+            for (int c = lane; c < ntg; c += 32) s += row[c];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) marg_u[(size_t)b * nug + iu] = s / A;     // :93,156
+    }
+    if (tid == 0) amp[b] = A;
+    const int nneg = __syncthreads_count(neg > 0);
+    if (tid == 0 && nneg && status) atomicAdd(status + WFOT_STAT_NEG_PDF, 1);
+}
+
+// ============================================================ k_ot1d
+struct OtArgs {
+    const void* f; const void* g; int dtype; const double* xf; const double* xg;
+    long long f_stride, g_stride, xf_stride, xg_stride; int n, m, pmask, deriv;
+    double* W; double* dW1; double* dW2; double* dpos; double* amp_f; double* cdf_f; double* cdf_g;
+    int32_t* merge_order; int32_t* status;
+};
+
+__global__ void __launch_bounds__(256) k_ot1d(OtArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long long b = blockIdx.x;
+    const int n = a.n, m = a.m, K = n + m - 1, tid = threadIdx.x;
+    double* cf = reinterpret_cast<double*>(smem_raw);
+    double* cg = cf + n;
+    double* tk = cg + m;
+    double* dx = tk + K;
+    double* E = dx + K;
+    double* xfs = E + n;
+    double* xgs = xfs + n;
+    double* red = xgs + m;
+    int* posf = reinterpret_cast<int*>(red + 34);
+    // target CDF: same OTpdf normalisation as the source (libs/OTlib.py:92-93,112-114)
+    double part = 0.0;
+    int neg = 0;
+    for (int i = tid; i < m; i += 256) {
+        const double v = load_sample(a.g, a.dtype, b * a.g_stride + i);
+        cg[i] = v; part += v; neg += (v < 0.0);
+    }
+    const double ampg = block_sum(part, red);
+    for (int i = tid; i < m; i += 256) cg[i] = cg[i] / ampg;
+    __syncthreads();
+    block_scan(cg, m, false, red);
+    const double lastg = cg[m - 1];
+    __syncthreads();
+    for (int i = tid; i < m; i += 256) cg[i] = cg[i] / lastg;
+    for (int j = tid; j < n; j += 256) {
+        cf[j] = load_sample(a.f, a.dtype, b * a.f_stride + j);
+        xfs[j] = a.xf[b * a.xf_stride + j];
+    }
+    for (int i = tid; i < m; i += 256) xgs[i] = a.xg[b * a.xg_stride + i];
+    __syncthreads();
+    OtScratch sc{cf, tk, dx, E, posf, red};
+    double* o1 = (a.deriv && a.dW1) ? a.dW1 + (size_t)b * n : nullptr;
+    double* o2 = (a.deriv && a.dW2) ? a.dW2 + (size_t)b * n : nullptr;
+    const OtResult r = block_ot1d(sc, n, cg, m, xfs, xgs, a.pmask, o1, o2,
+                                  a.merge_order ? a.merge_order + (size_t)b * K : nullptr);
+    if (a.cdf_f) for (int j = tid; j < n; j += 256) a.cdf_f[(size_t)b * n + j] = cf[j];
+    if (a.cdf_g) for (int i = tid; i < m; i += 256) a.cdf_g[(size_t)b * m + i] = cg[i];
+    if (tid == 0) {
+        if (a.W) { if (a.pmask & 1) a.W[2 * b] = r.W1; if (a.pmask & 2) a.W[2 * b + 1] = r.W2; }
+        if (a.dpos) { if (a.pmask & 1) a.dpos[2 * b] = r.dpos1; if (a.pmask & 2) a.dpos[2 * b + 1] = r.dpos2; }
+        if (a.amp_f) a.amp_f[b] = r.amp;
+        if (a.status) {
+            if (r.neg) atomicAdd(a.status + WFOT_STAT_NEG_PDF, 1);
+            if (r.common) atomicAdd(a.status + WFOT_STAT_COMMON_CDF, r.common);
+        }
+    }
+    const int nneg = __syncthreads_count(neg > 0);
+    if (tid == 0 && nneg && a.status) atomicAdd(a.status + WFOT_STAT_NEG_PDF, 1);
+}
+
+// ============================================================ k_pdfderiv
+// One block per (window, chain).  A thread walks whole pixel columns, so consecutive
+// pixels mostly share their nearest segment and are combined before the shared-memory add.
+__global__ void __launch_bounds__(256) k_pdfderiv(const double* __restrict__ pdf,
+                                                  const double* __restrict__ dfield,
+                                                  const int32_t* __restrict__ iray,
+                                                  const double* __restrict__ dddy,
+                                                  const double* __restrict__ chain, int nchain,
+                                                  int npix, int nt, double lambda, int q, double* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* bins = reinterpret_cast<double*>(smem_raw);   // [nt]
+    const long long b = blockIdx.x;
+    const int ch = blockIdx.y, tid = threadIdx.x;
+    for (int j = tid; j < nt; j += 256) bins[j] = 0.0;
+    __syncthreads();
+    const size_t base = (size_t)b * npix;
+    const double* C = chain ? chain + ((size_t)b * nchain + ch) * npix : nullptr;
+    const int per = (npix + 255) / 256;
+    const int k0 = tid * per, k1 = min(k0 + per, npix);
+    int cur = -1;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int k = k0; k < k1; ++k) {
+        double row = pdf[base + k] * (C ? C[k] : 1.0);                   // :189,211
+        if (q == 2) row = 2.0 * row * fabs(dfield[base + k]);            // :194,216
+        const int i = iray[base + k];
+        if (i != cur) {
+            if (cur >= 0) { atomicAdd(&bins[cur], acc0); atomicAdd(&bins[cur + 1], acc1); }
+            cur = i; acc0 = 0.0; acc1 = 0.0;
+        }
+        acc0 += dddy[2 * (base + k)] * row;                               // :200,223
+        acc1 += dddy[2 * (base + k) + 1] * row;                           // :201,224
+    }
+    if (cur >= 0) { atomicAdd(&bins[cur], acc0); atomicAdd(&bins[cur + 1], acc1); }
+    __syncthreads();
+    for (int j = tid; j < nt; j += 256)
+        out[((size_t)b * nchain + ch) * nt + j] = -bins[j] / lambda;       // :203,228
+}
+
+// ============================================================ k_chain
+// out[m][p] = sum_l J[m][p][l] * dr[m][l]; one warp per (m,p), 16-byte loads.
+__global__ void __launch_bounds__(256) k_chain(const double* __restrict__ J, const double* __restrict__ dr,
+                                               int P, int L, int M, long long Jstride, double* out) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= M * P) return;
+    const int mI = warp / P, p = warp % P;
+    const double* row = J + (size_t)mI * Jstride + (size_t)p * L;
+    const double* d = dr + (size_t)mI * L;
+    double s = 0.0;
+    for (int l = lane; l < L; l += 32) s += row[l] * d[l];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[(size_t)mI * P + p] = s;
+}
+
+// ============================================================ FP32 peak probe
+template <int PACKED>
+__global__ void __launch_bounds__(256) k_peak(int iters, float* sink) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+    const float a = 1.0000001f, c = 1e-7f;
+    if (PACKED) {
+        uint64_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = pack2(x[2 * i], x[2 * i + 1]);
+        const uint64_t a2 = pack2(a, a), c2 = pack2(c, c);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = ffma2(v[i], a2, c2);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) unpack2(v[i], x[2 * i], x[2 * i + 1]);
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = __fmaf_rn(x[i], a, c);
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 12345.678f) sink[0] = s;
+}
+
+}  // namespace wfot
+
+// ==================================================================== C ABI
+using namespace wfot;
+
+extern "C" {
+
+int wfot_version(void) { return WFOT_VERSION; }
+
+const char* wfot_strerror(int status) {
+    switch (status) {
+        case WFOT_OK: return "ok";
+        case WFOT_ERR_INVALID_ARG: return "invalid argument";
+        case WFOT_ERR_CUDA: return "CUDA error (see wfot_last_cuda_error)";
+        case WFOT_ERR_UNSUPPORTED: return "unsupported device or problem size";
+        case WFOT_ERR_WORKSPACE: return "workspace too small";
+        default: return "unknown status";
+    }
+}
+
+const char* wfot_last_cuda_error(void) { return g_cuda_err; }
+
+int wfot_device_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return WFOT_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return WFOT_ERR_CUDA;
+    return n;
+}
+
+int wfot_device_cc(void) {
+    int dev = 0, ma = 0, mi = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return WFOT_ERR_CUDA;
+    cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev);
+    return ma * 10 + mi;
+}
+
+size_t wfot_fingerprint_workspace_bytes(int B, int nt, int nug, int ntg) {
+    if (B <= 0 || nt < 2 || nug < 1 || ntg < 1) return 0;
+    const int chunk = B < kFpChunk ? B : kFpChunk;
+    return fp_workspace_per_window(nt, nug, ntg) * (size_t)chunk + 256;
+}
+
+int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
+                           const wfot_grid* grids, int n_grids, int B, int nug, int ntg,
+                           double lambda, int q, double* pn, double* dfield, int32_t* iray,
+                           double* lray, double* xray, double* pdf, double* dddy, void* workspace,
+                           size_t workspace_bytes, int32_t* status, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!t || !w || !grids || !workspace || B <= 0 || nt < 2 || nug < 1 || ntg < 1 ||
+        (n_grids != 1 && n_grids != B) || (q != 0 && q != 2) || !(lambda > 0.0) ||
+        (in_dtype != WFOT_F32 && in_dtype != WFOT_F64))
+        return WFOT_ERR_INVALID_ARG;
+    const size_t per = fp_workspace_per_window(nt, nug, ntg);
+    uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    const size_t avail = workspace_bytes - (base - (uintptr_t)workspace);
+    int chunk = (int)(avail / per);
+    if (chunk < 1) return WFOT_ERR_WORKSPACE;
+    if (chunk > B) chunk = B;
+    if (chunk > kFpChunk) chunk = kFpChunk;
+    FpWorkspace ws = fp_workspace_carve((void*)base, chunk, nt, nug, ntg);
+    constexpr int R = 8;
+    const size_t smem = (size_t)ws.Spad * 36 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
+    if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(k_fingerprint<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_fingerprint)");
+    const int ncp = (ntg + 1) / 2, nrg = (nug + R - 1) / R;
+    const int gx = (ncp * nrg + 255) / 256;
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = (int)((B - b0) < chunk ? (B - b0) : chunk);
+        PrepArgs pa{t, w, in_dtype, t_stride, nt, grids, n_grids, b0, nug, ntg, 0, ws, pn, status};
+        k_prep<<<nb, 256, 0, stream>>>(pa);
+        FpArgs fa{ws, nt, b0, nug, ntg, lambda, q, dfield, iray, lray, xray, pdf, dddy, status};
+        k_fingerprint<R><<<dim3(gx, nb), 256, smem, stream>>>(fa);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_fingerprint_batch launch");
+    return WFOT_OK;
+}
+
+int wfot_marginals_batch(const double* pdf, int B, int nug, int ntg, double* amp, double* marg_t,
+                         double* marg_u, int32_t* status, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!pdf || !amp || !marg_t || !marg_u || B <= 0 || nug < 1 || ntg < 1) return WFOT_ERR_INVALID_ARG;
+    const size_t smem = (size_t)ntg * 8;
+    if (smem > 200 * 1024) return WFOT_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(k_marginals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_marginals)");
+    k_marginals<<<B, 256, smem, stream>>>(pdf, nug, ntg, amp, marg_t, marg_u, status);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_marginals_batch launch");
+    return WFOT_OK;
+}
+
+int wfot_ot1d_batch(const void* f, const void* g, int in_dtype, const double* xf, const double* xg,
+                    long long f_stride, long long g_stride, long long xf_stride, long long xg_stride,
+                    int n, int m, int B, int pmask, int derivatives, double* W, double* dW1,
+                    double* dW2, double* dpos, double* amp_f, double* cdf_f, double* cdf_g,
+                    int32_t* merge_order, int32_t* status, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!f || !g || !xf || !xg || n < 1 || m < 1 || B <= 0 || pmask < 1 || pmask > 3 ||
+        (in_dtype != WFOT_F32 && in_dtype != WFOT_F64))
+        return WFOT_ERR_INVALID_ARG;
+    const int K = n + m - 1;
+    const size_t smem = (size_t)(n + m + 2 * K + n + n + m + 34) * 8 + (size_t)n * 4;
+    if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(k_ot1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ot1d)");
+    OtArgs a{f, g, in_dtype, xf, xg, f_stride, g_stride, xf_stride, xg_stride, n, m, pmask, derivatives,
+             W, dW1, dW2, dpos, amp_f, cdf_f, cdf_g, merge_order, status};
+    k_ot1d<<<B, 256, smem, stream>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_ot1d_batch launch");
+    return WFOT_OK;
+}
+
+int wfot_pdfderiv_batch(const double* pdf, const double* dfield, const int32_t* iray, const double* dddy,
+                        const double* chain, int nchain, int B, int npix, int nt, double lambda, int q,
+                        double* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!pdf || !iray || !dddy || !out || B <= 0 || npix < 1 || nt < 2 || nchain < 1 ||
+        (!chain && nchain != 1) || (q == 2 && !dfield) || !(lambda > 0.0))
+        return WFOT_ERR_INVALID_ARG;
+    const size_t smem = (size_t)nt * 8;
+    if (smem > 200 * 1024) return WFOT_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(k_pdfderiv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_pdfderiv)");
+    k_pdfderiv<<<dim3(B, nchain), 256, smem, stream>>>(pdf, dfield, iray, dddy, chain, nchain, npix, nt, lambda, q, out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_pdfderiv_batch launch");
+    return WFOT_OK;
+}
+
+int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M, long long J_stride_models,
+                     double* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!J || !dr || !out || P < 1 || L < 1 || M < 1) return WFOT_ERR_INVALID_ARG;
+    const long long warps = (long long)M * P;
+    const int blocks = (int)((warps * 32 + 255) / 256);
+    k_chain<<<blocks, 256, 0, stream>>>(J, dr, P, L, M, J_stride_models, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_chain_batch launch");
+    return WFOT_OK;
+}
+
+int wfot_fp32_peak_probe(int packed, int iters, float* sink, double* fma_ops, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int sms = wfot_device_sm_count();
+    if (sms <= 0 || iters < 1 || !sink) return WFOT_ERR_INVALID_ARG;
+    const int blocks = sms * 8;
+    if (packed) k_peak<1><<<blocks, 256, 0, stream>>>(iters, sink);
+    else k_peak<0><<<blocks, 256, 0, stream>>>(iters, sink);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_fp32_peak_probe launch");
+    if (fma_ops) *fma_ops = (double)blocks * 256.0 * (double)iters * 8.0 * 16.0;
+    return WFOT_OK;
+}
+
+}  // extern "C"
