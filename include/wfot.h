@@ -180,6 +180,13 @@ int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M,
  * SM; returns executed FMA lane-operations through *fma_ops (host pointer). */
 int wfot_fp32_peak_probe(int packed, int iters, float* sink, double* fma_ops, void* stream);
 
+/* ---- diagnostic: the brute-force scan alone -------------------------------------
+ * prep + FP32 scan of every (pixel, segment) pair, no FP64 resolve: dist32 (B, nug, ntg)
+ * = FP32 nearest distance.  bench.py uses it to attribute time to the scan. */
+int wfot_scan_probe(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
+                    const wfot_grid* grids, int n_grids, int B, int nug, int ntg, float* dist32,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,21 @@
+"""ncu driver: a few launches of the materialising fingerprint kernel and the fused kernel (cfg5 shape)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from oracle import wfot_oracle as O
+from waveform_ot_b200 import batch as B
+
+nt, nug, ntg, lam = 1024, 256, 256, 0.04
+nb = int(sys.argv[1]) if len(sys.argv) > 1 else 37
+which = sys.argv[2] if len(sys.argv) > 2 else "both"
+w = torch.from_numpy(O.random_walk_windows(nb + 1, nt, seed=5)).cuda()
+t = torch.linspace(0, 1, nt, device="cuda")
+grid = (0.0, 1.0, -1.3, 1.3, nug, ntg)
+tg = B.Target.from_waveform(t, w[0], grid, nug, ntg, lam)
+for _ in range(2):
+    if which in ("both", "fp"):
+        B.fingerprint_batch(t, w[1:], grid, nug, ntg, lam, deriv=True)
+    if which in ("both", "fused"):
+        B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg)
+torch.cuda.synchronize()
+print("ok")

@@ -46,6 +46,10 @@ def main():
         print("%s fused: B=%d %.2f ms  %.1f windows/s  %.3f Tpair/s  alg %.1f TFLOP/s  slow_px/window %.1f" % (
             name, nb, ms, nb / ms * 1e3, pairs / ms / 1e9, 15 * pairs / ms / 1e9,
             r["status"].read()[4] / nb))
+        d32 = torch.empty((nb, nug, ntg), dtype=torch.float32, device="cuda")
+        fns = lambda: C.check(C.lib.wfot_scan_probe(C.ptr(t), C.ptr(w[1:]), 0, 0, nt, C.ptr(g), 1, nb, nug, ntg, C.ptr(d32), None))
+        fns(); ms0 = ev_time(fns)
+        print("   scan only: %.2f ms  %.3f Tpair/s  alg %.1f TFLOP/s" % (ms0, pairs / ms0 / 1e9, 15 * pairs / ms0 / 1e9))
         fnm = lambda: B.misfit_grad_batch(t, w[1:], g, nug, ntg, lam, tg, workspace=ws, want_grad=False)
         fnm(); ms2 = ev_time(fnm)
         print("   misfit only: %.2f ms" % ms2)

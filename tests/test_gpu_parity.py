@@ -104,18 +104,20 @@ def test_fingerprint_random_batch_vs_oracle(B, dtype):
 
 
 def test_fingerprint_symmetric_ties(B):
-    """Exact far-apart ties (mirror-symmetric waveform, pixel column on the symmetry axis) and
-    vertex ties on every column (Nt == nt): first-minimum rule must hold bit-exactly."""
-    nt = 65
+    """Exact far-apart ties (mirror-symmetric waveform, odd Nt puts a pixel column on the symmetry
+    axis, so equidistant segments sit in non-adjacent tiles -> all-segment FP64 rescan) and vertex
+    ties on every column (Nt == nt): the first-minimum rule must hold bit-exactly."""
+    nt = 257
     t = np.linspace(0.0, 1.0, nt)
     w = np.abs(np.sin(6 * np.pi * t)) * np.cos(2 * np.pi * t) ** 2
     w = 0.5 * (w + w[::-1])
-    grid = (0.0, 1.0, -0.5, 1.5, 41, 65)
-    out = B.fingerprint_batch(t, w, grid, 41, 65, 0.04, deriv=False)
-    torch.cuda.synchronize()
-    win = _oracle_window(t, w, grid, 0.04, deriv=False)
-    _check_fields(out, win)
-    assert int(out["status"].read()[4]) > 0      # some pixels went through the full FP64 rescan
+    for ntg in (129, 257):
+        grid = (0.0, 1.0, -0.5, 1.5, 41, ntg)
+        out = B.fingerprint_batch(t, w, grid, 41, ntg, 0.04, deriv=False)
+        torch.cuda.synchronize()
+        win = _oracle_window(t, w, grid, 0.04, deriv=False)
+        _check_fields(out, win)
+        assert int(out["status"].read()[4]) > 0      # some pixels went through the all-segment rescan
 
 
 def test_marginals_and_ot1d_vs_oracle(B, golden):

@@ -52,6 +52,7 @@ SIGNATURES = {
                                          _p, _p, _p, _p, _i, _p, _p, _p, _p, _sz, _p, _p]),
     "wfot_chain_batch": (C.c_int, [_p, _p, _i, _i, _i, _ll, _p, _p]),
     "wfot_fp32_peak_probe": (C.c_int, [_i, _i, _p, _p, _p]),
+    "wfot_scan_probe": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

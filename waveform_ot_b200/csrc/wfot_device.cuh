@@ -7,7 +7,10 @@
 //     frame" segment table in window-local, power-of-two-scaled coordinates.
 //   * scan_block<R>(): the hot loop.  A thread owns 2 pixel columns x R rows and
 //     walks every segment; per (pixel, segment) pair it spends 5 FP32 lane
-//     operations (4 of them issued as packed FFMA2/FMUL2) and half an FMNMX3:
+//     operations (4 of them issued as packed FFMA2/FMUL2 over a PAIR OF ROWS, the
+//     per-segment quantities entering as scalar-broadcast operands so that every
+//     FFMA2 reads at most 4 registers - three distinct register pairs would cost
+//     3 clk instead of 2 on the register banks) and half an FMNMX3:
 //         along = (p - mid).e      perp = (p - mid).n
 //         D     = perp^2 + sat(|along| - h)^2          (h = half segment length)
 //     which is the clamped point-to-segment distance of
@@ -28,7 +31,7 @@
 
 namespace wfot {
 
-constexpr int kTile = 32;          // segments per argmin tile
+constexpr int kTile = 16;          // segments per argmin tile
 constexpr float kBig = 3.0e38f;    // "no distance yet"
 constexpr float kPadD = 5.0f;      // squared distance produced by padding segments (> any real one)
 
@@ -66,8 +69,7 @@ struct WinHdr {
 
 // FP32 segment table in the rotated frame (shared or global memory)
 struct SegTable {
-    const float4* A;   // {ex, ex, ey, ey}
-    const float4* B;   // {-am, -am, -bm, -bm}   am = mid.e, bm = mid x e (scaled)
+    const float4* A;   // {ex, ey, -am, -bm}   e = unit direction, am = mid.e, bm = mid x e (scaled)
     const float* H;    // half length (scaled)
     int S;             // real segments
     int Spad;          // padded to a multiple of kTile
@@ -82,12 +84,11 @@ __device__ __forceinline__ double lin_axis(double a0, double step, double alast,
 // ------------------------------------------------------------------ FP32 pair kernel (scalar form)
 __device__ __forceinline__ float eval32(const SegTable& tb, int s, float px, float py) {
     const float4 a = tb.A[s];
-    const float4 b = tb.B[s];
     const float h = tb.H[s];
-    const float P = __fmaf_rn(px, a.x, b.x);
-    const float Q = __fmaf_rn(px, a.z, b.z);
-    const float al = __fmaf_rn(py, a.z, P);
-    const float pe = __fmaf_rn(-py, a.x, Q);
+    const float P = __fmaf_rn(px, a.x, a.z);     // px*ex - am
+    const float Q = __fmaf_rn(px, a.y, a.w);     // px*ey - bm
+    const float al = __fmaf_rn(py, a.y, P);      // along  = (p - mid).e
+    const float pe = __fmaf_rn(py, -a.x, Q);     // perp   = (p - mid) x e
     const float tm = __saturatef(__fadd_rn(fabsf(al), -h));
     return __fmaf_rn(tm, tm, __fmul_rn(pe, pe));
 }
@@ -124,24 +125,48 @@ struct PixelHit {
     int s;        // selected segment (np.argmin first-minimum)
 };
 
-// Walk tile t1 (+1 segment either side: vertex ties straddle tile boundaries).
-__device__ __forceinline__ void resolve_pixel(const SegTable& tb, const double2* __restrict__ pn,
+// Resolve one pixel from the scan's tile statistics.
+//   b1/t1 = smallest tile minimum and its tile, b2/b3 = 2nd / 3rd smallest tile minimum.
+// Every segment whose true FP64 distance could be minimal has an FP32 distance <= thr
+// (thr = b1 + rounding tolerance), and therefore lives in a tile whose minimum is <= thr.
+//   b2 > thr            : only tile t1 -> 16 FP32 re-evaluations;
+//   b2 <= thr < b3      : exactly one other tile; if it is t1-1 or t1+1 (a vertex shared
+//                         across the tile boundary - by far the common case) the three tiles
+//                         are walked; otherwise, or if b3 <= thr, the caller queues the pixel
+//                         for the all-segment rescan.
+// The FP32 walk only builds a candidate bit mask; the FP64 reference-order evaluations run
+// afterwards in ascending segment order (strict '<' keeps np.argmin's first-minimum rule),
+// so lanes of a warp do not serialise on each other's candidates.
+// Returns false if the pixel must go to the full rescan.
+__device__ __forceinline__ bool resolve_pixel(const SegTable& tb, const double2* __restrict__ pn,
                                               float pxl, float pyl, double px, double py,
-                                              float b1, int t1, PixelHit& hit) {
+                                              float b1, int t1, float b2, float b3, PixelHit& hit) {
     const float thr = b1 + tau32(b1);
-    const int lo = max(t1 * kTile - 1, 0);
-    const int hi = min(t1 * kTile + kTile, tb.S - 1);
-    hit.D = CUDART_INF;
-    hit.lam = 0.0;
-    hit.s = lo;
-    for (int s = lo; s <= hi; ++s) {
-        const float d32 = eval32(tb, s, pxl, pyl);
-        if (d32 <= thr) {
-            double D, l;
-            eval64(pn, s, px, py, D, l);
-            if (D < hit.D) { hit.D = D; hit.lam = l; hit.s = s; }
-        }
+    int lo = t1 * kTile, n = kTile;
+    const bool multi = (b2 <= thr);
+    if (multi) {
+        if (b3 <= thr) return false;
+        lo -= kTile; n = 3 * kTile;
     }
+    unsigned long long mask = 0ull;
+    float adj = kBig;
+    for (int j = 0; j < n; ++j) {
+        const int s = lo + j;
+        if (s < 0 || s >= tb.S) continue;
+        const float d32 = eval32(tb, s, pxl, pyl);
+        if (d32 <= thr) mask |= (1ull << j);
+        if (multi && (j < kTile || j >= 2 * kTile)) adj = fminf(adj, d32);
+    }
+    if (multi && !(adj <= thr)) return false;      // the second tile is not a neighbour
+    hit.D = CUDART_INF; hit.lam = 0.0; hit.s = max(lo, 0);
+    while (mask) {
+        const int j = __ffsll((long long)mask) - 1;
+        mask &= mask - 1ull;
+        double D, l;
+        eval64(pn, lo + j, px, py, D, l);
+        if (D < hit.D) { hit.D = D; hit.lam = l; hit.s = lo + j; }
+    }
+    return true;
 }
 
 // Full rescan of every segment by one thread (queue-overflow fallback).
@@ -188,57 +213,67 @@ __device__ __forceinline__ void resolve_pixel_warp(const SegTable& tb, const dou
 
 // ------------------------------------------------------------------ the hot loop
 // Thread-owned pixel block: columns (px0, px1) x rows py[0..R).  Slot k = 2*r + c.
-// On return b1[k] = min_s D, t1[k] = tile holding it, b2[k] = second-smallest tile minimum.
+// On return b1[k] = min_s D, t1[k] = tile holding it, b2[k] / b3[k] = 2nd / 3rd smallest tile minimum.
 template <int R>
 __device__ __forceinline__ void scan_block(const SegTable& tb, float px0, float px1,
                                            const float (&py)[R],
-                                           float (&b1)[2 * R], int (&t1)[2 * R], float (&b2)[2 * R]) {
+                                           float (&b1)[2 * R], int (&t1)[2 * R], float (&b2)[2 * R],
+                                           float (&b3)[2 * R]) {
+    static_assert(R % 2 == 0, "rows are processed in pairs");
     const uint64_t px2 = pack2(px0, px1);
+    uint64_t y2[R / 2];
 #pragma unroll
-    for (int k = 0; k < 2 * R; ++k) { b1[k] = kBig; b2[k] = kBig; t1[k] = 0; }
+    for (int i = 0; i < R / 2; ++i) y2[i] = pack2(py[2 * i], py[2 * i + 1]);
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) { b1[k] = kBig; b2[k] = kBig; b3[k] = kBig; t1[k] = 0; }
     const int ntiles = tb.Spad / kTile;
     for (int tile = 0; tile < ntiles; ++tile) {
         float tm[2 * R];
 #pragma unroll
         for (int k = 0; k < 2 * R; ++k) tm[k] = kBig;
         const float4* __restrict__ A = tb.A + tile * kTile;
-        const float4* __restrict__ B = tb.B + tile * kTile;
         const float* __restrict__ H = tb.H + tile * kTile;
 #pragma unroll 2
         for (int j = 0; j < kTile; j += 2) {
-            const float4 a0 = A[j], c0 = B[j];
-            const float4 a1 = A[j + 1], c1 = B[j + 1];
-            const float h0 = H[j], h1 = H[j + 1];
-            const uint64_t ex0 = pack2(a0.x, a0.y), ey0 = pack2(a0.z, a0.w);
-            const uint64_t ex1 = pack2(a1.x, a1.y), ey1 = pack2(a1.z, a1.w);
-            const uint64_t P0 = ffma2(px2, ex0, pack2(c0.x, c0.y));
-            const uint64_t Q0 = ffma2(px2, ey0, pack2(c0.z, c0.w));
-            const uint64_t P1 = ffma2(px2, ex1, pack2(c1.x, c1.y));
-            const uint64_t Q1 = ffma2(px2, ey1, pack2(c1.z, c1.w));
+            const float4 a0 = A[j], a1 = A[j + 1];
+            const float2 hh = *reinterpret_cast<const float2*>(H + j);
+            // per column: P = px*ex - am, Q = px*ey - bm (both columns in one packed op)
+            float P0[2], Q0[2], P1[2], Q1[2];
+            unpack2(ffma2(px2, pack2(a0.x, a0.x), pack2(a0.z, a0.z)), P0[0], P0[1]);
+            unpack2(ffma2(px2, pack2(a0.y, a0.y), pack2(a0.w, a0.w)), Q0[0], Q0[1]);
+            unpack2(ffma2(px2, pack2(a1.x, a1.x), pack2(a1.z, a1.z)), P1[0], P1[1]);
+            unpack2(ffma2(px2, pack2(a1.y, a1.y), pack2(a1.w, a1.w)), Q1[0], Q1[1]);
+            const uint64_t ey0 = pack2(a0.y, a0.y), nex0 = pack2(-a0.x, -a0.x);
+            const uint64_t ey1 = pack2(a1.y, a1.y), nex1 = pack2(-a1.x, -a1.x);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint64_t y2 = pack2(py[r], py[r]);
-                const uint64_t ny2 = pack2(-py[r], -py[r]);
-                float al0, al1, bl0, bl1;
-                unpack2(ffma2(y2, ey0, P0), al0, al1);
-                unpack2(ffma2(y2, ey1, P1), bl0, bl1);
-                const uint64_t pe0 = ffma2(ny2, ex0, Q0);
-                const uint64_t pe1 = ffma2(ny2, ex1, Q1);
-                const float u0 = __saturatef(__fadd_rn(fabsf(al0), -h0));
-                const float u1 = __saturatef(__fadd_rn(fabsf(al1), -h0));
-                const float v0 = __saturatef(__fadd_rn(fabsf(bl0), -h1));
-                const float v1 = __saturatef(__fadd_rn(fabsf(bl1), -h1));
-                const uint64_t u2 = pack2(u0, u1), v2 = pack2(v0, v1);
-                float d00, d01, d10, d11;
-                unpack2(ffma2(u2, u2, fmul2(pe0, pe0)), d00, d01);
-                unpack2(ffma2(v2, v2, fmul2(pe1, pe1)), d10, d11);
-                tm[2 * r] = fminf(tm[2 * r], fminf(d00, d10));
-                tm[2 * r + 1] = fminf(tm[2 * r + 1], fminf(d01, d11));
+            for (int c = 0; c < 2; ++c) {
+                const uint64_t Pc0 = pack2(P0[c], P0[c]), Qc0 = pack2(Q0[c], Q0[c]);
+                const uint64_t Pc1 = pack2(P1[c], P1[c]), Qc1 = pack2(Q1[c], Q1[c]);
+#pragma unroll
+                for (int rp = 0; rp < R / 2; ++rp) {
+                    float al0, al1, bl0, bl1;
+                    unpack2(ffma2(y2[rp], ey0, Pc0), al0, al1);        // along, segment j,   rows 2rp, 2rp+1
+                    unpack2(ffma2(y2[rp], ey1, Pc1), bl0, bl1);        // along, segment j+1
+                    const uint64_t pe0 = ffma2(y2[rp], nex0, Qc0);     // perp
+                    const uint64_t pe1 = ffma2(y2[rp], nex1, Qc1);
+                    const float u0 = __saturatef(__fadd_rn(fabsf(al0), -hh.x));
+                    const float u1 = __saturatef(__fadd_rn(fabsf(al1), -hh.x));
+                    const float v0 = __saturatef(__fadd_rn(fabsf(bl0), -hh.y));
+                    const float v1 = __saturatef(__fadd_rn(fabsf(bl1), -hh.y));
+                    const uint64_t u2 = pack2(u0, u1), v2 = pack2(v0, v1);
+                    float d00, d01, d10, d11;
+                    unpack2(ffma2(u2, u2, fmul2(pe0, pe0)), d00, d01);
+                    unpack2(ffma2(v2, v2, fmul2(pe1, pe1)), d10, d11);
+                    const int k0 = (2 * rp) * 2 + c, k1 = (2 * rp + 1) * 2 + c;
+                    tm[k0] = fminf(tm[k0], fminf(d00, d10));
+                    tm[k1] = fminf(tm[k1], fminf(d01, d11));
+                }
             }
         }
 #pragma unroll
         for (int k = 0; k < 2 * R; ++k) {
             const bool better = tm[k] < b1[k];
+            b3[k] = fminf(b3[k], fmaxf(tm[k], b2[k]));
             b2[k] = fminf(b2[k], fmaxf(tm[k], b1[k]));
             t1[k] = better ? tile : t1[k];
             b1[k] = fminf(b1[k], tm[k]);
@@ -272,8 +307,7 @@ __device__ __forceinline__ double block_reduce_minmax(double v, bool is_max, dou
 // Destination buffers may live in shared or global memory.
 struct PrepOut {
     double2* pn;    // [nt]
-    float4* A;      // [Spad]
-    float4* B;      // [Spad]
+    float4* A;      // [Spad]  {ex, ey, -am, -bm}
     float* H;       // [Spad]
     float* pxs;     // [ntg]  scaled local pixel time coordinates
     float* pys;     // [nug]
@@ -339,7 +373,7 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
     const int Spad = ((S + kTile - 1) / kTile) * kTile;
     int degen = 0;
     for (int s = tid; s < Spad; s += nth) {
-        float4 A, B;
+        float4 A;
         float h;
         if (s < S) {
             const double2 a = o.pn[s], b = o.pn[s + 1];
@@ -351,15 +385,13 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
             const float fex = (float)exd, fey = (float)eyd;
             const float am = (float)(mx * exd + my * eyd);     // mid . e
             const float bm = (float)(mx * eyd - my * exd);     // perp' = px*ey - py*ex - bm
-            A = make_float4(fex, fex, fey, fey);
-            B = make_float4(-am, -am, -bm, -bm);
+            A = make_float4(fex, fey, -am, -bm);
             h = (float)(0.5 * len * sigma);
         } else {   // padding: along = -4 -> sat -> 1, perp = 2 -> D = kPadD
-            A = make_float4(0.f, 0.f, 0.f, 0.f);
-            B = make_float4(-4.f, -4.f, 2.f, 2.f);
+            A = make_float4(0.f, 0.f, -4.f, 2.f);
             h = 0.f;
         }
-        o.A[s] = A; o.B[s] = B; o.H[s] = h;
+        o.A[s] = A; o.H[s] = h;
     }
     for (int i = tid; i < ntg; i += nth)
         o.pxs[i] = (float)((lin_axis(T0, Ts, Tl, i, ntg) - ccx) * sigma);

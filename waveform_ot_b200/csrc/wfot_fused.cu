@@ -18,6 +18,8 @@
 // CalcWasserWaveform(deriv=True, returnmarg=True)).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "wfot_device.cuh"
 #include "wfot_host.h"
@@ -27,6 +29,44 @@ namespace wfot {
 
 constexpr int kFQCap = 1024;
 struct FQEntry { int pix; float b1; };
+
+
+// Shared-memory layout (byte offsets from the dynamic shared base).  Pointers are formed
+// from the `extern __shared__` symbol inside each kernel so the compiler keeps them in the
+// shared address space (LDS/STS instead of generic loads).
+struct SmemLayout {
+    int pn, A, H, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
+    int total;
+};
+
+__host__ __device__ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nmax) {
+    SmemLayout L;
+    int o = 0;
+    auto take = [&](int bytes) { const int at = o; o += (bytes + 15) & ~15; return at; };
+    L.pn = take(nt * 16);
+    L.A = take(Spad * 16);
+    L.margt = take(ntg_pad * 8);
+    L.margu = take(nug_pad * 8);
+    L.Rt = take(ntg_pad * 8);
+    L.Ru = take(nug_pad * 8);
+    L.xt = take(ntg_pad * 8);
+    L.xu = take(nug_pad * 8);
+    L.cf = take(nmax * 8);
+    L.E = take(nmax * 8);
+    L.tk = take(nmax * 16);
+    L.dx = take(nmax * 16);
+    L.red = take(64 * 8);
+    L.gbins = take(nt * 16);
+    L.hdr = take(128);
+    L.queue = take(kFQCap * (int)sizeof(FQEntry));
+    L.H = take(Spad * 4);
+    L.pxs = take(ntg_pad * 4);
+    L.pys = take(nug_pad * 4);
+    L.posf = take(nmax * 4);
+    L.qcount = take(16);
+    L.total = o;
+    return L;
+}
 
 struct FusedArgs {
     const void* t; const void* w; int dtype; long long t_stride; int nt;
@@ -39,61 +79,36 @@ struct FusedArgs {
     double* s_pdf; double* s_wa; double* s_wb; int32_t* s_idx;
     int32_t* status;
     int Spad, ntg_pad, nug_pad, nmax;
+    SmemLayout L;
 };
 
-struct FusedSmem {
-    double2* pn; float4* A; float4* B; float* H; float* pxs; float* pys;
-    double* margt; double* margu; double* Rt; double* Ru; double* xt; double* xu;
-    double* cf; double* tk; double* dx; double* E; double* red; double* gbins;
-    int* posf; FQEntry* queue; WinHdr* hdr; int* qcount;
-};
-
-__host__ __device__ inline size_t fused_smem_bytes(int nt, int Spad, int ntg_pad, int nug_pad, int nmax) {
-    size_t s = 0;
-    s += (size_t)nt * 16;                 // pn
-    s += (size_t)Spad * 36;               // A, B, H
-    s += (size_t)(ntg_pad + nug_pad) * 4; // pxs, pys
-    s += (size_t)(ntg_pad + nug_pad) * 8 * 3;   // marg, R, x
-    s += (size_t)nmax * 8 * 2 + (size_t)(2 * nmax) * 8 * 2;   // cf, E, tk, dx
-    s += 64 * 8;                          // red
-    s += (size_t)2 * nt * 8;              // gbins
-    s += (size_t)nmax * 4;                // posf
-    s += (size_t)kFQCap * sizeof(FQEntry);
-    s += 128 + 16;                        // hdr, qcount
-    return s + 64;
-}
-
-__device__ __forceinline__ FusedSmem carve(unsigned char* p, const FusedArgs& a) {
-    FusedSmem s;
-    s.pn = (double2*)p;      p += (size_t)a.nt * 16;
-    s.A = (float4*)p;        p += (size_t)a.Spad * 16;
-    s.B = (float4*)p;        p += (size_t)a.Spad * 16;
-    s.margt = (double*)p;    p += (size_t)a.ntg_pad * 8;
-    s.margu = (double*)p;    p += (size_t)a.nug_pad * 8;
-    s.Rt = (double*)p;       p += (size_t)a.ntg_pad * 8;
-    s.Ru = (double*)p;       p += (size_t)a.nug_pad * 8;
-    s.xt = (double*)p;       p += (size_t)a.ntg_pad * 8;
-    s.xu = (double*)p;       p += (size_t)a.nug_pad * 8;
-    s.cf = (double*)p;       p += (size_t)a.nmax * 8;
-    s.E = (double*)p;        p += (size_t)a.nmax * 8;
-    s.tk = (double*)p;       p += (size_t)a.nmax * 16;
-    s.dx = (double*)p;       p += (size_t)a.nmax * 16;
-    s.red = (double*)p;      p += 64 * 8;
-    s.gbins = (double*)p;    p += (size_t)a.nt * 16;
-    s.hdr = (WinHdr*)p;      p += 128;
-    s.queue = (FQEntry*)p;   p += (size_t)kFQCap * sizeof(FQEntry);
-    s.H = (float*)p;         p += (size_t)a.Spad * 4;
-    s.pxs = (float*)p;       p += (size_t)a.ntg_pad * 4;
-    s.pys = (float*)p;       p += (size_t)a.nug_pad * 4;
-    s.posf = (int*)p;        p += (size_t)a.nmax * 4;
-    s.qcount = (int*)p;
-    return s;
-}
+#define WFOT_SMEM_POINTERS(L)                                                            \
+    double2* const s_pn = reinterpret_cast<double2*>(smem_raw + (L).pn);                 \
+    float4* const s_A = reinterpret_cast<float4*>(smem_raw + (L).A);                     \
+    float* const s_H = reinterpret_cast<float*>(smem_raw + (L).H);                       \
+    float* const s_pxs = reinterpret_cast<float*>(smem_raw + (L).pxs);                   \
+    float* const s_pys = reinterpret_cast<float*>(smem_raw + (L).pys);                   \
+    double* const s_margt = reinterpret_cast<double*>(smem_raw + (L).margt);             \
+    double* const s_margu = reinterpret_cast<double*>(smem_raw + (L).margu);             \
+    double* const s_Rt = reinterpret_cast<double*>(smem_raw + (L).Rt);                   \
+    double* const s_Ru = reinterpret_cast<double*>(smem_raw + (L).Ru);                   \
+    double* const s_xt = reinterpret_cast<double*>(smem_raw + (L).xt);                   \
+    double* const s_xu = reinterpret_cast<double*>(smem_raw + (L).xu);                   \
+    double* const s_cf = reinterpret_cast<double*>(smem_raw + (L).cf);                   \
+    double* const s_E = reinterpret_cast<double*>(smem_raw + (L).E);                     \
+    double* const s_tk = reinterpret_cast<double*>(smem_raw + (L).tk);                   \
+    double* const s_dx = reinterpret_cast<double*>(smem_raw + (L).dx);                   \
+    double* const s_red = reinterpret_cast<double*>(smem_raw + (L).red);                 \
+    double* const s_gbins = reinterpret_cast<double*>(smem_raw + (L).gbins);             \
+    int* const s_posf = reinterpret_cast<int*>(smem_raw + (L).posf);                     \
+    FQEntry* const s_queue = reinterpret_cast<FQEntry*>(smem_raw + (L).queue);           \
+    WinHdr* const s_hdr = reinterpret_cast<WinHdr*>(smem_raw + (L).hdr);                 \
+    int* const s_qcount = reinterpret_cast<int*>(smem_raw + (L).qcount)
 
 // pixel -> scratch: density and the two gradient weights of its nearest segment
-__device__ __forceinline__ void store_pixel(const FusedArgs& a, const FusedSmem& sm, size_t slab,
+__device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* pn, size_t slab,
                                             int it, int iu, const PixelHit& hit, double py, int& zero_dist) {
-    const PixelVals v = pixel_values(sm.pn, hit, py, a.lambda, a.q);
+    const PixelVals v = pixel_values(pn, hit, py, a.lambda, a.q);
     const size_t k = slab + (size_t)iu * a.ntg + it;
     double wgt = v.pdf * v.g;                                  // pdf * dddx_y (FingerprintLib.py:355)
     if (a.q == 2) wgt *= 2.0 * fabs(v.d);                      // :214-217
@@ -105,30 +120,31 @@ __device__ __forceinline__ void store_pixel(const FusedArgs& a, const FusedSmem&
 }
 
 template <int R>
-__global__ void __launch_bounds__(256) k_misfit_grad(FusedArgs a) {
+__global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const FusedSmem sm = carve(smem_raw, a);
+    WFOT_SMEM_POINTERS(a.L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     const size_t slab = (size_t)blockIdx.x * npix;
     const int ncp = (a.ntg + 1) >> 1, nrg = (a.nug + R - 1) / R, nblk = ncp * nrg;
-    const SegTable tb{sm.A, sm.B, sm.H, S, a.Spad};
+    const SegTable tb{s_A, s_H, S, a.Spad};
     int zero_dist = 0, slow = 0, common = 0, degen = 0;
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         // ---------------- P0: window -> shared memory
         const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
-        if (tid == 0) { sm.hdr->degenerate = 0; *sm.qcount = 0; }
+        if (tid == 0) { s_hdr->degenerate = 0; *s_qcount = 0; }
         __syncthreads();
-        PrepOut po{sm.pn, sm.A, sm.B, sm.H, sm.pxs, sm.pys, sm.hdr};
+        PrepOut po{s_pn, s_A, s_H, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
-                    a.nug, a.ntg, a.transform, po, sm.red, nullptr);
+                    a.nug, a.ntg, a.transform, po, s_red, nullptr);
         __syncthreads();
-        const WinHdr hdr = *sm.hdr;
+        const WinHdr hdr = *s_hdr;
         degen += (tid == 0) ? hdr.degenerate : 0;
-        for (int i = tid; i < a.ntg; i += 256) sm.xt[i] = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, i, a.ntg);
-        for (int i = tid; i < a.nug; i += 256) sm.xu[i] = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, i, a.nug);
-        for (int j = tid; j < 2 * a.nt; j += 256) sm.gbins[j] = 0.0;
+        for (int i = tid; i < a.ntg; i += 256) s_xt[i] = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, i, a.ntg);
+        for (int i = tid; i < a.nug; i += 256) s_xu[i] = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, i, a.nug);
+        for (int j = tid; j < 2 * a.nt; j += 256) s_gbins[j] = 0.0;
+        __syncthreads();
 
         // ---------------- P1: nearest segment per pixel
         for (int blk = tid; blk < nblk; blk += 256) {
@@ -136,83 +152,92 @@ __global__ void __launch_bounds__(256) k_misfit_grad(FusedArgs a) {
             const int it0 = 2 * cp, it1 = min(2 * cp + 1, a.ntg - 1);
             float py[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) py[r] = sm.pys[min(rg * R + r, a.nug - 1)];
-            float b1[2 * R], b2[2 * R];
+            for (int r = 0; r < R; ++r) py[r] = s_pys[min(rg * R + r, a.nug - 1)];
+            float b1[2 * R], b2[2 * R], b3[2 * R];
             int t1[2 * R];
-            scan_block<R>(tb, sm.pxs[it0], sm.pxs[it1], py, b1, t1, b2);
-            float lb1[2 * R], lb2[2 * R];
+            scan_block<R>(tb, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3);
+            float lb1[2 * R], lb2[2 * R], lb3[2 * R];
             int lt1[2 * R];
 #pragma unroll
-            for (int k = 0; k < 2 * R; ++k) { lb1[k] = b1[k]; lb2[k] = b2[k]; lt1[k] = t1[k]; }
+            for (int k = 0; k < 2 * R; ++k) { lb1[k] = b1[k]; lb2[k] = b2[k]; lb3[k] = b3[k]; lt1[k] = t1[k]; }
 #pragma unroll 1
             for (int k = 0; k < 2 * R; ++k) {
                 const int it = 2 * cp + (k & 1), iu = rg * R + (k >> 1);
                 if (it >= a.ntg || iu >= a.nug) continue;
                 const float kb1 = lb1[k];
-                const double pyd = sm.xu[iu];
+                const double pyd = s_xu[iu];
                 PixelHit hit;
-                if (lb2[k] <= kb1 + tau32(kb1)) {
-                    const int qi = atomicAdd(sm.qcount, 1);
-                    if (qi < kFQCap) { sm.queue[qi] = FQEntry{iu * a.ntg + it, kb1}; continue; }
+                if (!resolve_pixel(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, kb1, lt1[k], lb2[k], lb3[k], hit)) {
+                    const int qi = atomicAdd(s_qcount, 1);
+                    if (qi < kFQCap) { s_queue[qi] = FQEntry{iu * a.ntg + it, kb1}; continue; }
                     ++slow;
-                    resolve_pixel_full(tb, sm.pn, sm.pxs[it], sm.pys[iu], sm.xt[it], pyd, kb1, hit);
-                } else {
-                    resolve_pixel(tb, sm.pn, sm.pxs[it], sm.pys[iu], sm.xt[it], pyd, kb1, lt1[k], hit);
+                    resolve_pixel_full(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, kb1, hit);
                 }
-                store_pixel(a, sm, slab, it, iu, hit, pyd, zero_dist);
+                store_pixel(a, s_pn, slab, it, iu, hit, pyd, zero_dist);
             }
         }
         __syncthreads();
         {
-            const int nq = min(*sm.qcount, kFQCap);
+            const int nq = min(*s_qcount, kFQCap);
             for (int e = warp; e < nq; e += 8) {
-                const FQEntry qe = sm.queue[e];
+                const FQEntry qe = s_queue[e];
                 const int it = qe.pix % a.ntg, iu = qe.pix / a.ntg;
                 PixelHit hit;
-                resolve_pixel_warp(tb, sm.pn, sm.pxs[it], sm.pys[iu], sm.xt[it], sm.xu[iu], qe.b1, hit);
-                if (lane == 0) { store_pixel(a, sm, slab, it, iu, hit, sm.xu[iu], zero_dist); ++slow; }
+                resolve_pixel_warp(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], s_xu[iu], qe.b1, hit);
+                if (lane == 0) { store_pixel(a, s_pn, slab, it, iu, hit, s_xu[iu], zero_dist); ++slow; }
             }
         }
         __syncthreads();   // scratch slab complete (block-scope visibility of global writes)
 
-        // ---------------- P2: marginals of the normalised density
+        // ---------------- P2: marginals of the normalised density (fixed summation order;
+        //                  8 independent loads in flight per thread)
         double part = 0.0;
         for (int c = tid; c < a.ntg; c += 256) {
+            const double* col = a.s_pdf + slab + c;
             double s0 = 0.0;
-            for (int iu = 0; iu < a.nug; ++iu) s0 += a.s_pdf[slab + (size_t)iu * a.ntg + c];
-            sm.margt[c] = s0;
+            int iu = 0;
+            for (; iu + 8 <= a.nug; iu += 8) {
+                double v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldcg(col + (size_t)(iu + j) * a.ntg);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s0 += v[j];
+            }
+            for (; iu < a.nug; ++iu) s0 += __ldcg(col + (size_t)iu * a.ntg);
+            s_margt[c] = s0;
             part += s0;
         }
-        const double A = block_sum(part, sm.red);                       // OTpdf.amp (OTlib.py:92)
+        const double A = block_sum(part, s_red);                        // OTpdf.amp (OTlib.py:92)
         for (int iu = warp; iu < a.nug; iu += 8) {
+            const double* row = a.s_pdf + slab + (size_t)iu * a.ntg;
             double s0 = 0.0;
-            for (int c = lane; c < a.ntg; c += 32) s0 += a.s_pdf[slab + (size_t)iu * a.ntg + c];
+            for (int c = lane; c < a.ntg; c += 32) s0 += __ldcg(row + c);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-            if (lane == 0) sm.margu[iu] = s0 / A;                       // OTlib.py:93,156
+            if (lane == 0) s_margu[iu] = s0 / A;                        // OTlib.py:93,156
         }
-        for (int c = tid; c < a.ntg; c += 256) sm.margt[c] = sm.margt[c] / A;   // OTlib.py:93,155
+        for (int c = tid; c < a.ntg; c += 256) s_margt[c] = s_margt[c] / A;     // OTlib.py:93,155
         __syncthreads();
 
         // ---------------- P3: 1-D OT per marginal
         const size_t trow = a.tgt_per_window ? (size_t)b : 0;
-        OtScratch sc{sm.cf, sm.tk, sm.dx, sm.E, sm.posf, sm.red};
-        for (int c = tid; c < a.ntg; c += 256) sm.cf[c] = sm.margt[c];
+        OtScratch sc{s_cf, s_tk, s_dx, s_E, s_posf, s_red};
+        for (int c = tid; c < a.ntg; c += 256) s_cf[c] = s_margt[c];
         __syncthreads();
-        const OtResult rt = block_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, a.ntg, sm.xt,
+        const OtResult rt = block_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, a.ntg, s_xt,
                                        a.tgt_x_t + trow * a.ntg, a.pmask,
-                                       (a.pmask & 1) ? sm.Rt : nullptr, (a.pmask & 2) ? sm.Rt : nullptr, nullptr);
+                                       (a.pmask & 1) ? s_Rt : nullptr, (a.pmask & 2) ? s_Rt : nullptr, nullptr);
         double gp = 0.0;
-        for (int c = tid; c < a.ntg; c += 256) gp += sm.margt[c] * sm.Rt[c];
-        const double Gt = block_sum(gp, sm.red);                        // <dwpmargX, pbar> (OTlib.py:1144)
-        for (int c = tid; c < a.nug; c += 256) sm.cf[c] = sm.margu[c];
+        for (int c = tid; c < a.ntg; c += 256) gp += s_margt[c] * s_Rt[c];
+        const double Gt = block_sum(gp, s_red);                         // <dwpmargX, pbar> (OTlib.py:1144)
+        for (int c = tid; c < a.nug; c += 256) s_cf[c] = s_margu[c];
         __syncthreads();
-        const OtResult ru = block_ot1d(sc, a.nug, a.tgt_cdf_u + trow * a.nug, a.nug, sm.xu,
+        const OtResult ru = block_ot1d(sc, a.nug, a.tgt_cdf_u + trow * a.nug, a.nug, s_xu,
                                        a.tgt_x_u + trow * a.nug, a.pmask,
-                                       (a.pmask & 1) ? sm.Ru : nullptr, (a.pmask & 2) ? sm.Ru : nullptr, nullptr);
+                                       (a.pmask & 1) ? s_Ru : nullptr, (a.pmask & 2) ? s_Ru : nullptr, nullptr);
         gp = 0.0;
-        for (int c = tid; c < a.nug; c += 256) gp += sm.margu[c] * sm.Ru[c];
-        const double Gu = block_sum(gp, sm.red);                        // OTlib.py:1145
+        for (int c = tid; c < a.nug; c += 256) gp += s_margu[c] * s_Ru[c];
+        const double Gu = block_sum(gp, s_red);                         // OTlib.py:1145
         common += (tid == 0) ? (rt.common + ru.common) : 0;
         if (tid == 0) {
             a.W[2 * (size_t)b] = (a.pmask & 1) ? rt.W1 : rt.W2;
@@ -222,27 +247,39 @@ __global__ void __launch_bounds__(256) k_misfit_grad(FusedArgs a) {
 
         // ---------------- P4: gradient assembly (FingerprintLib.py:205-228)
         if (a.grad) {
+            // chain vectors: (R - <R, pbar>)/A  (OTlib.py:1144-1147)
+            for (int c = tid; c < a.ntg; c += 256) s_Rt[c] = (s_Rt[c] - Gt) / A;
+            for (int c = tid; c < a.nug; c += 256) s_Ru[c] = (s_Ru[c] - Gu) / A;
+            __syncthreads();
             for (int c = tid; c < a.ntg; c += 256) {
-                const double ct = (sm.Rt[c] - Gt) / A;                   // dwpmargX (OTlib.py:1144,1146)
+                const double ct = s_Rt[c];
                 int cur = -1;
                 double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
-                for (int iu = 0; iu < a.nug; ++iu) {
-                    const size_t k = slab + (size_t)iu * a.ntg + c;
-                    const int i = a.s_idx[k];
-                    if (i != cur) {
-                        if (cur >= 0) {
-                            atomicAdd(&sm.gbins[cur], t0); atomicAdd(&sm.gbins[cur + 1], t1);
-                            atomicAdd(&sm.gbins[a.nt + cur], u0); atomicAdd(&sm.gbins[a.nt + cur + 1], u1);
-                        }
-                        cur = i; t0 = t1 = u0 = u1 = 0.0;
+                for (int iu0 = 0; iu0 < a.nug; iu0 += 4) {
+                    int idx[4];
+                    double wa[4], wb[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const size_t k = slab + (size_t)min(iu0 + j, a.nug - 1) * a.ntg + c;
+                        idx[j] = __ldcg(a.s_idx + k); wa[j] = __ldcg(a.s_wa + k); wb[j] = __ldcg(a.s_wb + k);
                     }
-                    const double cu = (sm.Ru[iu] - Gu) / A;              // dwpmargY (OTlib.py:1145,1147)
-                    const double wa = a.s_wa[k], wb = a.s_wb[k];
-                    t0 += wa * ct; t1 += wb * ct; u0 += wa * cu; u1 += wb * cu;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (iu0 + j >= a.nug) break;
+                        if (idx[j] != cur) {
+                            if (cur >= 0) {
+                                atomicAdd(&s_gbins[cur], t0); atomicAdd(&s_gbins[cur + 1], t1);
+                                atomicAdd(&s_gbins[a.nt + cur], u0); atomicAdd(&s_gbins[a.nt + cur + 1], u1);
+                            }
+                            cur = idx[j]; t0 = t1 = u0 = u1 = 0.0;
+                        }
+                        const double cu = s_Ru[iu0 + j];
+                        t0 += wa[j] * ct; t1 += wb[j] * ct; u0 += wa[j] * cu; u1 += wb[j] * cu;
+                    }
                 }
                 if (cur >= 0) {
-                    atomicAdd(&sm.gbins[cur], t0); atomicAdd(&sm.gbins[cur + 1], t1);
-                    atomicAdd(&sm.gbins[a.nt + cur], u0); atomicAdd(&sm.gbins[a.nt + cur + 1], u1);
+                    atomicAdd(&s_gbins[cur], t0); atomicAdd(&s_gbins[cur + 1], t1);
+                    atomicAdd(&s_gbins[a.nt + cur], u0); atomicAdd(&s_gbins[a.nt + cur + 1], u1);
                 }
             }
             __syncthreads();
@@ -254,8 +291,8 @@ __global__ void __launch_bounds__(256) k_misfit_grad(FusedArgs a) {
                     const double up = ((wj - hdr.u0raw) + (wj - hdr.u1raw)) / (hdr.u1raw - hdr.u0raw);
                     chain *= 2.0 / ((hdr.u1raw - hdr.u0raw) * CUDART_PI * (1.0 + up * up));
                 }
-                a.grad[((size_t)b * 2) * a.nt + j] = sm.gbins[j] * chain;
-                a.grad[((size_t)b * 2 + 1) * a.nt + j] = sm.gbins[a.nt + j] * chain;
+                a.grad[((size_t)b * 2) * a.nt + j] = s_gbins[j] * chain;
+                a.grad[((size_t)b * 2 + 1) * a.nt + j] = s_gbins[a.nt + j] * chain;
             }
         }
         __syncthreads();
@@ -268,13 +305,64 @@ __global__ void __launch_bounds__(256) k_misfit_grad(FusedArgs a) {
     }
 }
 
-static int fused_resident_ctas(size_t smem, int* per_sm_out) {
+// ------------------------------------------------------------------ scan-only probe
+// prep_window + scan_block, nothing else: FP32 nearest distance per pixel (no FP64 resolve).
+// Used by bench.py to attribute time between the brute-force scan and the epilogues.
+template <int R>
+__global__ void __launch_bounds__(256, 2) k_scan_probe(FusedArgs a, float* out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WFOT_SMEM_POINTERS(a.L);
+    const int tid = threadIdx.x, S = a.nt - 1;
+    const int ncp = (a.ntg + 1) >> 1, nrg = (a.nug + R - 1) / R, nblk = ncp * nrg;
+    const SegTable tb{s_A, s_H, S, a.Spad};
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
+        if (tid == 0) s_hdr->degenerate = 0;
+        __syncthreads();
+        PrepOut po{s_pn, s_A, s_H, s_pxs, s_pys, s_hdr};
+        prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
+                    a.nug, a.ntg, 0, po, s_red, nullptr);
+        __syncthreads();
+        const float inv_sigma = (float)(1.0 / s_hdr->sigma);
+        for (int blk = tid; blk < nblk; blk += 256) {
+            const int cp = blk % ncp, rg = blk / ncp;
+            const int it0 = 2 * cp, it1 = min(2 * cp + 1, a.ntg - 1);
+            float py[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) py[r] = s_pys[min(rg * R + r, a.nug - 1)];
+            float b1[2 * R], b2[2 * R], b3[2 * R];
+            int t1[2 * R];
+            scan_block<R>(tb, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3);
+#pragma unroll
+            for (int k = 0; k < 2 * R; ++k) {
+                const int it = 2 * cp + (k & 1), iu = rg * R + (k >> 1);
+                if (it < a.ntg && iu < a.nug)
+                    out[((size_t)b * a.nug + iu) * a.ntg + it] = sqrtf(b1[k]) * inv_sigma + 0.f * (b2[k] + b3[k] + t1[k]);
+            }
+        }
+        __syncthreads();
+        (void)s_margt; (void)s_margu; (void)s_Rt; (void)s_Ru; (void)s_xt; (void)s_xu; (void)s_cf; (void)s_E;
+        (void)s_tk; (void)s_dx; (void)s_gbins; (void)s_posf; (void)s_queue; (void)s_qcount;
+    }
+}
+
+// Rows per thread-owned pixel block (2 columns x R rows).  R = 8 halves the per-segment
+// set-up work per pixel; R = 4 halves the register footprint.  WFOT_DEV_R overrides (tuning aid).
+static int rows_per_thread() {
+    const char* e = getenv("WFOT_DEV_R");
+    if (e && e[0] == '4') return 4;
+    if (e && e[0] == '8') return 8;
+    return 8;
+}
+
+template <typename K>
+static int resident_ctas(K kernel, size_t smem, int* per_sm_out) {
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(k_misfit_grad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_misfit_grad<8>, 256, smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess) return -1;
     if (per_sm < 1) return -1;
     if (per_sm_out) *per_sm_out = per_sm;
     return sms * per_sm;
@@ -317,10 +405,12 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     a.status = status;
     a.Spad = seg_pad(nt); a.ntg_pad = pad4(ntg); a.nug_pad = pad4(nug);
     a.nmax = pad4(ntg > nug ? ntg : nug);
-    const size_t smem = fused_smem_bytes(nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax);
+    a.L = make_layout(nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax);
+    const size_t smem = (size_t)a.L.total;
     if (smem > 227 * 1024) return WFOT_ERR_UNSUPPORTED;
     int per_sm = 0;
-    int ctas = fused_resident_ctas(smem, &per_sm);
+    const int R = rows_per_thread();
+    int ctas = (R == 4) ? resident_ctas(k_misfit_grad<4>, smem, &per_sm) : resident_ctas(k_misfit_grad<8>, smem, &per_sm);
     if (ctas < 1) return cuda_fail(cudaGetLastError(), "k_misfit_grad occupancy");
     if (ctas > B) ctas = B;
     const size_t npix = (size_t)nug * ntg;
@@ -334,9 +424,36 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     a.s_wa = (double*)p;    p += (size_t)ctas * npix * 8;
     a.s_wb = (double*)p;    p += (size_t)ctas * npix * 8;
     a.s_idx = (int32_t*)p;
-    k_misfit_grad<8><<<ctas, 256, smem, stream>>>(a);
+    if (R == 4) k_misfit_grad<4><<<ctas, 256, smem, stream>>>(a);
+    else k_misfit_grad<8><<<ctas, 256, smem, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_misfit_grad_batch launch");
+    return WFOT_OK;
+}
+
+int wfot_scan_probe(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
+                    const wfot_grid* grids, int n_grids, int B, int nug, int ntg, float* dist32,
+                    void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!t || !w || !grids || !dist32 || B <= 0 || nt < 2 || nug < 1 || ntg < 1) return WFOT_ERR_INVALID_ARG;
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.t = t; a.w = w; a.dtype = in_dtype; a.t_stride = t_stride; a.nt = nt; a.grids = grids;
+    a.n_grids = n_grids; a.B = B; a.nug = nug; a.ntg = ntg;
+    a.Spad = seg_pad(nt); a.ntg_pad = pad4(ntg); a.nug_pad = pad4(nug);
+    a.nmax = pad4(ntg > nug ? ntg : nug);
+    a.L = make_layout(nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax);
+    const size_t smem = (size_t)a.L.total;
+    if (smem > 227 * 1024) return WFOT_ERR_UNSUPPORTED;
+    int per_sm = 0;
+    const int R = rows_per_thread();
+    int ctas = (R == 4) ? resident_ctas(k_scan_probe<4>, smem, &per_sm) : resident_ctas(k_scan_probe<8>, smem, &per_sm);
+    if (ctas < 1) return cuda_fail(cudaGetLastError(), "k_scan_probe occupancy");
+    if (ctas > B) ctas = B;
+    if (R == 4) k_scan_probe<4><<<ctas, 256, smem, stream>>>(a, dist32);
+    else k_scan_probe<8><<<ctas, 256, smem, stream>>>(a, dist32);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_scan_probe launch");
     return WFOT_OK;
 }
 

@@ -14,8 +14,7 @@ constexpr int kFpChunk = 2048;   // windows prepared + scanned per launch pair (
 struct FpWorkspace {
     WinHdr* hdr;     // [chunk]
     double2* pn;     // [chunk][nt]
-    float4* A;       // [chunk][Spad]
-    float4* B;       // [chunk][Spad]
+    float4* A;       // [chunk][Spad]  {ex, ey, -am, -bm}
     float* H;        // [chunk][Spad]
     float* pxs;      // [chunk][ntg_pad]
     float* pys;      // [chunk][nug_pad]
@@ -27,7 +26,7 @@ inline int pad4(int n) { return (n + 3) & ~3; }
 
 inline size_t fp_workspace_per_window(int nt, int nug, int ntg) {
     const size_t Spad = (size_t)seg_pad(nt);
-    return 128 + (size_t)nt * 16 + Spad * 36 + (size_t)(pad4(ntg) + pad4(nug)) * 4;
+    return 128 + (size_t)nt * 16 + Spad * 20 + (size_t)(pad4(ntg) + pad4(nug)) * 4;
 }
 
 inline FpWorkspace fp_workspace_carve(void* base, int chunk, int nt, int nug, int ntg) {
@@ -39,7 +38,6 @@ inline FpWorkspace fp_workspace_carve(void* base, int chunk, int nt, int nug, in
     ws.hdr = (WinHdr*)p;   p += (size_t)chunk * 128;
     ws.pn = (double2*)p;   p += (size_t)chunk * nt * 16;
     ws.A = (float4*)p;     p += (size_t)chunk * ws.Spad * 16;
-    ws.B = (float4*)p;     p += (size_t)chunk * ws.Spad * 16;
     ws.H = (float*)p;      p += (size_t)chunk * ws.Spad * 4;
     ws.pxs = (float*)p;    p += (size_t)chunk * ws.ntg_pad * 4;
     ws.pys = (float*)p;

@@ -38,7 +38,6 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs a) {
     PrepOut o;
     o.pn = a.ws.pn + (size_t)wl * a.nt;
     o.A = a.ws.A + (size_t)wl * a.ws.Spad;
-    o.B = a.ws.B + (size_t)wl * a.ws.Spad;
     o.H = a.ws.H + (size_t)wl * a.ws.Spad;
     o.pxs = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
     o.pys = a.ws.pys + (size_t)wl * a.ws.nug_pad;
@@ -88,8 +87,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     const long long b = a.b0 + wl;
     const int Spad = a.ws.Spad, S = a.nt - 1;
     float4* sA = reinterpret_cast<float4*>(smem_raw);
-    float4* sB = sA + Spad;
-    float* sH = reinterpret_cast<float*>(sB + Spad);
+    float* sH = reinterpret_cast<float*>(sA + Spad);
     float* sPx = sH + Spad;
     float* sPy = sPx + a.ws.ntg_pad;
     QEntry* queue = reinterpret_cast<QEntry*>(sPy + a.ws.nug_pad);
@@ -98,9 +96,8 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     const int tid = threadIdx.x;
     {   // stage the window's segment table (contiguous, 16-byte vector copies)
         const float4* gA = a.ws.A + (size_t)wl * Spad;
-        const float4* gB = a.ws.B + (size_t)wl * Spad;
         const float* gH = a.ws.H + (size_t)wl * Spad;
-        for (int i = tid; i < Spad; i += 256) { sA[i] = gA[i]; sB[i] = gB[i]; sH[i] = gH[i]; }
+        for (int i = tid; i < Spad; i += 256) { sA[i] = gA[i]; sH[i] = gH[i]; }
         const float* gx = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
         const float* gy = a.ws.pys + (size_t)wl * a.ws.nug_pad;
         for (int i = tid; i < a.ntg; i += 256) sPx[i] = gx[i];
@@ -109,7 +106,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     }
     __syncthreads();
     const double2* pn = a.ws.pn + (size_t)wl * a.nt;
-    SegTable tb{sA, sB, sH, S, Spad};
+    SegTable tb{sA, sH, S, Spad};
     const int ncp = (a.ntg + 1) >> 1, nrg = (a.nug + R - 1) / R;
     const int blk = blockIdx.x * 256 + tid;
     int zero_dist = 0, slow = 0;
@@ -119,15 +116,15 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
         float py[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) py[r] = sPy[min(rg * R + r, a.nug - 1)];
-        float b1[2 * R], b2[2 * R];
+        float b1[2 * R], b2[2 * R], b3[2 * R];
         int t1[2 * R];
-        scan_block<R>(tb, sPx[it0], sPx[it1], py, b1, t1, b2);
+        scan_block<R>(tb, sPx[it0], sPx[it1], py, b1, t1, b2, b3);
         // The epilogue is deliberately NOT unrolled (FP64 division/exp per pixel would
         // multiply the code size by 2R); the scan results move to local arrays first.
-        float lb1[2 * R], lb2[2 * R];
+        float lb1[2 * R], lb2[2 * R], lb3[2 * R];
         int lt1[2 * R];
 #pragma unroll
-        for (int k = 0; k < 2 * R; ++k) { lb1[k] = b1[k]; lb2[k] = b2[k]; lt1[k] = t1[k]; }
+        for (int k = 0; k < 2 * R; ++k) { lb1[k] = b1[k]; lb2[k] = b2[k]; lb3[k] = b3[k]; lt1[k] = t1[k]; }
 #pragma unroll 1
         for (int k = 0; k < 2 * R; ++k) {
             const int it = 2 * cp + (k & 1), iu = rg * R + (k >> 1);
@@ -136,13 +133,11 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
             const double px = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, it, a.ntg);
             const double pyd = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, iu, a.nug);
             PixelHit hit;
-            if (lb2[k] <= kb1 + tau32(kb1)) {   // another tile within rounding distance
-                const int qi = atomicAdd(&qcount, 1);
+            if (!resolve_pixel(tb, pn, sPx[it], sPy[iu], px, pyd, kb1, lt1[k], lb2[k], lb3[k], hit)) {
+                const int qi = atomicAdd(&qcount, 1);   // far-apart near-tie: all-segment rescan
                 if (qi < kQCap) { queue[qi] = QEntry{it, iu, kb1, 0.f}; continue; }
                 ++slow;
                 resolve_pixel_full(tb, pn, sPx[it], sPy[iu], px, pyd, kb1, hit);
-            } else {
-                resolve_pixel(tb, pn, sPx[it], sPy[iu], px, pyd, kb1, lt1[k], hit);
             }
             emit_pixel(a, pn, hdr, b, it, iu, hit, pyd, zero_dist);
         }
@@ -435,7 +430,7 @@ int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long
     if (chunk > kFpChunk) chunk = kFpChunk;
     FpWorkspace ws = fp_workspace_carve((void*)base, chunk, nt, nug, ntg);
     constexpr int R = 8;
-    const size_t smem = (size_t)ws.Spad * 36 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
+    const size_t smem = (size_t)ws.Spad * 20 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
     if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(k_fingerprint<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_fingerprint)");
