@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- waveform-pair W2 misfit + gradient evaluations per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], "cfg5"): synthetic waveform windows of 1024 samples onto
+256 x 256 fingerprint grids, lambda = 0.04, W2 per marginal + d/d(waveform) + d/d(origin time)
+against one shared observed window.  A step = one pass of the fused hot path over one batch
+of `--batch` windows PER GPU (weak scaling: the 4 M-window sweep of the config is 4M/batch
+such steps), followed by the local reduction to [sum misfit, sum gradient] and - for N > 1 -
+the single NCCL allreduce of that vector.
+
+One JSON line is printed by rank 0 (see README / the task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NT, NUG, NTG, LAM = 1024, 256, 256, 0.04
+GRID = (0.0, 1.0, -1.3, 1.3, NUG, NTG)
+ALG_FLOP_PER_PAIR = 15.0                      # brute-force Enumerate count
+ALG_FLOP_PER_WINDOW = ALG_FLOP_PER_PAIR * NUG * NTG * (NT - 1)
+METRIC = "waveform-pair W2 misfit+grad evals/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4736, help="windows per GPU per step (32 per SM)")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="windows timed for cpu_baseline (N=1, rank 0)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+                for n, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------- synthetic input
+def make_windows_device(nb, nt, seed, device):
+    """cfg5 input rule on the device: cumulative-sum random walk, moving average 8,
+    mean removed, scaled to max|w| = 1, float32."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    x = torch.randn((nb, nt + 7), generator=g, device=device, dtype=torch.float32).cumsum(dim=1)
+    y = torch.nn.functional.avg_pool1d(x[:, None, :], kernel_size=8, stride=1)[:, 0, :]
+    y = y - y.mean(dim=1, keepdim=True)
+    y = y / y.abs().amax(dim=1, keepdim=True)
+    return y.contiguous()
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle port)
+def _cpu_one(args):
+    from oracle import wfot_oracle as O
+    t, w, tgt = args
+    t0 = time.perf_counter()
+    O.misfit_grad_window(t, w, GRID, tgt, lambdav=LAM, distfunc="W2", chunk=2048)
+    return time.perf_counter() - t0
+
+
+def cpu_eval_rate(n_windows, procs):
+    """evals/s of the oracle port (NumPy FP64 restatement of the reference path) on host cores."""
+    from oracle import wfot_oracle as O
+    w = O.random_walk_windows(n_windows + 1, NT, seed=5).astype(np.float64)
+    t = np.linspace(0, 1, NT)
+    _, tgt = O.build_ot_from_waveform(t, w[0], GRID, lambdav=LAM, chunk=2048)
+    O.set_marginals(tgt)
+    jobs = [(t, w[1 + i], tgt) for i in range(n_windows)]
+    t0 = time.perf_counter()
+    if procs <= 1:
+        for j in jobs:
+            _cpu_one(j)
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_one, jobs, chunksize=1)
+    dt = time.perf_counter() - t0
+    return n_windows / dt, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm (oracle port; the reference is pure Python +
+    NumPy and cannot travel to the GPU box) on all host cores, same workload/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    per_window_s = 9.0
+    nsteps = args.steps + args.warmup
+    per_step = int(max(1, min(procs, 150.0 / (nsteps * per_window_s) * procs)))
+    procs = min(procs, per_step)
+    for _ in range(args.warmup):
+        cpu_eval_rate(per_step, procs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_eval_rate(per_step, procs)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg5: 1024-sample windows -> 256x256 fingerprint, W2 misfit + gradient",
+                   "nt": NT, "nug": NUG, "ntg": NTG, "lambda": LAM, "windows_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "port",
+                         "sample": "%d windows per step on %d processes (oracle/wfot_oracle.py, NumPy FP64)" % (per_step, procs)},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from waveform_ot_b200 import _cabi as C
+    from waveform_ot_b200 import batch as B
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    nb = args.batch
+    n_pool = 3      # distinct input batches cycled through (with the 28 B/pixel scratch slabs the
+    #                 per-step working set is far larger than the 126 MB L2)
+    pools = [make_windows_device(nb, NT, 1000 * (rank + 1) + i, dev) for i in range(n_pool)]
+    t = torch.linspace(0, 1, NT, device=dev, dtype=torch.float32)
+    obs = make_windows_device(1, NT, 5, dev)
+    target = B.Target.from_waveform(t, obs[0], GRID, NUG, NTG, LAM)
+    grids = B.pack_grids(GRID)
+    ws = torch.empty(C.lib.wfot_misfit_grad_workspace_bytes(nb, NT, NUG, NTG), dtype=torch.uint8, device=dev)
+    status = B.Status()
+    C_out = 2 + 2 * NT + 1
+    packed = torch.empty((nb, C_out), dtype=torch.float64, device=dev)
+
+    def step(w):
+        r = B.misfit_grad_batch(t, w, grids, NUG, NTG, LAM, target, distfunc="W2", status=status, workspace=ws)
+        # [W^t, W^u, dwg, grad_t (nt), grad_u (nt)] per window -> summed over the shard -> allreduce
+        packed[:, 0:2] = r["W"]
+        packed[:, 2] = r["dwg"]
+        packed[:, 3:] = r["grad"].reshape(nb, 2 * NT)
+        tot = B.sum_windows(packed)
+        if world > 1:
+            dist.all_reduce(tot)
+        return r, tot
+
+    # ---- FP32 peak probe (the roofline denominator for the CUDA-core bound scan)
+    sink = torch.zeros(4, device=dev)
+    ops = ctypes.c_double()
+    C.check(C.lib.wfot_fp32_peak_probe(1, 2000, C.ptr(sink), ctypes.byref(ops), None))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e30
+    for _ in range(3):
+        e0.record(); C.check(C.lib.wfot_fp32_peak_probe(1, 4000, C.ptr(sink), ctypes.byref(ops), None)); e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    fp32_peak_tflops = 2.0 * ops.value / best / 1e9
+
+    for i in range(args.warmup):
+        step(pools[i % n_pool])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    s_ev.record()
+    for i in range(args.steps):
+        w = pools[(args.warmup + i) % n_pool]
+        kev[i][0].record()
+        r = B.misfit_grad_batch(t, w, grids, NUG, NTG, LAM, target, distfunc="W2", status=status, workspace=ws)
+        kev[i][1].record()
+        packed[:, 0:2] = r["W"]
+        packed[:, 2] = r["dwg"]
+        packed[:, 3:] = r["grad"].reshape(nb, 2 * NT)
+        tot = B.sum_windows(packed)
+        if world > 1:
+            dist.all_reduce(tot)
+    e_ev.record()
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    ms = s_ev.elapsed_time(e_ev)
+    ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
+    host_w = [p.cpu().pin_memory() for p in pools]
+    host_t = t.cpu().pin_memory()
+    nrep = max(2, min(args.steps, 3))
+
+    def e2e_step(hw):
+        wd = hw.to(dev, non_blocking=True)
+        td = host_t.to(dev, non_blocking=True)
+        r = B.misfit_grad_batch(td, wd, grids, NUG, NTG, LAM, target, distfunc="W2", status=status, workspace=ws)
+        return r["W"].cpu(), r["dwg"].cpu(), r["grad"].cpu()
+
+    e2e_step(host_w[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(nrep):
+        e2e_step(host_w[i % n_pool])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * nb * nrep / float(e2e_t.item())
+    h2d = nb * NT * 4 + NT * 4
+    d2h = nb * (2 + 1 + 2 * NT) * 8
+
+    st = status.read()
+    if rank == 0:
+        total_windows = world * nb * args.steps
+        value = total_windows / (ms_max / 1e3)
+        achieved = ALG_FLOP_PER_WINDOW * nb / (k_ms / 1e3) / 1e12
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            try:
+                tj = json.load(open(tf))
+                traffic = tj.get("dram_bytes_per_window", 0) * nb
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 scan + f64 resolve/OT", "data": "synthetic",
+            "config": {"workload": "cfg5: 1024-sample windows -> 256x256 fingerprint, W2 misfit + gradient",
+                       "nt": NT, "nug": NUG, "ntg": NTG, "lambda": LAM, "windows_per_gpu_per_step": nb,
+                       "global_windows_per_step": world * nb,
+                       "l2": "3 input batches cycled; per-step scratch (28 B/pixel x resident CTAs) + inputs exceed the 126 MB L2",
+                       "parallelism": "windows sharded over %d GPU(s), one allreduce of [sum misfit, sum grad]" % world},
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak_tflops, "traffic": traffic,
+                         "kernel": "k_misfit_grad", "kernel_ms": k_ms,
+                         "peak_source": "FFMA2 probe measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core entry)",
+                         "algorithmic_flop_per_window": ALG_FLOP_PER_WINDOW},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 3 * args.steps,
+            "clocks": clocks,
+            "status_counters": {"slow_pixels": int(st[4]), "common_cdf": int(st[1]), "zero_dist": int(st[2])},
+        }
+        if world == 1 and args.cpu_sample > 0:
+            v, dt = cpu_eval_rate(args.cpu_sample, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
+                                    "sample": "%d windows of the same workload, oracle/wfot_oracle.py (NumPy FP64), %.1f s" % (args.cpu_sample, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

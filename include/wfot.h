@@ -114,6 +114,13 @@ int wfot_marginals_batch(const double* pdf, int B, int nug, int ntg,
                          double* amp, double* marg_t, double* marg_u,
                          int32_t* status, void* stream);
 
+/* ---- 1-D OTpdf ---------------------------------------------------------------
+ * Replaces OTpdf.__init__ for 1-D input: libs/OTlib.py:91-93,112-114.
+ * f (B, n) un-normalised -> amp (B,), pdf_norm (B, n) = f/amp, cdf (B, n) =
+ * cumsum(pdf_norm)/cumsum(pdf_norm)[-1] (FP64 block prefix scan).  Outputs nullable. */
+int wfot_otpdf1d_batch(const void* f, int in_dtype, int n, int B,
+                       double* amp, double* pdf_norm, double* cdf, int32_t* status, void* stream);
+
 /* ---- 1-D optimal transport -------------------------------------------------
  * Replaces OTpdf.__init__ (1-D) + wasser(distfunc in {'W1','W2','W12'},
  * derivatives=...): libs/OTlib.py:90-117, 596-706.
@@ -174,6 +181,15 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
  * J_stride_models = 0 shares one Jacobian. */
 int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M,
                      long long J_stride_models, double* out, void* stream);
+
+/* ---- batch reduction -----------------------------------------------------------
+ * out (C,) = sum over b of in (B, C), FP64, fixed summation order (run-to-run and
+ * shard-order reproducible).  This is the local step before the single NCCL allreduce of
+ * [sum misfit, sum gradient] across GPUs; the reference's counterpart is
+ * the Python accumulation `mis += w2p` in libs/loc_cmt_util.py:260-271. */
+size_t wfot_sum_windows_workspace_bytes(int C);
+int wfot_sum_windows(const double* in, long long B, int C, double* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- microbenchmark used by bench.py to measure the FP32-pipe peak -----------
  * Runs `iters` dependent-free FFMA2 (packed) or FFMA (scalar) bundles on every

@@ -1,0 +1,158 @@
+"""GPU: the reference-facing Python surface (waveformFP / OTpdf / wasser / MargWasserstein and the
+adapters) used exactly the way the reference's notebooks and libs/ricker_util.py use it, checked
+against the reference-generated goldens."""
+import pickle
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import wfot_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from waveform_ot_b200 import FingerprintLib as fp, OTlib as OT, adapters
+    return fp, OT, adapters
+
+
+def _grid(g):
+    return tuple(g["grid"][:4]) + (int(g["grid"][4]), int(g["grid"][5]))
+
+
+def test_point_mass_demo(mods):
+    """Point_mass_demo_Fig_5.ipynb cells 3/6/11/13."""
+    fp, OT, _ = mods
+    fx, gx = np.linspace(3, 14, 6), np.linspace(7, 18, 6)
+    f = np.array([.2, .01, .18, .21, .2, .2])
+    g = np.array([.18, .07, .2, .05, .27, .23])
+    source, target = OT.OTpdf((f, fx)), OT.OTpdf((g, gx))
+    assert source.type == '1D' and source.n == 6 and abs(target.amp - 1.0) < 1e-15
+    assert OT.wasser(source, target, distfunc='W1')[0] == pytest.approx(4.11, abs=1e-12)
+    assert OT.wasser(source, target, distfunc='W2')[0] == pytest.approx(18.09, abs=1e-12)
+    out = OT.wasser(source, target, 'W12', derivatives=True)
+    assert len(out) == 6
+    np.testing.assert_allclose(out[1], [6.16, 3.96, 1.76, -0.44, -2.64, -4.84], atol=1e-12)
+    np.testing.assert_allclose(out[4], [49.28, 26.84, 14.08, 1.32, -21.12, -43.56], atol=1e-11)
+    assert out[2] == pytest.approx(-1.0) and out[5] == pytest.approx(-8.22)
+    with pytest.raises(OT.TargetSourceCDFError):
+        OT.wasser(source, OT.OTpdf((f, fx)), 'W2', derivatives=True)
+    with pytest.raises(OT.PDFSignError):
+        OT.OTpdf((np.array([0.5, -0.1, 0.6]), fx[:3]))
+    with pytest.raises(OT.PDFShapeError):
+        OT.OTpdf((f, fx[:5]))
+    with pytest.raises(NotImplementedError):
+        OT.wasser(source, target, returnplan=True)
+
+
+@pytest.mark.parametrize("case", ["small_q1", "small_q2", "small_theta", "small_fpgrid", "ricker_cfg1"])
+def test_reference_call_sequence(mods, golden, case):
+    """waveformFP -> calcpdf -> OTpdf -> MargWasserstein -> PDFderivMarg / PDFderiv, the sequence of
+    libs/ricker_util.py:250-268,321-337."""
+    fp, OT, _ = mods
+    g = golden(case)
+    q = None if int(g["q"]) < 0 else int(g["q"])
+    fpgrid = tuple(g["fpgrid"]) if g["fpgrid"].size else None
+    grid, lam, theta, distfunc = _grid(g), float(g["lam"]), float(g["theta"]), str(g["distfunc"])
+    wf = fp.waveformFP(g["tp"], g["wp"], grid, fpgrid=fpgrid, theta=theta)
+    wf.calcpdf(q=q, lambdav=lam, deriv=True)
+    wo = fp.waveformFP(g["to"], g["wo"], grid, fpgrid=fpgrid, theta=theta)
+    wo.calcpdf(q=q, lambdav=lam)
+    assert wf.type == 'Enu' and wf.dfield.shape == (grid[4], grid[5]) and wf.irays.dtype == np.int64
+    assert wf.pos.shape == (grid[4], grid[5], 2) and wf.tcalc_fp >= 0
+    if "irays" in g:
+        np.testing.assert_array_equal(wf.irays, g["irays"])
+        np.testing.assert_array_equal(wf.dfield, g["dfield"])
+        np.testing.assert_array_equal(wf.lrays, g["lrays"])
+    else:
+        np.testing.assert_array_equal(wf.irays, g["irays_all"].astype(np.int64))
+    src, tgt = OT.OTpdf((wf.pdf, wf.pos)), OT.OTpdf((wo.pdf, wo.pos))
+    assert src.type == '2D' and (src.nx, src.ny) == (grid[4], grid[5])
+    assert src.amp == pytest.approx(float(g["amp"]), rel=1e-14)
+    W, dW, dwg = OT.MargWasserstein(src, tgt, distfunc=distfunc, derivatives=True, returnmargW=True)
+    np.testing.assert_allclose(src.marg[0].cdf, g["cdf_t"], rtol=1e-13)
+    np.testing.assert_allclose(W, g["W"], rtol=1e-11)
+    np.testing.assert_allclose(dwg, g["dwg"], rtol=1e-10)
+    if "dWt" in g:
+        np.testing.assert_allclose(dW[0], g["dWt"], rtol=1e-8, atol=1e-12 * np.abs(g["dWt"]).max())
+        np.testing.assert_allclose(dW[1], g["dWu"], rtol=1e-8, atol=1e-12 * np.abs(g["dWu"]).max())
+    wf.PDFderivMarg(dW)
+    np.testing.assert_allclose(wf.pdfdMarg[0], g["pdfdMarg0"], rtol=1e-7, atol=1e-9 * np.abs(g["pdfdMarg0"]).max())
+    np.testing.assert_allclose(wf.pdfdMarg[1], g["pdfdMarg1"], rtol=1e-7, atol=1e-9 * np.abs(g["pdfdMarg1"]).max())
+    Wavg, dWavg, dwgavg = OT.MargWasserstein(src, tgt, distfunc=distfunc, derivatives=True)
+    assert Wavg == pytest.approx(float(g["Wavg"]), rel=1e-11)
+    assert dwgavg == pytest.approx(float(g["dwgavg"]), rel=1e-10)
+    wf.PDFderiv(chainmatrix=dWavg)
+    np.testing.assert_allclose(wf.pdfd, g["pdfd"], rtol=1e-7, atol=1e-9 * np.abs(g["pdfd"]).max())
+    assert OT.MargWasserstein(src, tgt, distfunc=distfunc)[0] == pytest.approx(float(g["Wavg"]), rel=1e-11)
+    with pytest.raises(OT.MarginalWassersteinError):
+        OT.MargWasserstein(src, tgt, distfunc='W12')
+    with pytest.raises(OT.TargetSourceCDFError):           # identical source/target
+        OT.MargWasserstein(src, src, derivatives=True)
+    wf2 = pickle.loads(pickle.dumps(wf))                    # history lists / result pickles
+    np.testing.assert_array_equal(wf2.irays, wf.irays)
+    np.testing.assert_array_equal(wf2.pdf, wf.pdf)
+    pickle.loads(pickle.dumps(src))
+
+
+def test_ricker_optfunc_adapter(mods):
+    """optfunc (libs/ricker_util.py:373-404) through the fused kernel vs the oracle's composition."""
+    fp, OT, adapters = mods
+    to, wo = O.rickerwavelet(0.0, 1.6, 1.0)
+    grid, lam, alpha = (-2.0, 2.0, -1.8, 4.2, 40, 128), 0.03, 0.5
+    target = adapters.make_target(to, wo, grid, lam)
+
+    def forward(x, trange):
+        t, w = O.rickerwavelet(x[0], x[1], x[2], trange=trange)
+        dw = np.zeros((3, len(w)))
+        dw[0] = -np.gradient(w, t[1] - t[0])
+        dw[1] = w / x[1]
+        return t, w, dw
+
+    x = np.array([0.6, 1.2, 0.9])
+    w2, deriv = adapters.optfunc_ricker(x, [target, "W2", (-2.0, 2.0), grid, lam, False, alpha, 45.0], forward)
+    t, w, dw = forward(x, (-2.0, 2.0))
+    _, tgt = O.build_ot_from_waveform(to, wo, grid, lambdav=lam)
+    W, dr, dg, _, _ = O.misfit_grad_window(t, w, grid, tgt, lambdav=lam)
+    assert w2 == pytest.approx(alpha * W[0] + (1 - alpha) * W[1], rel=1e-10)
+    ref = alpha * dw.dot(dr[0]) + (1 - alpha) * dw.dot(dr[1])
+    ref[0] = alpha * dg[0] + (1 - alpha) * dg[1]
+    np.testing.assert_allclose(deriv, ref, rtol=1e-7, atol=1e-10)
+
+
+def test_cmt_models_adapter(mods):
+    """Batched libs/loc_cmt_util.py:251-296: M models x (nr x nc) windows, arctan transform in-kernel,
+    Jacobian chain; against the per-window oracle loop."""
+    fp, OT, adapters = mods
+    from waveform_ot_b200 import batch as B
+    rng = np.random.default_rng(1)
+    M, nr, nc, nt, lam = 3, 2, 3, 61, 0.04
+    t = np.arange(float(nt))
+    base = np.stack([[np.exp(-0.5 * ((t - 20 - 3 * i - 2 * j) / 4.0) ** 2) * np.sin(0.4 * (t - 20 - 3 * i))
+                      for j in range(nc)] for i in range(nr)]) * 1e-3
+    obs = base + 2e-5 * rng.standard_normal(base.shape)
+    pred = np.stack([np.roll(base, m + 1, axis=-1) * (1 + 0.1 * m) + 1e-5 * rng.standard_normal(base.shape)
+                     for m in range(M)])
+    grids = [[O.build_fingerprint_window(t, obs[i, j]) for j in range(nc)] for i in range(nr)]
+    Nu, Nt = grids[0][0][4], grids[0][0][5]
+    uo = np.stack([[O.arctan_trans(obs[i, j], grids[i][j][2], grids[i][j][3]) for j in range(nc)] for i in range(nr)])
+    g01 = [(grids[i][j][0], grids[i][j][1], 0.0, 1.0, Nu, Nt) for i in range(nr) for j in range(nc)]
+    targets = B.Target.from_waveform(t, uo.reshape(nr * nc, nt), g01, Nu, Nt, lam)
+    J = rng.standard_normal((M, 9, nr * nc * nt))
+    mis, dmis, dr = adapters.misfit_grad_models(t, pred, grids, targets, lam, J=J)
+    for m in range(M):
+        tot, drm = 0.0, np.zeros((nr, nc, nt))
+        for i in range(nr):
+            for j in range(nc):
+                _, tgt = O.build_ot_from_waveform(t, obs[i, j], tuple(grids[i][j]), lambdav=lam, transform=True)
+                W, d, dg, _, _ = O.misfit_grad_window(t, pred[m, i, j], tuple(grids[i][j]), tgt, lambdav=lam,
+                                                      transform=True, adapter="cmt")
+                tot += 0.5 * (W[0] + W[1])
+                drm[i, j] = 0.5 * (d[0] + d[1])
+        assert mis[m] == pytest.approx(tot, rel=1e-7)
+        np.testing.assert_allclose(dr[m], drm, rtol=1e-5, atol=1e-7 * np.abs(drm).max())
+        np.testing.assert_allclose(dmis[m], J[m].dot(drm.reshape(-1)), rtol=1e-5, atol=1e-7 * np.abs(dmis[m]).max())

@@ -1,0 +1,91 @@
+"""CPU: host-side logic of the reference-facing shim (no GPU work)."""
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle import wfot_oracle as O
+
+
+def test_grid_struct_layout():
+    from waveform_ot_b200 import _cabi, batch
+    assert batch.GRID_DTYPE.itemsize == 80
+    for name, (dt, off) in batch.GRID_DTYPE.fields.items():
+        assert getattr(_cabi.wfot_grid, name).offset == off
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a CUDA device."""
+    import torch
+    from waveform_ot_b200 import batch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        batch.fingerprint_batch(np.linspace(0, 1, 8), np.zeros(8), (0, 1, -1, 1, 4, 4), 4, 4, 0.04)
+    import waveform_ot_b200.batch as b
+    src = open(b.__file__).read() + open(b.__file__.replace("batch.py", "OTlib.py")).read()
+    assert "oracle" not in src              # the shim never imports the oracle
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(theta=60.0), dict(tantheta=0.5),
+                                dict(fpgrid=(0.2, 3.9, -2.0, 2.2))])
+def test_waveformfp_constructor_matches_reference_semantics(kw):
+    """waveformFP.__init__ is host-only: same attributes as libs/FingerprintLib.py:75-115."""
+    from waveform_ot_b200 import FingerprintLib as fp
+    rng = np.random.default_rng(1)
+    t = np.sort(rng.random(30)) * 3 + 0.5
+    w = rng.standard_normal(30)
+    grid = (0.0, 4.0, -2.5, 2.5, 20, 16)
+    wf = fp.waveformFP(t, w, grid, **kw)
+    win = O.make_window(t, w, grid, **kw)
+    assert (wf.ntg, wf.nug, wf.nt) == (16, 20, 30)
+    assert wf.tant == pytest.approx(win.tant) and wf.theta == pytest.approx(win.theta)
+    assert wf.tlimn == win.tlimn and wf.tlimnfp == win.tlimnfp and wf.ulimnfp == win.ulimnfp
+    np.testing.assert_array_equal(wf.pn, win.pn)
+    np.testing.assert_array_equal(wf.delta_n, win.delta_n)
+    np.testing.assert_array_equal(wf.lsq_n, win.lsq_n)
+    assert wf.x0.shape == (1, 29, 2) and not wf.dcalc
+    with pytest.raises(fp.WaveformPFderivError):
+        wf.wdistderiv()
+    with pytest.raises(NotImplementedError):
+        wf.calcpdf(method="FMM")
+    with pytest.raises(fp.FingerprintMethodError):
+        wf.calcpdf(method="bogus")
+    wf2 = pickle.loads(pickle.dumps(wf))
+    np.testing.assert_array_equal(wf2.pn, wf.pn)
+
+
+def test_otlib_argument_errors():
+    from waveform_ot_b200 import OTlib as OT
+    with pytest.raises(OT.UnknownOTDistanceTypeError):
+        OT._checkdistfunc(3.0)
+    with pytest.raises(NotImplementedError):
+        OT._checkdistfunc(np.zeros((2, 2)))
+    assert OT._checkdistfunc("W12") == (True, True) and OT._checkdistfunc("W1") == (True, False)
+    for name in ("PDFSignError", "PDFShapeError", "TargetSourceCDFError", "TargetSource2DShapeError",
+                 "MarginalWassersteinError", "UnknownOTDistanceTypeError", "DistfuncShapeError"):
+        assert issubclass(getattr(OT, name), Exception)
+
+
+def test_adapters_arctan_and_install():
+    from waveform_ot_b200 import adapters
+    u = np.linspace(-3, 3, 11)
+    a, da = adapters.arctan_trans(u, -1.0, 2.0, deriv=True)
+    b, db = O.arctan_trans(u, -1.0, 2.0, deriv=True)
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(da, db)
+    fpm, otm = adapters.install("libs_test_prefix")
+    import sys
+    assert sys.modules["libs_test_prefix.FingerprintLib"] is fpm
+    assert sys.modules["libs_test_prefix.OTlib"] is otm
+
+
+def test_shard_bounds_cover_exactly():
+    from waveform_ot_b200.dist import shard_bounds
+    for n in (0, 1, 7, 30, 4096, 4_000_000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1

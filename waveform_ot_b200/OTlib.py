@@ -1,0 +1,258 @@
+"""Drop-in for the hot-path part of the reference's ``libs/OTlib.py``:
+``OTpdf`` (+ ``setMarginals``), ``wasser`` and ``MargWasserstein`` with the
+reference's signatures, return-list layouts and exception classes
+(libs/OTlib.py:34-75, 82-163, 596-716, 1055-1154); the arithmetic runs in
+libwfot.so on the GPU.
+
+Out of scope (NotImplementedError): transport plans (``returnplan``), user
+supplied cost matrices (``distfunc`` as ndarray/tuple), sliced Wasserstein,
+LP / Sinkhorn / POT cross-checks, barycentres, plotting.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import batch as _B
+
+
+class Error(Exception):
+    """Base class for other exceptions"""
+
+
+class PDFShapeError(Exception):
+    """Raised when input PDF has inconsistent set of amplitdues and locations"""
+
+    def __init__(self, msg=''):
+        super().__init__('\n PDF amplitude and point location have different shapes \n')
+
+
+class DistfuncShapeError(Exception):
+    def __init__(self, msg=''):
+        super().__init__('\n Input distfunc is an array with wrong shape. First index should be source PDF '
+                         'dimension and second index target PDF dimension\n')
+
+
+class PDFSignError(Exception):
+    """Raised when input PDF has a component with a negative amplitude"""
+
+    def __init__(self, msg=''):
+        super().__init__('\n OTpdf Error: Input PDF has a negative amplitude\n')
+
+
+class UnknownOTDistanceTypeError(Exception):
+    def __init__(self, msg=''):
+        super().__init__('\n Error in wasserPOT: Do not recognize parameter distfunc\n')
+
+
+class TargetSourceCDFError(Exception):
+    """Raised when the target and source CDFs have common entries"""
+
+    def __init__(self, cset=[]):
+        msg = '\n Identical values in CDF of source and target detected \n\n Common set :' + str(cset) \
+              + '\n\n This will introduce errors into derivative calculations \n'
+        super().__init__(msg)
+
+
+class TargetSource2DShapeError(Exception):
+    def __init__(self, msg=''):
+        super().__init__('\n  Input PDF is not 2D when it should be.\n')
+
+
+class SlicedWassersteinError(Exception):
+    pass
+
+
+class MarginalWassersteinError(Exception):
+    def __init__(self, mset=[]):
+        msg = '\n Marginal Wasserstein routine not set up to recognize distfunc:' + mset + '\n \n'
+        super().__init__(msg)
+
+
+def _sync():
+    import torch
+    torch.cuda.current_stream().synchronize()
+
+
+class OTpdf(object):
+    """libs/OTlib.py:82-163.  ``pdf`` = (amplitudes, positions), 1-D or 2-D."""
+
+    def __init__(self, pdf):
+        f = np.asarray(pdf[0], dtype=np.float64)
+        x = np.asarray(pdf[1])
+        self.ndim = 1
+        self.nproj = 0
+        self._raw = f                       # un-normalised amplitudes as given (kernel input)
+        self._raw_dev = None
+        if f.ndim == 2:
+            self.type = '2D'
+            self.ndim = 2
+            self.nx = np.shape(x)[0]
+            self.ny = np.shape(x)[1]
+            self.n = self.nx * self.ny
+            if np.shape(f) != np.shape(x)[:2]:                       # :104-105
+                raise PDFShapeError
+            r = _B.marginals_batch(f)
+            _sync()
+            if r["status"].read()[0]:
+                raise PDFSignError()                                  # :91
+            self.amp = float(r["amp"][0])                             # :92
+            self._marg_dev = (r["marg_t"], r["marg_u"])
+        else:
+            self.n = len(f)
+            self.type = '1D'
+            if self.n != len(x):                                      # :109-110
+                raise PDFShapeError
+            r = _B.otpdf1d_batch(f)
+            _sync()
+            if r["status"].read()[0]:
+                raise PDFSignError()
+            self.amp = float(r["amp"][0])
+            self._pdf = r["pdf"][0].cpu().numpy()
+            self._cdf = r["cdf"][0].cpu().numpy()
+        self.x = x.copy()                                             # :94
+        self.calcproj = True
+        self.calcmarg = True
+        self.ProjNum = -1
+
+    @property
+    def pdf(self):
+        if not hasattr(self, "_pdf"):
+            self._pdf = self._raw / self.amp                          # :93 (attribute shaping only)
+        return self._pdf
+
+    @property
+    def cdf(self):
+        if not hasattr(self, "_cdf"):                                 # 2-D: flattened CDF nobody reads (:112-114)
+            r = _B.otpdf1d_batch(self._raw.reshape(1, -1))
+            _sync()
+            self._cdf = r["cdf"][0].cpu().numpy()
+        return self._cdf
+
+    def setSliced(self, Nproj, org):
+        raise NotImplementedError("waveform_ot_b200: sliced Wasserstein is out of scope (SURVEY section 2 #13)")
+
+    def setMarginals(self):
+        """libs/OTlib.py:146-163."""
+        if self.type != '2D':
+            raise TargetSource2DShapeError
+        self.nproj = 2
+        f0 = self._marg_dev[0][0].cpu().numpy()                       # :155 (sum over rows of pdf/amp)
+        f1 = self._marg_dev[1][0].cpu().numpy()                       # :156
+        self.marg = [OTpdf((f0, self.x[0, :, 0])), OTpdf((f1, self.x[:, 0, 1]))]   # :157-160
+        self.angles = np.array([0.0, np.pi / 2.])
+        self.calcmarg = False
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop("_marg_dev", None)
+        st["_raw_dev"] = None
+        return st
+
+
+def _checkdistfunc(distfunc):
+    """libs/OTlib.py:165-185."""
+    if isinstance(distfunc, str):
+        return (distfunc in ('W1', 'W12')), (distfunc in ('W2', 'W12'))
+    if type(distfunc) in (tuple, np.ndarray):
+        raise NotImplementedError("waveform_ot_b200: user-supplied distance arrays are out of scope "
+                                  "(SURVEY section 2 #12)")
+    raise UnknownOTDistanceTypeError
+
+
+def wasser(source, target, distfunc='W12', proj=-1, returnplan=False, derivatives=False, memory=False,
+           checkCommonCDF=False, ignoreCommonCDFerror=False):
+    """W_p^p(f,g), p = 1, 2, for 1-D PDFs and optionally derivatives w.r.t. un-normalised source
+    amplitudes and source translation; libs/OTlib.py:596-716.  Return list as the reference:
+    [W1, dW1, dW1_pos, W2, dW2, dW2_pos] restricted to the requested entries."""
+    calcW1, calcW2 = _checkdistfunc(distfunc)
+    if returnplan:
+        raise NotImplementedError("waveform_ot_b200: transport plans are out of scope (SURVEY section 2 #11)")
+    if source.type != '1D' or target.type != '1D':
+        raise NotImplementedError("waveform_ot_b200: wasser() takes 1-D OTpdf objects")
+    if derivatives and source.n != target.n:
+        # libs/OTlib.py:682-683 broadcasts (n, target.n) - (n,) and fails the same way
+        raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,) "
+                         % (source.n, target.n, source.n))
+    name = 'W12' if (calcW1 and calcW2) else ('W1' if calcW1 else 'W2')
+    r = _B.ot1d_batch(source._raw, target._raw, source.x, target.x, name, derivatives=derivatives)
+    _sync()
+    st = r["status"].read()
+    if (derivatives or checkCommonCDF) and st[1] and not ignoreCommonCDFerror:      # :663-666
+        cset = np.intersect1d(target.cdf[:-1], source.cdf[:-1])
+        raise TargetSourceCDFError(cset)
+    W = r["W"][0].cpu().numpy()
+    out = []
+    if calcW1:
+        out += [W[0]]
+        if derivatives:
+            out += [r["dW1"][0].cpu().numpy(), r["dpos"][0, 0].item()]
+    if calcW2:
+        out += [W[1]]
+        if derivatives:
+            out += [r["dW2"][0].cpu().numpy(), r["dpos"][0, 1].item()]
+    return out
+
+
+def MargWasserstein(source, target, distfunc='W2', derivatives=False, verbose=False, memory=False,
+                    returnmargW=False):
+    """Marginal Wasserstein distance between two 2-D PDFs; libs/OTlib.py:1055-1154."""
+    if source.type != '2D':
+        raise TargetSource2DShapeError
+    if target.type != '2D':
+        raise TargetSource2DShapeError
+    if type(distfunc) == str:
+        if distfunc == 'W12':
+            raise MarginalWassersteinError(mset='W12')
+    if source.calcmarg:
+        source.setMarginals()
+    if target.calcmarg:
+        target.setMarginals()
+    if derivatives:
+        dwp = np.zeros((source.nx, source.ny))
+        dwpmargX = np.zeros_like(dwp)
+        dwpmargY = np.zeros_like(dwp)
+    wp = 0.
+    Nproj = 2
+    wpmarg = np.zeros(2)
+    dwgmarg = [0.] * 2
+    gbar = [0., 0.]      # <dW_i, pbar> = sum_j m_j dW_i[j] over the marginal (same value as :1141,1144-1145)
+    for i in range(2):                                               # :1106-1134
+        wout = wasser(source.marg[i], target.marg[i], distfunc=distfunc, derivatives=derivatives,
+                      checkCommonCDF=True, memory=memory)
+        wsqpd = wout[0]
+        if derivatives:
+            wsqpd, dw = wout[0:2]
+            gbar[i] = float(np.dot(dw, source.marg[i]._raw))
+            if i == 0:
+                dwp[:] += dw
+                dwg = wout[2]
+                dwgmarg[i] = dwg
+                if returnmargW:
+                    dwpmargX = np.copy(dwp)
+            else:
+                dwp.T[:] += dw
+                if returnmargW:
+                    dwpmargY.T[:] += dw
+        wpmarg[i] = wsqpd
+        wp += wsqpd
+        if verbose:
+            print('Projection ', i, ' completed w =', np.sqrt(wsqpd), ' theta ', source.angles[i] * 180 / np.pi)
+    out = [wp / Nproj]
+    outMarg = [[wpmarg[0], wpmarg[1]]]
+    if derivatives:
+        gt, gu = gbar
+        gall = gt + gu
+        dwp -= gall
+        dwp /= source.amp
+        if returnmargW:
+            dwpmargX -= gt
+            dwpmargY -= gu
+            dwpmargX /= source.amp
+            dwpmargY /= source.amp
+            outMarg += [[dwpmargX, dwpmargY]]
+            outMarg += [dwgmarg]
+        out += [dwp / Nproj]
+        out += [dwg / Nproj]
+    if returnmargW:
+        return outMarg
+    return out

@@ -44,6 +44,7 @@ SIGNATURES = {
     "wfot_fingerprint_batch": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _d, _i,
                                          _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "wfot_marginals_batch": (C.c_int, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "wfot_otpdf1d_batch": (C.c_int, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "wfot_ot1d_batch": (C.c_int, [_p, _p, _i, _p, _p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i,
                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "wfot_pdfderiv_batch": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _i, _p, _p]),
@@ -51,6 +52,8 @@ SIGNATURES = {
     "wfot_misfit_grad_batch": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _d, _i, _i, _i,
                                          _p, _p, _p, _p, _i, _p, _p, _p, _p, _sz, _p, _p]),
     "wfot_chain_batch": (C.c_int, [_p, _p, _i, _i, _i, _ll, _p, _p]),
+    "wfot_sum_windows_workspace_bytes": (_sz, [_i]),
+    "wfot_sum_windows": (C.c_int, [_p, _ll, _i, _p, _p, _sz, _p]),
     "wfot_fp32_peak_probe": (C.c_int, [_i, _i, _p, _p, _p]),
     "wfot_scan_probe": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _p, _p]),
 }

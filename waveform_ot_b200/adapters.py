@@ -1,0 +1,126 @@
+"""Reference-facing adapters: the glue either side of the hot path,
+with the reference's names and argument meaning, on top of the B200 kernels.
+
+* ``install()`` substitutes this package's ``FingerprintLib`` / ``OTlib`` for the reference's
+  ``libs.FingerprintLib`` / ``libs.OTlib`` so ``libs.ricker_util`` / ``libs.loc_cmt_util`` and
+  the notebooks run unchanged.
+* ``optfunc_ricker`` is ``libs/ricker_util.py:373-404`` (``optfunc``) with the three calls in
+  its middle (:386-388) replaced by ONE fused kernel launch.
+* ``misfit_grad_models`` is the batched form of ``libs/loc_cmt_util.py:253-296``: windows of
+  M trial models x (stations x components) in one launch, arctan transform in-kernel, then
+  the Jacobian chain ``d.dot(dr*dundu)`` per model.
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+
+from . import batch as _B
+
+
+def install(module_prefix="libs"):
+    """Make `from libs import FingerprintLib, OTlib` resolve to the B200 implementation."""
+    from . import FingerprintLib, OTlib
+    sys.modules[module_prefix + ".FingerprintLib"] = FingerprintLib
+    sys.modules[module_prefix + ".OTlib"] = OTlib
+    pkg = sys.modules.get(module_prefix)
+    if pkg is not None:
+        pkg.FingerprintLib = FingerprintLib
+        pkg.OTlib = OTlib
+    return FingerprintLib, OTlib
+
+
+def arctan_trans(u, u0, u1, deriv=False):
+    """libs/ricker_util.py:270-275 (host-side helper for callers that transform themselves)."""
+    up = ((u - u0) + (u - u1)) / (u1 - u0)
+    un = 0.5 + np.arctan(up) / np.pi
+    if deriv:
+        return un, 2 / ((u1 - u0) * np.pi * (1 + up * up))
+    return un
+
+
+def make_target(t, wave, grid, lambdav, transform=False, theta=45.0, q=None):
+    """Observed window -> Target (libs/ricker_util.py:204-268 applied to the observation)."""
+    t0, t1, u0, u1, Nu, Nt = grid
+    wave = np.asarray(wave, dtype=np.float64)
+    if transform:
+        wave = arctan_trans(wave, u0, u1)
+        u0, u1 = 0.0, 1.0
+    tant = 1.0 if theta == 45.0 else float(np.tan(np.pi * theta / 180.0))
+    return _B.Target.from_waveform(t, wave, (t0, t1, u0, u1, Nu, Nt), int(Nu), int(Nt), lambdav, q=q,
+                                   tantheta=tant)
+
+
+def misfit_grad(t, waves, grid, target, lambdav, distfunc="W2", transform=False, theta=45.0, q=None,
+                alpha=None, to_host=True):
+    """CalcWasserWaveform(..., deriv=True, returnmarg=True) for a batch of predicted windows
+    (libs/ricker_util.py:289-339): returns W (B,2), dr (B,2,nt), dg (B,2) with dg[:,0] =
+    dwg/(tan(theta)*(t1-t0)) (:333), dg[:,1] = 0.  With `alpha` the weighted sums
+    alpha*Wt + (1-alpha)*Wu (:390-392) are returned instead."""
+    import torch
+    t0, t1, u0, u1, Nu, Nt = grid
+    tant = 1.0 if theta == 45.0 else float(np.tan(np.pi * theta / 180.0))
+    r = _B.misfit_grad_batch(t, waves, (t0, t1, u0, u1, Nu, Nt), int(Nu), int(Nt), lambdav, target,
+                             distfunc=distfunc, q=q, tantheta=tant, transform=transform)
+    W, dr = r["W"], r["grad"]
+    dg = torch.zeros_like(W)
+    dg[:, 0] = r["dwg"] / (tant * (t1 - t0))
+    if alpha is not None:
+        W = alpha * W[:, 0] + (1 - alpha) * W[:, 1]
+        dr = alpha * dr[:, 0] + (1 - alpha) * dr[:, 1]
+        dg = alpha * dg[:, 0] + (1 - alpha) * dg[:, 1]
+    if to_host:
+        torch.cuda.current_stream().synchronize()
+        return W.cpu().numpy(), dr.cpu().numpy(), dg.cpu().numpy()
+    return W, dr, dg
+
+
+def optfunc_ricker(x, data, forward):
+    """libs/ricker_util.py:373-404 with the fingerprint/OT/derivative middle fused.
+    data = [target, distfunc, trange, grid, lambdav, transform, alpha, theta] where `target`
+    comes from make_target(); forward(x, trange) -> (t, w, dw (3, nt)) is the caller's model
+    (libs.ricker_util.rickerwavelet(..., deriv=True) in the notebooks)."""
+    target, distfunc, trange, grid, lambdav, transform, alpha, theta = data
+    tpos, wpos, dw = forward(x, trange)
+    W, dr, dg = misfit_grad(tpos, np.asarray(wpos)[None], grid, target, lambdav, distfunc=distfunc,
+                            transform=transform, theta=theta)
+    w2 = alpha * W[0, 0] + (1 - alpha) * W[0, 1]                                  # :390
+    dgs = alpha * dg[0, 0] + (1 - alpha) * dg[0, 1]                               # :392
+    deriv = alpha * dw.dot(dr[0, 0]) + (1 - alpha) * dw.dot(dr[0, 1])             # :399-401
+    deriv[0] = dgs                                                                 # :402
+    return w2, deriv
+
+
+def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfunc="W2", Wopt="Wavg"):
+    """Batched libs/loc_cmt_util.py:251-296.  seis_pred (M, nr, nc, nt) predicted seismograms of M
+    trial models; obs_grids[i][j] = (t0,t1,u0,u1,Nu,Nt) per station/component (u-box from the
+    observed window, :430-446); targets = Target with one row per (i,j) (built from the arctan-
+    transformed observations); J (M, P, nr*nc*nt) Jacobian d(seis)/d(model) or None.
+    Returns mis (M,), dmis (M, P) or None, dr (M, nr, nc, nt)."""
+    import torch
+    seis = np.ascontiguousarray(seis_pred)
+    M, nr, nc, nt = seis.shape
+    Nu, Nt = int(obs_grids[0][0][4]), int(obs_grids[0][0][5])
+    flat = [tuple(obs_grids[i][j][:4]) + (Nu, Nt) for i in range(nr) for j in range(nc)]
+    g1 = _B.pack_grids(flat)                                   # (nr*nc, 80 B)
+    g = g1.repeat(M, 1).contiguous()                           # window b = m*(nr*nc) + i*nc + j
+    tgt = _B.Target(targets.cdf_t.repeat(M, 1).contiguous(), targets.x_t.repeat(M, 1).contiguous(),
+                    targets.cdf_u.repeat(M, 1).contiguous(), targets.x_u.repeat(M, 1).contiguous())
+    tgt.per_window = True
+    r = _B.misfit_grad_batch(t, seis.reshape(M * nr * nc, nt), g, Nu, Nt, lambdav, tgt, distfunc=distfunc,
+                             transform=True)
+    W = r["W"].reshape(M, nr * nc, 2)
+    gr = r["grad"].reshape(M, nr * nc, 2, nt)
+    if Wopt == "Wavg":                                          # OTlib.py:1136,1150
+        mis = 0.5 * (W[..., 0] + W[..., 1]).sum(dim=1)
+        dr = 0.5 * (gr[:, :, 0] + gr[:, :, 1])
+    elif Wopt == "Wt":
+        mis, dr = W[..., 0].sum(dim=1), gr[:, :, 0]
+    else:
+        mis, dr = W[..., 1].sum(dim=1), gr[:, :, 1]
+    dmis = None
+    if J is not None:
+        dmis = _B.chain_batch(J, dr.reshape(M, nr * nc * nt).contiguous())        # :296
+    torch.cuda.current_stream().synchronize()
+    return mis.cpu().numpy(), None if dmis is None else dmis.cpu().numpy(), dr.reshape(M, nr, nc, nt).cpu().numpy()

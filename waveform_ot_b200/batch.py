@@ -132,6 +132,21 @@ def marginals_batch(pdf, status=None):
     return dict(amp=amp, marg_t=mt, marg_u=mu, status=st)
 
 
+def otpdf1d_batch(f, status=None):
+    """OTpdf.__init__ for B 1-D densities (B, n): amp, normalised pdf, CDF."""
+    dev = _device()
+    f = _as_device(f)
+    if f.dim() == 1:
+        f = f[None]
+    B, n = f.shape
+    f64 = dict(dtype=torch.float64, device=dev)
+    amp, pdfn, cdf = torch.empty(B, **f64), torch.empty((B, n), **f64), torch.empty((B, n), **f64)
+    st = status or Status()
+    C.check(C.lib.wfot_otpdf1d_batch(C.ptr(f), _dt(f), n, B, C.ptr(amp), C.ptr(pdfn), C.ptr(cdf),
+                                     C.ptr(st.t), _stream()), "wfot_otpdf1d_batch")
+    return dict(amp=amp, pdf=pdfn, cdf=cdf, status=st, _keepalive=(f,))
+
+
 def ot1d_batch(f, g, xf, xg, distfunc="W12", derivatives=False, want_cdf=False, want_merge=False,
                status=None):
     """OTpdf (1-D) + wasser for B pairs.  f (B,n) or (n,); g (B,m) or (m,) shared; x likewise."""
@@ -201,16 +216,12 @@ class Target:
                                fields=("pdf", "pn"))
         mg = marginals_batch(fp["pdf"])
         Bt = mg["marg_t"].shape[0]
-        dev = _device()
         # bin positions = pixel axes (libs/OTlib.py:157-158 on wf.pos)
         pn = fp["pn"]
         g = grids if isinstance(grids, torch.Tensor) else pack_grids(grids, tantheta, fpgrids)
         x_t, x_u = pixel_axes(pn, g, nug, ntg)
-        ones = torch.ones(1, dtype=torch.float64, device=dev)
-        ct = ot1d_batch(mg["marg_t"], ones.expand(2).contiguous(), x_t, torch.zeros(2, dtype=torch.float64, device=dev),
-                        distfunc="W1", want_cdf=True)["cdf_f"]
-        cu = ot1d_batch(mg["marg_u"], ones.expand(2).contiguous(), x_u, torch.zeros(2, dtype=torch.float64, device=dev),
-                        distfunc="W1", want_cdf=True)["cdf_f"]
+        ct = otpdf1d_batch(mg["marg_t"])["cdf"]
+        cu = otpdf1d_batch(mg["marg_u"])["cdf"]
         tg = Target(ct, x_t, cu, x_u)
         tg.per_window = Bt > 1
         return tg
@@ -282,4 +293,17 @@ def chain_batch(J, dr):
     out = torch.empty((M, P), dtype=torch.float64, device=dev)
     C.check(C.lib.wfot_chain_batch(C.ptr(J), C.ptr(dr), P, L, M, 0 if J.dim() == 2 else P * L,
                                    C.ptr(out), _stream()), "wfot_chain_batch")
+    return out
+
+
+def sum_windows(x):
+    """Deterministic FP64 sum over the leading (window) axis of a device tensor (B, ...)."""
+    dev = _device()
+    x = x.contiguous()
+    B = x.shape[0]
+    Cn = x[0].numel()
+    out = torch.empty(x.shape[1:], dtype=torch.float64, device=dev)
+    wsb = C.lib.wfot_sum_windows_workspace_bytes(Cn)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    C.check(C.lib.wfot_sum_windows(C.ptr(x), B, Cn, C.ptr(out), C.ptr(ws), wsb, _stream()), "wfot_sum_windows")
     return out

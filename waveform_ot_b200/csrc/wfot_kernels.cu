@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs a) {
 
 // ============================================================ k_fingerprint
 constexpr int kQCap = 1024;
+constexpr int kSumGroups = 592;   // partial-sum blocks of wfot_sum_windows (4 per SM)
 
 struct FpArgs {
     FpWorkspace ws; int nt; long long b0; int nug, ntg; double lambda; int q;
@@ -278,6 +279,37 @@ __global__ void __launch_bounds__(256) k_ot1d(OtArgs a) {
     if (tid == 0 && nneg && a.status) atomicAdd(a.status + WFOT_STAT_NEG_PDF, 1);
 }
 
+// ============================================================ k_otpdf1d
+// OTpdf.__init__ for B 1-D densities: amp, pdf/amp, cumsum/last (libs/OTlib.py:91-93,112-114).
+__global__ void __launch_bounds__(256) k_otpdf1d(const void* f, int dtype, int n, double* amp,
+                                                 double* pdfn, double* cdf, int32_t* status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* c = reinterpret_cast<double*>(smem_raw);
+    __shared__ double red[33];
+    const long long b = blockIdx.x;
+    const int tid = threadIdx.x;
+    double part = 0.0;
+    int neg = 0;
+    for (int j = tid; j < n; j += 256) {
+        const double v = load_sample(f, dtype, b * n + j);
+        c[j] = v; part += v; neg += (v < 0.0);
+    }
+    const double A = block_sum(part, red);
+    for (int j = tid; j < n; j += 256) {
+        const double p = c[j] / A;
+        c[j] = p;
+        if (pdfn) pdfn[b * n + j] = p;
+    }
+    __syncthreads();
+    block_scan(c, n, false, red);
+    const double last = c[n - 1];
+    __syncthreads();
+    if (cdf) for (int j = tid; j < n; j += 256) cdf[b * n + j] = c[j] / last;
+    if (tid == 0 && amp) amp[b] = A;
+    const int nneg = __syncthreads_count(neg > 0);
+    if (tid == 0 && nneg && status) atomicAdd(status + WFOT_STAT_NEG_PDF, 1);
+}
+
 // ============================================================ k_pdfderiv
 // One block per (window, chain).  A thread walks whole pixel columns, so consecutive
 // pixels mostly share their nearest segment and are combined before the shared-memory add.
@@ -330,6 +362,25 @@ __global__ void __launch_bounds__(256) k_chain(const double* __restrict__ J, con
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) out[(size_t)mI * P + p] = s;
+}
+
+// ============================================================ k_sum_windows
+// out[c] = sum_b in[b][c]  (fixed order: block i adds rows i, i+G, ... ; then one block adds the G partials)
+__global__ void __launch_bounds__(256) k_sum_windows(const double* __restrict__ in, long long B, int C,
+                                                     double* __restrict__ partial, int G) {
+    const int c = blockIdx.y * 256 + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (long long b = blockIdx.x; b < B; b += G) s += in[b * C + c];
+    partial[(size_t)blockIdx.x * C + c] = s;
+}
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partial, int G, int C,
+                                                      double* __restrict__ out) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int g = 0; g < G; ++g) s += partial[(size_t)g * C + c];
+    out[c] = s;
 }
 
 // ============================================================ FP32 peak probe
@@ -462,6 +513,20 @@ int wfot_marginals_batch(const double* pdf, int B, int nug, int ntg, double* amp
     return WFOT_OK;
 }
 
+int wfot_otpdf1d_batch(const void* f, int in_dtype, int n, int B, double* amp, double* pdf_norm,
+                       double* cdf, int32_t* status, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!f || n < 1 || B <= 0 || (in_dtype != WFOT_F32 && in_dtype != WFOT_F64)) return WFOT_ERR_INVALID_ARG;
+    const size_t smem = (size_t)n * 8;
+    if (smem > 200 * 1024) return WFOT_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(k_otpdf1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_otpdf1d)");
+    k_otpdf1d<<<B, 256, smem, stream>>>(f, in_dtype, n, amp, pdf_norm, cdf, status);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_otpdf1d_batch launch");
+    return WFOT_OK;
+}
+
 int wfot_ot1d_batch(const void* f, const void* g, int in_dtype, const double* xf, const double* xg,
                     long long f_stride, long long g_stride, long long xf_stride, long long xg_stride,
                     int n, int m, int B, int pmask, int derivatives, double* W, double* dW1,
@@ -510,6 +575,21 @@ int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M, lon
     k_chain<<<blocks, 256, 0, stream>>>(J, dr, P, L, M, J_stride_models, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_chain_batch launch");
+    return WFOT_OK;
+}
+
+size_t wfot_sum_windows_workspace_bytes(int C) { return (size_t)kSumGroups * (size_t)(C > 0 ? C : 0) * 8; }
+
+int wfot_sum_windows(const double* in, long long B, int C, double* out, void* workspace,
+                     size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!in || !out || !workspace || B <= 0 || C <= 0) return WFOT_ERR_INVALID_ARG;
+    if (workspace_bytes < wfot_sum_windows_workspace_bytes(C)) return WFOT_ERR_WORKSPACE;
+    const int G = (int)(B < kSumGroups ? B : kSumGroups);
+    k_sum_windows<<<dim3(G, (C + 255) / 256), 256, 0, stream>>>(in, B, C, (double*)workspace, G);
+    k_sum_partials<<<(C + 255) / 256, 256, 0, stream>>>((const double*)workspace, G, C, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_sum_windows launch");
     return WFOT_OK;
 }
 
