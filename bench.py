@@ -268,11 +268,20 @@ def run_ours(args):
     host_t = t.cpu().pin_memory()
     nrep = max(2, min(args.steps, 3))
 
+    out_W = torch.empty((nb, 2), dtype=torch.float64).pin_memory()
+    out_g = torch.empty((nb,), dtype=torch.float64).pin_memory()
+    out_grad = torch.empty((nb, 2, NT), dtype=torch.float64).pin_memory()
+
     def e2e_step(hw):
+        # host (pinned) -> device, fused evaluation, every per-window result back to the host
         wd = hw.to(dev, non_blocking=True)
         td = host_t.to(dev, non_blocking=True)
         r = B.misfit_grad_batch(td, wd, grids, NUG, NTG, LAM, target, distfunc="W2", status=status, workspace=ws)
-        return r["W"].cpu(), r["dwg"].cpu(), r["grad"].cpu()
+        out_W.copy_(r["W"], non_blocking=True)
+        out_g.copy_(r["dwg"], non_blocking=True)
+        out_grad.copy_(r["grad"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_W, out_g, out_grad
 
     e2e_step(host_w[0])
     torch.cuda.synchronize()
