@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwfot.so")
 
 STAT_NEG_PDF, STAT_COMMON_CDF, STAT_ZERO_DIST, STAT_DEGENERATE_SEG, STAT_SLOW_PIXELS = range(5)
+STAT_SCAN_TILES = 6          # slots 6-7: one 64-bit counter
 STAT_SLOTS = 8
 F32, F64 = 0, 1
 W1, W2, W12 = 1, 2, 3

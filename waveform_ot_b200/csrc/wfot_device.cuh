@@ -71,8 +71,16 @@ struct WinHdr {
 struct SegTable {
     const float4* A;   // {ex, ey, -am, -bm}   e = unit direction, am = mid.e, bm = mid x e (scaled)
     const float* H;    // half length (scaled)
+    const float4* bbox;   // per tile of kTile segments: {xlo, xhi, ylo, yhi} of its vertices (scaled frame)
     int S;             // real segments
     int Spad;          // padded to a multiple of kTile
+};
+
+// Pixel footprint of one warp in the scaled frame (warp-uniform): the scan skips every segment
+// tile whose bounding box is farther from the footprint than the largest running minimum of the
+// warp's pixels (exact pruning: a skipped tile cannot hold a nearest segment of any of them).
+struct Footprint {
+    float x0, x1, y0, y1;
 };
 
 __device__ __forceinline__ double lin_axis(double a0, double step, double alast, int i, int n) {
@@ -211,14 +219,94 @@ __device__ __forceinline__ void resolve_pixel_warp(const SegTable& tb, const dou
     hit.D = bD; hit.lam = bl; hit.s = (bs == 0x7fffffff) ? 0 : bs;
 }
 
+// ------------------------------------------------------------------ warp footprints
+// The pixel grid is cut into warp footprints of FC x FR thread blocks (FC * FR = 32; a thread block
+// is 2 columns x R rows).  FC is chosen per window so that the footprint is as square as possible
+// in normalised units, which is what makes the pruning of scan_block() effective.
+struct FootMap {
+    int fcl;     // log2(FC)
+    int nfc;     // footprints along the time axis
+    int nfoot;   // footprints per window
+};
+
+// wx, wy: extents of the pixel time / amplitude axes in the scaled frame.
+template <int R>
+__host__ __device__ inline FootMap make_footmap(int ntg, int nug, float wx, float wy) {
+    const int ncp = (ntg + 1) >> 1, nrg = (nug + R - 1) / R;
+    const float dx = ntg > 1 ? wx / (float)(ntg - 1) : 0.f, dy = nug > 1 ? wy / (float)(nug - 1) : 0.f;
+    int fcl = 4;
+    if (dx > 0.f && dy > 0.f) {
+        // 2 FC dx = R (32 / FC) dy  ->  FC = sqrt(16 R dy / dx), rounded in log2
+        float v = 16.f * (float)R * dy / dx;
+        fcl = 0;
+        while (fcl < 5 && v >= 2.f) { v *= 0.25f; ++fcl; }    // fcl = round(0.5 log2 v)
+    }
+    while (fcl > 0 && (1 << (fcl - 1)) >= ncp) --fcl;          // never wider than the grid ...
+    while (fcl < 5 && (32 >> (fcl + 1)) >= nrg) ++fcl;         // ... nor taller
+    FootMap m;
+    m.fcl = fcl;
+    const int FC = 1 << fcl, FR = 32 >> fcl;
+    m.nfc = (ncp + FC - 1) / FC;
+    m.nfoot = m.nfc * ((nrg + FR - 1) / FR);
+    return m;
+}
+
+// upper bound of FootMap::nfoot over every footprint shape (host-side grid sizing)
+template <int R>
+inline int max_footprints(int ntg, int nug) {
+    const int ncp = (ntg + 1) >> 1, nrg = (nug + R - 1) / R;
+    int best = 0;
+    for (int fcl = 0; fcl <= 5; ++fcl) {
+        const int FC = 1 << fcl, FR = 32 >> fcl;
+        const int n = ((ncp + FC - 1) / FC) * ((nrg + FR - 1) / FR);
+        best = n > best ? n : best;
+    }
+    return best;
+}
+
+// Lane's pixel block inside footprint f, and the footprint's bounding box.
+struct LaneBlock {
+    int cp, rg;       // column pair / row group (clamped into the grid: duplicates do valid, unused work)
+    bool owns;        // false for a clamped duplicate
+    Footprint fp;
+};
+
+template <int R>
+__device__ __forceinline__ LaneBlock lane_block(const FootMap& m, int f, int lane, int ntg, int nug,
+                                                const float* pxs, const float* pys) {
+    const int ncp = (ntg + 1) >> 1, nrg = (nug + R - 1) / R;
+    const int FC = 1 << m.fcl, FR = 32 >> m.fcl;
+    const int fc = f % m.nfc, fr = f / m.nfc;
+    const int cpi = fc * FC + (lane & (FC - 1)), rgi = fr * FR + (lane >> m.fcl);
+    LaneBlock b;
+    b.owns = (cpi < ncp) && (rgi < nrg);
+    b.cp = min(cpi, ncp - 1);
+    b.rg = min(rgi, nrg - 1);
+    const int c0 = 2 * fc * FC, c1 = min(2 * min(fc * FC + FC - 1, ncp - 1) + 1, ntg - 1);
+    const int r0 = fr * FR * R, r1 = min((fr * FR + FR) * R - 1, nug - 1);
+    const float xa = pxs[c0], xb = pxs[c1], ya = pys[r0], yb = pys[r1];
+    b.fp.x0 = fminf(xa, xb); b.fp.x1 = fmaxf(xa, xb);
+    b.fp.y0 = fminf(ya, yb); b.fp.y1 = fmaxf(ya, yb);
+    return b;
+}
+
 // ------------------------------------------------------------------ the hot loop
 // Thread-owned pixel block: columns (px0, px1) x rows py[0..R).  Slot k = 2*r + c.
-// On return b1[k] = min_s D, t1[k] = tile holding it, b2[k] / b3[k] = 2nd / 3rd smallest tile minimum.
+// On return b1[k] = min_s D, t1[k] = tile holding it, b2[k] / b3[k] = 2nd / 3rd smallest tile minimum
+// among the tiles that were evaluated.
+//
+// Exact pruning (must be called by all 32 lanes of a converged warp; `fp` is the bounding box of
+// the warp's pixels).  Tiles are visited outwards from the one nearest in time to the footprint
+// centre.  A tile is skipped when the distance `lb` between its bounding box and the footprint
+// satisfies (lb - 4e-6)^2 (1 - 4e-6) > max over the warp's pixels of the running minimum b1:
+// every FP32 distance of such a tile exceeds b1 + tau32(b1) of every pixel of the warp (the FP32
+// rounding tolerance is 1.25e-6 absolute + 1.5e-7 relative in distance units, see tau32), so the
+// tile can neither hold the FP64 nearest segment nor a near-tie the resolve step has to look at.
 template <int R>
-__device__ __forceinline__ void scan_block(const SegTable& tb, float px0, float px1,
+__device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& fp, float px0, float px1,
                                            const float (&py)[R],
                                            float (&b1)[2 * R], int (&t1)[2 * R], float (&b2)[2 * R],
-                                           float (&b3)[2 * R]) {
+                                           float (&b3)[2 * R], int& tiles_done) {
     static_assert(R % 2 == 0, "rows are processed in pairs");
     const uint64_t px2 = pack2(px0, px1);
     uint64_t y2[R / 2];
@@ -227,7 +315,31 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, float px0, float 
 #pragma unroll
     for (int k = 0; k < 2 * R; ++k) { b1[k] = kBig; b2[k] = kBig; b3[k] = kBig; t1[k] = 0; }
     const int ntiles = tb.Spad / kTile;
-    for (int tile = 0; tile < ntiles; ++tile) {
+    // start tile: the one whose time span holds the footprint centre (segments are normally time ordered;
+    // any start is correct, a poor one only prunes less)
+    int ct;
+    {
+        const float xc = 0.5f * (fp.x0 + fp.x1);
+        const float xa = tb.bbox[0].x, xb = tb.bbox[ntiles - 1].y;
+        const float fr = (xb != xa) ? (xc - xa) / (xb - xa) : 0.f;
+        ct = min(max((int)(fr * (float)ntiles), 0), ntiles - 1);
+        for (int i = 0; i < ntiles && ct < ntiles - 1 && tb.bbox[ct].y < xc; ++i) ++ct;
+        for (int i = 0; i < ntiles && ct > 0 && tb.bbox[ct].x > xc; ++i) --ct;
+    }
+    float wmax = kBig;   // max over the warp's pixels of b1 (warp-uniform)
+    const int nsteps = 2 * max(ct, ntiles - 1 - ct) + 1;
+    for (int step = 0; step < nsteps; ++step) {
+        const int dd = (step + 1) >> 1;
+        const int tile = (step & 1) ? ct + dd : ct - dd;
+        if (tile < 0 || tile >= ntiles) continue;
+        {
+            const float4 bb = tb.bbox[tile];
+            const float dx = fmaxf(0.f, fmaxf(bb.x - fp.x1, fp.x0 - bb.y));
+            const float dy = fmaxf(0.f, fmaxf(bb.z - fp.y1, fp.y0 - bb.w));
+            const float lb = fmaxf(sqrtf(__fmaf_rn(dx, dx, dy * dy)) - 4.0e-6f, 0.f);
+            if (lb * lb * 0.999996f > wmax) continue;
+        }
+        ++tiles_done;
         float tm[2 * R];
 #pragma unroll
         for (int k = 0; k < 2 * R; ++k) tm[k] = kBig;
@@ -270,6 +382,7 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, float px0, float 
                 }
             }
         }
+        float mx = 0.f;
 #pragma unroll
         for (int k = 0; k < 2 * R; ++k) {
             const bool better = tm[k] < b1[k];
@@ -277,7 +390,10 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, float px0, float 
             b2[k] = fminf(b2[k], fmaxf(tm[k], b1[k]));
             t1[k] = better ? tile : t1[k];
             b1[k] = fminf(b1[k], tm[k]);
+            mx = fmaxf(mx, b1[k]);
         }
+        // non-negative floats order like their bit patterns: one REDUX gives the warp maximum
+        wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
     }
 }
 
@@ -309,6 +425,7 @@ struct PrepOut {
     double2* pn;    // [nt]
     float4* A;      // [Spad]  {ex, ey, -am, -bm}
     float* H;       // [Spad]
+    float4* bbox;   // [Spad / kTile]  per-tile vertex bounding boxes (scaled frame)
     float* pxs;     // [ntg]  scaled local pixel time coordinates
     float* pys;     // [nug]
     WinHdr* hdr;    // [1]
@@ -392,6 +509,16 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
             h = 0.f;
         }
         o.A[s] = A; o.H[s] = h;
+    }
+    for (int tile = tid; tile < Spad / kTile; tile += nth) {
+        const int s0 = tile * kTile, s1 = min(s0 + kTile, S);      // vertices s0 .. s1 inclusive
+        double xlo = CUDART_INF, xhi = -CUDART_INF, ylo = CUDART_INF, yhi = -CUDART_INF;
+        for (int j = s0; j <= s1; ++j) {
+            const double2 p = o.pn[j];
+            xlo = fmin(xlo, p.x); xhi = fmax(xhi, p.x); ylo = fmin(ylo, p.y); yhi = fmax(yhi, p.y);
+        }
+        o.bbox[tile] = make_float4((float)((xlo - ccx) * sigma), (float)((xhi - ccx) * sigma),
+                                   (float)((ylo - ccy) * sigma), (float)((yhi - ccy) * sigma));
     }
     for (int i = tid; i < ntg; i += nth)
         o.pxs[i] = (float)((lin_axis(T0, Ts, Tl, i, ntg) - ccx) * sigma);

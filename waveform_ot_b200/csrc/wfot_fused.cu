@@ -35,7 +35,7 @@ struct FQEntry { int pix; float b1; };
 // from the `extern __shared__` symbol inside each kernel so the compiler keeps them in the
 // shared address space (LDS/STS instead of generic loads).
 struct SmemLayout {
-    int pn, A, H, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
+    int pn, A, H, bbox, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
     int total;
 };
 
@@ -60,6 +60,7 @@ __host__ __device__ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad,
     L.hdr = take(128);
     L.queue = take(kFQCap * (int)sizeof(FQEntry));
     L.H = take(Spad * 4);
+    L.bbox = take((Spad / kTile) * 16);
     L.pxs = take(ntg_pad * 4);
     L.pys = take(nug_pad * 4);
     L.posf = take(nmax * 4);
@@ -86,6 +87,7 @@ struct FusedArgs {
     double2* const s_pn = reinterpret_cast<double2*>(smem_raw + (L).pn);                 \
     float4* const s_A = reinterpret_cast<float4*>(smem_raw + (L).A);                     \
     float* const s_H = reinterpret_cast<float*>(smem_raw + (L).H);                       \
+    float4* const s_bbox = reinterpret_cast<float4*>(smem_raw + (L).bbox);               \
     float* const s_pxs = reinterpret_cast<float*>(smem_raw + (L).pxs);                   \
     float* const s_pys = reinterpret_cast<float*>(smem_raw + (L).pys);                   \
     double* const s_margt = reinterpret_cast<double*>(smem_raw + (L).margt);             \
@@ -126,16 +128,15 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     const size_t slab = (size_t)blockIdx.x * npix;
-    const int ncp = (a.ntg + 1) >> 1, nrg = (a.nug + R - 1) / R, nblk = ncp * nrg;
-    const SegTable tb{s_A, s_H, S, a.Spad};
-    int zero_dist = 0, slow = 0, common = 0, degen = 0;
+    const SegTable tb{s_A, s_H, s_bbox, S, a.Spad};
+    int zero_dist = 0, slow = 0, common = 0, degen = 0, tiles = 0;
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         // ---------------- P0: window -> shared memory
         const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
-        if (tid == 0) { s_hdr->degenerate = 0; *s_qcount = 0; }
+        if (tid == 0) { s_hdr->degenerate = 0; s_qcount[0] = 0; s_qcount[1] = 0; }
         __syncthreads();
-        PrepOut po{s_pn, s_A, s_H, s_pxs, s_pys, s_hdr};
+        PrepOut po{s_pn, s_A, s_H, s_bbox, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
         __syncthreads();
@@ -146,16 +147,25 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         for (int j = tid; j < 2 * a.nt; j += 256) s_gbins[j] = 0.0;
         __syncthreads();
 
-        // ---------------- P1: nearest segment per pixel
-        for (int blk = tid; blk < nblk; blk += 256) {
-            const int cp = blk % ncp, rg = blk / ncp;
+        // ---------------- P1: nearest segment per pixel.  Warps draw footprints from a shared counter
+        //                  (the pruned scan makes their cost uneven).
+        const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(s_pxs[a.ntg - 1] - s_pxs[0]),
+                                           fabsf(s_pys[a.nug - 1] - s_pys[0]));
+        for (;;) {
+            int f = 0;
+            if (lane == 0) f = atomicAdd(s_qcount + 1, 1);
+            f = __shfl_sync(0xffffffffu, f, 0);
+            if (f >= fm.nfoot) break;
+            const LaneBlock lb = lane_block<R>(fm, f, lane, a.ntg, a.nug, s_pxs, s_pys);
+            const int cp = lb.cp, rg = lb.rg;
             const int it0 = 2 * cp, it1 = min(2 * cp + 1, a.ntg - 1);
             float py[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) py[r] = s_pys[min(rg * R + r, a.nug - 1)];
             float b1[2 * R], b2[2 * R], b3[2 * R];
             int t1[2 * R];
-            scan_block<R>(tb, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3);
+            scan_block<R>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles);
+            if (!lb.owns) continue;
             float lb1[2 * R], lb2[2 * R], lb3[2 * R];
             int lt1[2 * R];
 #pragma unroll
@@ -302,6 +312,8 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         if (slow) atomicAdd(a.status + WFOT_STAT_SLOW_PIXELS, slow);
         if (common) atomicAdd(a.status + WFOT_STAT_COMMON_CDF, common);
         if (degen) atomicAdd(a.status + WFOT_STAT_DEGENERATE_SEG, degen);
+        if (lane == 0 && tiles)
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.status + WFOT_STAT_SCAN_TILES), (unsigned long long)tiles);
     }
 }
 
@@ -313,26 +325,30 @@ __global__ void __launch_bounds__(256, 2) k_scan_probe(FusedArgs a, float* out) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     const int tid = threadIdx.x, S = a.nt - 1;
-    const int ncp = (a.ntg + 1) >> 1, nrg = (a.nug + R - 1) / R, nblk = ncp * nrg;
-    const SegTable tb{s_A, s_H, S, a.Spad};
+    const SegTable tb{s_A, s_H, s_bbox, S, a.Spad};
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
         if (tid == 0) s_hdr->degenerate = 0;
         __syncthreads();
-        PrepOut po{s_pn, s_A, s_H, s_pxs, s_pys, s_hdr};
+        PrepOut po{s_pn, s_A, s_H, s_bbox, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, 0, po, s_red, nullptr);
         __syncthreads();
         const float inv_sigma = (float)(1.0 / s_hdr->sigma);
-        for (int blk = tid; blk < nblk; blk += 256) {
-            const int cp = blk % ncp, rg = blk / ncp;
+        const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(s_pxs[a.ntg - 1] - s_pxs[0]),
+                                           fabsf(s_pys[a.nug - 1] - s_pys[0]));
+        int tiles = 0;
+        for (int f = tid >> 5; f < fm.nfoot; f += 8) {
+            const LaneBlock lb = lane_block<R>(fm, f, tid & 31, a.ntg, a.nug, s_pxs, s_pys);
+            const int cp = lb.cp, rg = lb.rg;
             const int it0 = 2 * cp, it1 = min(2 * cp + 1, a.ntg - 1);
             float py[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) py[r] = s_pys[min(rg * R + r, a.nug - 1)];
             float b1[2 * R], b2[2 * R], b3[2 * R];
             int t1[2 * R];
-            scan_block<R>(tb, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3);
+            scan_block<R>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles);
+            if (!lb.owns) continue;
 #pragma unroll
             for (int k = 0; k < 2 * R; ++k) {
                 const int it = 2 * cp + (k & 1), iu = rg * R + (k >> 1);

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs a) {
     o.pn = a.ws.pn + (size_t)wl * a.nt;
     o.A = a.ws.A + (size_t)wl * a.ws.Spad;
     o.H = a.ws.H + (size_t)wl * a.ws.Spad;
+    o.bbox = a.ws.bbox + (size_t)wl * (a.ws.Spad / kTile);
     o.pxs = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
     o.pys = a.ws.pys + (size_t)wl * a.ws.nug_pad;
     o.hdr = a.ws.hdr + wl;
@@ -88,7 +89,8 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     const long long b = a.b0 + wl;
     const int Spad = a.ws.Spad, S = a.nt - 1;
     float4* sA = reinterpret_cast<float4*>(smem_raw);
-    float* sH = reinterpret_cast<float*>(sA + Spad);
+    float4* sBB = sA + Spad;
+    float* sH = reinterpret_cast<float*>(sBB + Spad / kTile);
     float* sPx = sH + Spad;
     float* sPy = sPx + a.ws.ntg_pad;
     QEntry* queue = reinterpret_cast<QEntry*>(sPy + a.ws.nug_pad);
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
         const float4* gA = a.ws.A + (size_t)wl * Spad;
         const float* gH = a.ws.H + (size_t)wl * Spad;
         for (int i = tid; i < Spad; i += 256) { sA[i] = gA[i]; sH[i] = gH[i]; }
+        const float4* gBB = a.ws.bbox + (size_t)wl * (Spad / kTile);
+        for (int i = tid; i < Spad / kTile; i += 256) sBB[i] = gBB[i];
         const float* gx = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
         const float* gy = a.ws.pys + (size_t)wl * a.ws.nug_pad;
         for (int i = tid; i < a.ntg; i += 256) sPx[i] = gx[i];
@@ -107,19 +111,21 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     }
     __syncthreads();
     const double2* pn = a.ws.pn + (size_t)wl * a.nt;
-    SegTable tb{sA, sH, S, Spad};
-    const int ncp = (a.ntg + 1) >> 1, nrg = (a.nug + R - 1) / R;
-    const int blk = blockIdx.x * 256 + tid;
-    int zero_dist = 0, slow = 0;
-    if (blk < ncp * nrg) {
-        const int cp = blk % ncp, rg = blk / ncp;
+    SegTable tb{sA, sH, sBB, S, Spad};
+    const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(sPx[a.ntg - 1] - sPx[0]), fabsf(sPy[a.nug - 1] - sPy[0]));
+    const int foot = blockIdx.x * 8 + (tid >> 5);     // one warp per footprint (warp-uniform)
+    int zero_dist = 0, slow = 0, tiles = 0;
+    if (foot < fm.nfoot) {
+        const LaneBlock lb = lane_block<R>(fm, foot, tid & 31, a.ntg, a.nug, sPx, sPy);
+        const int cp = lb.cp, rg = lb.rg;
         const int it0 = 2 * cp, it1 = min(2 * cp + 1, a.ntg - 1);
         float py[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) py[r] = sPy[min(rg * R + r, a.nug - 1)];
         float b1[2 * R], b2[2 * R], b3[2 * R];
         int t1[2 * R];
-        scan_block<R>(tb, sPx[it0], sPx[it1], py, b1, t1, b2, b3);
+        scan_block<R>(tb, lb.fp, sPx[it0], sPx[it1], py, b1, t1, b2, b3, tiles);
+        if (lb.owns) {
         // The epilogue is deliberately NOT unrolled (FP64 division/exp per pixel would
         // multiply the code size by 2R); the scan results move to local arrays first.
         float lb1[2 * R], lb2[2 * R], lb3[2 * R];
@@ -142,6 +148,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
             }
             emit_pixel(a, pn, hdr, b, it, iu, hit, pyd, zero_dist);
         }
+        }
     }
     __syncthreads();
     {   // ambiguous pixels: one warp each, all segments
@@ -158,6 +165,8 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     if (a.status) {
         if (zero_dist) atomicAdd(a.status + WFOT_STAT_ZERO_DIST, zero_dist);
         if (slow) atomicAdd(a.status + WFOT_STAT_SLOW_PIXELS, slow);
+        if ((tid & 31) == 0 && tiles)
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.status + WFOT_STAT_SCAN_TILES), (unsigned long long)tiles);
     }
 }
 
@@ -481,12 +490,11 @@ int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long
     if (chunk > kFpChunk) chunk = kFpChunk;
     FpWorkspace ws = fp_workspace_carve((void*)base, chunk, nt, nug, ntg);
     constexpr int R = 8;
-    const size_t smem = (size_t)ws.Spad * 20 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
+    const size_t smem = (size_t)ws.Spad * 21 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
     if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(k_fingerprint<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_fingerprint)");
-    const int ncp = (ntg + 1) / 2, nrg = (nug + R - 1) / R;
-    const int gx = (ncp * nrg + 255) / 256;
+    const int gx = (max_footprints<R>(ntg, nug) + 7) / 8;     // 8 warps = 8 footprints per CTA
     for (long long b0 = 0; b0 < B; b0 += chunk) {
         const int nb = (int)((B - b0) < chunk ? (B - b0) : chunk);
         PrepArgs pa{t, w, in_dtype, t_stride, nt, grids, n_grids, b0, nug, ntg, 0, ws, pn, status};
