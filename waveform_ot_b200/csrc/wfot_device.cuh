@@ -63,8 +63,8 @@ struct WinHdr {
     double sigma;              // power-of-two scale of the FP32 frame
     double du;                 // u1 - u0 (raw amplitude box)
     double u0raw, u1raw;       // raw amplitude box before an arctan transform
-    int degenerate;            // number of zero-length segments
-    int pad;
+    int degenerate;            // number of zero-length segments          } both zeroed by the caller
+    int nonmono;               // number of time-reversed segments        } before prep_window()
 };
 
 // FP32 segment table in the rotated frame (shared or global memory)
@@ -74,6 +74,7 @@ struct SegTable {
     const float4* bbox;   // per tile of kTile segments: {xlo, xhi, ylo, yhi} of its vertices (scaled frame)
     int S;             // real segments
     int Spad;          // padded to a multiple of kTile
+    bool mono;         // sample times are non-decreasing: tiles are ordered along the time axis
 };
 
 // Pixel footprint of one warp in the scaled frame (warp-uniform): the scan skips every segment
@@ -146,34 +147,63 @@ struct PixelHit {
 // afterwards in ascending segment order (strict '<' keeps np.argmin's first-minimum rule),
 // so lanes of a warp do not serialise on each other's candidates.
 // Returns false if the pixel must go to the full rescan.
+// FP32 re-evaluation of the 16 segments of one tile for one pixel: bit j set <=> D32(segment) <= thr.
+// Padding segments evaluate to kPadD > thr, so no bounds check is needed.
+__device__ __forceinline__ unsigned tile_mask(const SegTable& tb, int tile, float px, float py, float thr) {
+    const float4* __restrict__ A = tb.A + tile * kTile;
+    const float4* __restrict__ H4 = reinterpret_cast<const float4*>(tb.H + tile * kTile);
+    unsigned mask = 0u;
+#pragma unroll
+    for (int q4 = 0; q4 < kTile / 4; ++q4) {
+        const float4 h = H4[q4];
+        const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 a = A[4 * q4 + i];
+            const float P = __fmaf_rn(px, a.x, a.z);
+            const float Q = __fmaf_rn(px, a.y, a.w);
+            const float al = __fmaf_rn(py, a.y, P);
+            const float pe = __fmaf_rn(py, -a.x, Q);
+            const float tm = __saturatef(__fadd_rn(fabsf(al), -hh[i]));
+            const float d32 = __fmaf_rn(tm, tm, __fmul_rn(pe, pe));
+            mask |= (d32 <= thr) ? (1u << (4 * q4 + i)) : 0u;
+        }
+    }
+    return mask;
+}
+
+// FP64 reference-order evaluation of the candidate segments of one tile, ascending (strict '<'
+// keeps np.argmin's first-minimum rule across calls made in ascending tile order).
+__device__ __forceinline__ void eval_candidates(const double2* __restrict__ pn, int tile, unsigned mask,
+                                                double px, double py, PixelHit& hit) {
+    while (mask) {
+        const int j = __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        double D, l;
+        eval64(pn, tile * kTile + j, px, py, D, l);
+        if (D < hit.D) { hit.D = D; hit.lam = l; hit.s = tile * kTile + j; }
+    }
+}
+
 __device__ __forceinline__ bool resolve_pixel(const SegTable& tb, const double2* __restrict__ pn,
                                               float pxl, float pyl, double px, double py,
                                               float b1, int t1, float b2, float b3, PixelHit& hit) {
     const float thr = b1 + tau32(b1);
-    int lo = t1 * kTile, n = kTile;
-    const bool multi = (b2 <= thr);
-    if (multi) {
-        if (b3 <= thr) return false;
-        lo -= kTile; n = 3 * kTile;
+    hit.D = CUDART_INF; hit.lam = 0.0; hit.s = t1 * kTile;
+    if (b2 > thr) {                                   // the common case: one tile
+        eval_candidates(pn, t1, tile_mask(tb, t1, pxl, pyl, thr), px, py, hit);
+        return true;
     }
-    unsigned long long mask = 0ull;
-    float adj = kBig;
-    for (int j = 0; j < n; ++j) {
-        const int s = lo + j;
-        if (s < 0 || s >= tb.S) continue;
-        const float d32 = eval32(tb, s, pxl, pyl);
-        if (d32 <= thr) mask |= (1ull << j);
-        if (multi && (j < kTile || j >= 2 * kTile)) adj = fminf(adj, d32);
-    }
-    if (multi && !(adj <= thr)) return false;      // the second tile is not a neighbour
-    hit.D = CUDART_INF; hit.lam = 0.0; hit.s = max(lo, 0);
-    while (mask) {
-        const int j = __ffsll((long long)mask) - 1;
-        mask &= mask - 1ull;
-        double D, l;
-        eval64(pn, lo + j, px, py, D, l);
-        if (D < hit.D) { hit.D = D; hit.lam = l; hit.s = lo + j; }
-    }
+    if (b3 <= thr) return false;
+    // exactly one other tile holds a candidate: resolved here only if it is a neighbour of t1
+    const int ntiles = tb.Spad / kTile;
+    const unsigned m0 = (t1 > 0) ? tile_mask(tb, t1 - 1, pxl, pyl, thr) : 0u;
+    const unsigned m2 = (t1 + 1 < ntiles) ? tile_mask(tb, t1 + 1, pxl, pyl, thr) : 0u;
+    if ((m0 | m2) == 0u) return false;
+    const unsigned m1 = tile_mask(tb, t1, pxl, pyl, thr);
+    if (m0) eval_candidates(pn, t1 - 1, m0, px, py, hit);
+    eval_candidates(pn, t1, m1, px, py, hit);
+    if (m2) eval_candidates(pn, t1 + 1, m2, px, py, hit);
     return true;
 }
 
@@ -328,16 +358,24 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
     }
     float wmax = kBig;   // max over the warp's pixels of b1 (warp-uniform)
     const int nsteps = 2 * max(ct, ntiles - 1 - ct) + 1;
+    bool ldone = false, rdone = false;   // time-ordered tables: nothing farther out on that side can matter
     for (int step = 0; step < nsteps; ++step) {
         const int dd = (step + 1) >> 1;
-        const int tile = (step & 1) ? ct + dd : ct - dd;
-        if (tile < 0 || tile >= ntiles) continue;
+        const bool right = (step & 1);
+        const int tile = right ? ct + dd : ct - dd;
+        if (right ? rdone : ldone) { if (ldone && rdone) break; continue; }
+        if (tile < 0) { ldone = true; continue; }
+        if (tile >= ntiles) { rdone = true; continue; }
         {
             const float4 bb = tb.bbox[tile];
             const float dx = fmaxf(0.f, fmaxf(bb.x - fp.x1, fp.x0 - bb.y));
             const float dy = fmaxf(0.f, fmaxf(bb.z - fp.y1, fp.y0 - bb.w));
             const float lb = fmaxf(sqrtf(__fmaf_rn(dx, dx, dy * dy)) - 4.0e-6f, 0.f);
-            if (lb * lb * 0.999996f > wmax) continue;
+            if (lb * lb * 0.999996f > wmax) {
+                const float lx = fmaxf(dx - 4.0e-6f, 0.f);
+                if (tb.mono && step > 0 && lx * lx * 0.999996f > wmax) { if (right) rdone = true; else ldone = true; }
+                continue;
+            }
         }
         ++tiles_done;
         float tm[2 * R];
@@ -488,13 +526,14 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
     const double sigma = ldexp(1.0, -ex);
     const int S = nt - 1;
     const int Spad = ((S + kTile - 1) / kTile) * kTile;
-    int degen = 0;
+    int degen = 0, nonmono = 0;
     for (int s = tid; s < Spad; s += nth) {
         float4 A;
         float h;
         if (s < S) {
             const double2 a = o.pn[s], b = o.pn[s + 1];
             const double cx = b.x - a.x, cy = b.y - a.y;
+            nonmono += !(cx >= 0.0);
             const double len = sqrt(cx * cx + cy * cy);
             double exd = 1.0, eyd = 0.0;
             if (len > 0.0) { exd = cx / len; eyd = cy / len; } else { degen++; }
@@ -525,11 +564,11 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
     for (int i = tid; i < nug; i += nth)
         o.pys[i] = (float)((lin_axis(U0, Us, Ul, i, nug) - ccy) * sigma);
     if (degen) atomicAdd(&o.hdr->degenerate, degen);   // zeroed by the caller before prep_window
+    if (nonmono) atomicAdd(&o.hdr->nonmono, nonmono);
     if (tid == 0) {
         WinHdr* h = o.hdr;
         h->T0 = T0; h->Tstep = Ts; h->Tlast = Tl; h->U0 = U0; h->Ustep = Us; h->Ulast = Ul;
         h->ccx = ccx; h->ccy = ccy; h->sigma = sigma; h->du = du; h->u0raw = u0raw; h->u1raw = u1raw;
-        h->pad = 0;
     }
 }
 
