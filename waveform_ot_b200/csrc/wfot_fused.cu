@@ -135,6 +135,11 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         // ---------------- P0: window -> shared memory
         const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
         if (tid == 0) { s_hdr->degenerate = 0; s_hdr->nonmono = 0; s_qcount[0] = 0; s_qcount[1] = 0; }
+        if (a.grad) {      // P4 accumulates into these rows with L2 reductions
+            double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
+            for (int j = tid; j < 2 * a.nt; j += 256) g0[j] = 0.0;
+            __threadfence();
+        }
         __syncthreads();
         PrepOut po{s_pn, s_A, s_H, s_bbox, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
@@ -145,7 +150,6 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         degen += (tid == 0) ? hdr.degenerate : 0;
         for (int i = tid; i < a.ntg; i += 256) s_xt[i] = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, i, a.ntg);
         for (int i = tid; i < a.nug; i += 256) s_xu[i] = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, i, a.nug);
-        for (int j = tid; j < 2 * a.nt; j += 256) s_gbins[j] = 0.0;
         __syncthreads();
 
         // ---------------- P1: nearest segment per pixel.  Warps draw footprints from a shared counter
@@ -256,12 +260,28 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
             if (a.dwg) a.dwg[b] = (a.pmask & 1) ? rt.dpos1 : rt.dpos2;  // OTlib.py:1121
         }
 
-        // ---------------- P4: gradient assembly (FingerprintLib.py:205-228)
+        // ---------------- P4: gradient assembly (FingerprintLib.py:205-228).  A thread walks a pixel
+        //                  column, combines runs of equal nearest segment and adds each run to the
+        //                  window's gradient rows with fire-and-forget FP64 reductions in L2
+        //                  (RED.ADD.F64; shared-memory FP64 atomics are CAS loops).  The rows were
+        //                  zeroed in P0.
         if (a.grad) {
             // chain vectors: (R - <R, pbar>)/A  (OTlib.py:1144-1147)
             for (int c = tid; c < a.ntg; c += 256) s_Rt[c] = (s_Rt[c] - Gt) / A;
             for (int c = tid; c < a.nug; c += 256) s_Ru[c] = (s_Ru[c] - Gu) / A;
+            const double scale = -1.0 / (a.lambda * hdr.du);             // FingerprintLib.py:228,376-378
+            for (int j = tid; j < a.nt; j += 256) {
+                double chain = scale;
+                if (a.transform) {   // d(un)/du, ricker_util.py:273,393-397
+                    const double wj = load_sample(a.w, a.dtype, (long long)b * a.nt + j);
+                    const double up = ((wj - hdr.u0raw) + (wj - hdr.u1raw)) / (hdr.u1raw - hdr.u0raw);
+                    chain *= 2.0 / ((hdr.u1raw - hdr.u0raw) * CUDART_PI * (1.0 + up * up));
+                }
+                s_gbins[j] = chain;
+            }
             __syncthreads();
+            double* const gt = a.grad + ((size_t)b * 2) * a.nt;
+            double* const gu = gt + a.nt;
             for (int c = tid; c < a.ntg; c += 256) {
                 const double ct = s_Rt[c];
                 int cur = -1;
@@ -279,8 +299,9 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
                         if (iu0 + j >= a.nug) break;
                         if (idx[j] != cur) {
                             if (cur >= 0) {
-                                atomicAdd(&s_gbins[cur], t0); atomicAdd(&s_gbins[cur + 1], t1);
-                                atomicAdd(&s_gbins[a.nt + cur], u0); atomicAdd(&s_gbins[a.nt + cur + 1], u1);
+                                const double c0 = s_gbins[cur], c1 = s_gbins[cur + 1];
+                                atomicAdd(gt + cur, t0 * c0); atomicAdd(gt + cur + 1, t1 * c1);
+                                atomicAdd(gu + cur, u0 * c0); atomicAdd(gu + cur + 1, u1 * c1);
                             }
                             cur = idx[j]; t0 = t1 = u0 = u1 = 0.0;
                         }
@@ -289,21 +310,10 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
                     }
                 }
                 if (cur >= 0) {
-                    atomicAdd(&s_gbins[cur], t0); atomicAdd(&s_gbins[cur + 1], t1);
-                    atomicAdd(&s_gbins[a.nt + cur], u0); atomicAdd(&s_gbins[a.nt + cur + 1], u1);
+                    const double c0 = s_gbins[cur], c1 = s_gbins[cur + 1];
+                    atomicAdd(gt + cur, t0 * c0); atomicAdd(gt + cur + 1, t1 * c1);
+                    atomicAdd(gu + cur, u0 * c0); atomicAdd(gu + cur + 1, u1 * c1);
                 }
-            }
-            __syncthreads();
-            const double scale = -1.0 / (a.lambda * hdr.du);             // FingerprintLib.py:228,376-378
-            for (int j = tid; j < a.nt; j += 256) {
-                double chain = scale;
-                if (a.transform) {   // d(un)/du, ricker_util.py:273,393-397
-                    const double wj = load_sample(a.w, a.dtype, (long long)b * a.nt + j);
-                    const double up = ((wj - hdr.u0raw) + (wj - hdr.u1raw)) / (hdr.u1raw - hdr.u0raw);
-                    chain *= 2.0 / ((hdr.u1raw - hdr.u0raw) * CUDART_PI * (1.0 + up * up));
-                }
-                a.grad[((size_t)b * 2) * a.nt + j] = s_gbins[j] * chain;
-                a.grad[((size_t)b * 2 + 1) * a.nt + j] = s_gbins[a.nt + j] * chain;
             }
         }
         __syncthreads();
