@@ -45,7 +45,7 @@ def main():
         pairs = nb * nug * ntg * (nt - 1)
         print("%s fused: B=%d %.2f ms  %.1f windows/s  %.3f Tpair/s  alg %.1f TFLOP/s  slow_px/window %.1f  executed pairs %.3f" % (
             name, nb, ms, nb / ms * 1e3, pairs / ms / 1e9, 15 * pairs / ms / 1e9,
-            r["status"].read()[4] / nb, r["status"].scan_tiles() * 8192.0 / pairs))
+            r["status"].read()[4] / nb, r["status"].scan_pairs() / pairs))
         d32 = torch.empty((nb, nug, ntg), dtype=torch.float32, device="cuda")
         fns = lambda: C.check(C.lib.wfot_scan_probe(C.ptr(t), C.ptr(w[1:]), 0, 0, nt, C.ptr(g), 1, nb, nug, ntg, C.ptr(d32), None))
         fns(); ms0 = ev_time(fns)

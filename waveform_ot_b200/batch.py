@@ -78,10 +78,10 @@ class Status:
     def read(self):
         return self.t.cpu().numpy()
 
-    def scan_tiles(self):
-        """64-bit count (slots 6-7) of (warp, segment-tile) pairs the pruned scan evaluated;
-        x 8192 = executed (pixel, segment) pairs."""
-        return int(self.t.cpu().numpy()[C.STAT_SCAN_TILES:C.STAT_SCAN_TILES + 2].view("int64")[0])
+    def scan_pairs(self):
+        """Executed (pixel, segment) pairs of the pruned scan (64-bit counter in slots 6-7,
+        kept by the kernels in units of 4096 pairs)."""
+        return 4096 * int(self.t.cpu().numpy()[C.STAT_SCAN_TILES:C.STAT_SCAN_TILES + 2].view("int64")[0])
 
 
 def fingerprint_batch(t, w, grids, nug, ntg, lambdav, q=None, tantheta=1.0, fpgrids=None,

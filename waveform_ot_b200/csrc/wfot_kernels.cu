@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
         if (zero_dist) atomicAdd(a.status + WFOT_STAT_ZERO_DIST, zero_dist);
         if (slow) atomicAdd(a.status + WFOT_STAT_SLOW_PIXELS, slow);
         if ((tid & 31) == 0 && tiles)
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.status + WFOT_STAT_SCAN_TILES), (unsigned long long)tiles);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.status + WFOT_STAT_SCAN_TILES),
+                      (unsigned long long)tiles * (R / 4));
     }
 }
 
@@ -489,7 +490,7 @@ int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long
     if (chunk > B) chunk = B;
     if (chunk > kFpChunk) chunk = kFpChunk;
     FpWorkspace ws = fp_workspace_carve((void*)base, chunk, nt, nug, ntg);
-    constexpr int R = 8;
+    constexpr int R = 4;
     const size_t smem = (size_t)ws.Spad * 21 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
     if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(k_fingerprint<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
