@@ -2,7 +2,7 @@
 //   k_prep           window normalisation + FP32 segment table   (FingerprintLib.py:53-115)
 //   k_fingerprint    nearest segment / distance / density / d(d)/dw (FingerprintLib.py:230-385)
 //   k_marginals      2-D normalisation + time/amplitude marginals (OTlib.py:90-93,146-160)
-//   k_ot1d           batched 1-D W1/W2 + derivatives              (OTlib.py:596-706)
+//   (batched 1-D W1/W2 + derivatives: wfot_ot1d.cu)
 //   k_pdfderiv       pixel -> sample segmented reduction          (FingerprintLib.py:182-228)
 //   k_chain          J . dr batched                               (ricker_util.py:399-400)
 // The fused throughput kernel lives in wfot_fused.cu.
@@ -226,67 +226,6 @@ __global__ void __launch_bounds__(256) k_marginals(const double* __restrict__ pd
     if (tid == 0) amp[b] = A;
     const int nneg = __syncthreads_count(neg > 0);
     if (tid == 0 && nneg && status) atomicAdd(status + WFOT_STAT_NEG_PDF, 1);
-}
-
-// ============================================================ k_ot1d
-struct OtArgs {
-    const void* f; const void* g; int dtype; const double* xf; const double* xg;
-    long long f_stride, g_stride, xf_stride, xg_stride; int n, m, pmask, deriv;
-    double* W; double* dW1; double* dW2; double* dpos; double* amp_f; double* cdf_f; double* cdf_g;
-    int32_t* merge_order; int32_t* status;
-};
-
-__global__ void __launch_bounds__(256) k_ot1d(OtArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const long long b = blockIdx.x;
-    const int n = a.n, m = a.m, K = n + m - 1, tid = threadIdx.x;
-    double* cf = reinterpret_cast<double*>(smem_raw);
-    double* cg = cf + n;
-    double* tk = cg + m;
-    double* dx = tk + K;
-    double* E = dx + K;
-    double* xfs = E + n;
-    double* xgs = xfs + n;
-    double* red = xgs + m;
-    int* posf = reinterpret_cast<int*>(red + 34);
-    // target CDF: same OTpdf normalisation as the source (libs/OTlib.py:92-93,112-114)
-    double part = 0.0;
-    int neg = 0;
-    for (int i = tid; i < m; i += 256) {
-        const double v = load_sample(a.g, a.dtype, b * a.g_stride + i);
-        cg[i] = v; part += v; neg += (v < 0.0);
-    }
-    const double ampg = block_sum(part, red);
-    for (int i = tid; i < m; i += 256) cg[i] = cg[i] / ampg;
-    __syncthreads();
-    block_scan(cg, m, false, red);
-    const double lastg = cg[m - 1];
-    __syncthreads();
-    for (int i = tid; i < m; i += 256) cg[i] = cg[i] / lastg;
-    for (int j = tid; j < n; j += 256) {
-        cf[j] = load_sample(a.f, a.dtype, b * a.f_stride + j);
-        xfs[j] = a.xf[b * a.xf_stride + j];
-    }
-    for (int i = tid; i < m; i += 256) xgs[i] = a.xg[b * a.xg_stride + i];
-    __syncthreads();
-    OtScratch sc{cf, tk, dx, E, posf, red};
-    double* o1 = (a.deriv && a.dW1) ? a.dW1 + (size_t)b * n : nullptr;
-    double* o2 = (a.deriv && a.dW2) ? a.dW2 + (size_t)b * n : nullptr;
-    const OtResult r = block_ot1d(sc, n, cg, m, xfs, xgs, a.pmask, o1, o2,
-                                  a.merge_order ? a.merge_order + (size_t)b * K : nullptr);
-    if (a.cdf_f) for (int j = tid; j < n; j += 256) a.cdf_f[(size_t)b * n + j] = cf[j];
-    if (a.cdf_g) for (int i = tid; i < m; i += 256) a.cdf_g[(size_t)b * m + i] = cg[i];
-    if (tid == 0) {
-        if (a.W) { if (a.pmask & 1) a.W[2 * b] = r.W1; if (a.pmask & 2) a.W[2 * b + 1] = r.W2; }
-        if (a.dpos) { if (a.pmask & 1) a.dpos[2 * b] = r.dpos1; if (a.pmask & 2) a.dpos[2 * b + 1] = r.dpos2; }
-        if (a.amp_f) a.amp_f[b] = r.amp;
-        if (a.status) {
-            if (r.neg) atomicAdd(a.status + WFOT_STAT_NEG_PDF, 1);
-            if (r.common) atomicAdd(a.status + WFOT_STAT_COMMON_CDF, r.common);
-        }
-    }
-    const int nneg = __syncthreads_count(neg > 0);
-    if (tid == 0 && nneg && a.status) atomicAdd(a.status + WFOT_STAT_NEG_PDF, 1);
 }
 
 // ============================================================ k_otpdf1d
@@ -533,28 +472,6 @@ int wfot_otpdf1d_batch(const void* f, int in_dtype, int n, int B, double* amp, d
     k_otpdf1d<<<B, 256, smem, stream>>>(f, in_dtype, n, amp, pdf_norm, cdf, status);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_otpdf1d_batch launch");
-    return WFOT_OK;
-}
-
-int wfot_ot1d_batch(const void* f, const void* g, int in_dtype, const double* xf, const double* xg,
-                    long long f_stride, long long g_stride, long long xf_stride, long long xg_stride,
-                    int n, int m, int B, int pmask, int derivatives, double* W, double* dW1,
-                    double* dW2, double* dpos, double* amp_f, double* cdf_f, double* cdf_g,
-                    int32_t* merge_order, int32_t* status, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (!f || !g || !xf || !xg || n < 1 || m < 1 || B <= 0 || pmask < 1 || pmask > 3 ||
-        (in_dtype != WFOT_F32 && in_dtype != WFOT_F64))
-        return WFOT_ERR_INVALID_ARG;
-    const int K = n + m - 1;
-    const size_t smem = (size_t)(n + m + 2 * K + n + n + m + 34) * 8 + (size_t)n * 4;
-    if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(k_ot1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ot1d)");
-    OtArgs a{f, g, in_dtype, xf, xg, f_stride, g_stride, xf_stride, xg_stride, n, m, pmask, derivatives,
-             W, dW1, dW2, dpos, amp_f, cdf_f, cdf_g, merge_order, status};
-    k_ot1d<<<B, 256, smem, stream>>>(a);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "wfot_ot1d_batch launch");
     return WFOT_OK;
 }
 

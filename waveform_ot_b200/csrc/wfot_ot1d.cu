@@ -1,0 +1,444 @@
+// wfot_ot1d.cu -- batched 1-D optimal transport, one WARP per (source, target) pair (sm_100a).
+//
+// Replaces OTpdf.__init__ (1-D) + wasser(distfunc in {'W1','W2','W12'}, derivatives=...):
+// libs/OTlib.py:90-117 (normalise, cumsum -> CDF) and :596-706 (merge, W_p^p, derivatives).
+//
+// A warp owns one pair at a time; nothing but warp-level synchronisation is used:
+//   1. load f / g with 16-byte coalesced loads (lane L owns elements 4L..4L+3 of every 128-element
+//      round), FP64 sum -> amp, pdf/amp, FP64 prefix scan (4-element local scan + one warp scan per
+//      round), /last -> the two CDFs in shared memory (libs/OTlib.py:92-93,112-114);
+//   2. merge path: lane d binary-searches where diagonal d*ceil(K/32) of the (cf[:-1], cg) merge grid
+//      is crossed (source first on ties = a stable argsort of the concatenation, :668-669);
+//   3. each lane merges its K/32 knots sequentially: quantile ranks (bisect_left semantics, :671-672,
+//      including repeated CDF values), dx = x_f[indf] - x_g[indg], dt, and the fused epilogue
+//      W1 += |dx| dt, W2 += dx^2 dt, d/dx0 (:690-706); for the amplitude derivative the O(n) form of
+//      the dense (n x (n+m-1)) product at :682-686,694,704:
+//      E_j = |dx|^p at the merged position of source knot j minus the next knot's;
+//   4. suffix scan of E_j (parked in the dW output rows themselves) -> dW_i = (sum_{j>=i} E_j - Z)/amp.
+// Divisions by the per-pair scalars (amp, cdf[-1]) use one correctly rounded reciprocal and a fused
+// residual correction (q = x r; q += fma(-d, q, x) r), which reproduces IEEE division except in rare
+// last-bit cases; everything else is plain FP64 in a fixed order (run-to-run identical results).
+//
+// Algorithmic HBM bytes per pair: 4 (n + m) in (FP32 input) + 8 n per derivative vector out.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/wfot.h"
+#include "wfot_host.h"
+
+namespace wfot {
+
+struct Ot1dArgs {
+    const void* f; const void* g; int dtype; const double* xf; const double* xg;
+    long long f_stride, g_stride, xf_stride, xg_stride; int n, m, pmask, deriv; long long B;
+    double* W; double* dW1; double* dW2; double* dpos; double* amp_f; double* cdf_f; double* cdf_g;
+    int32_t* merge_order; int32_t* status;
+    int npad, mpad, wpc, xshared, need_e2;
+    size_t per_warp;
+};
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    return v;
+}
+
+// x / d with r = RN(1/d): one multiply and a fused residual correction
+__device__ __forceinline__ double div_by(double x, double d, double r) {
+    const double q = x * r;
+    return fma(fma(-d, q, x), r, q);
+}
+
+// four consecutive samples idx..idx+3 of a row as doubles (0 beyond n); 16-byte loads when aligned
+__device__ __forceinline__ void load4(const void* row, int dtype, bool vec, int idx, int n, double (&v)[4]) {
+    if (vec && idx + 3 < n) {
+        if (dtype == WFOT_F32) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + idx));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+            const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(row) + idx);
+            const double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+            v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double s = 0.0;
+            if (idx + i < n)
+                s = dtype == WFOT_F32 ? (double)reinterpret_cast<const float*>(row)[idx + i]
+                                      : reinterpret_cast<const double*>(row)[idx + i];
+            v[i] = s;
+        }
+    }
+}
+
+// OTpdf.__init__ for one 1-D density (libs/OTlib.py:91-93,112-114): c[0..n) <- cdf, returns amp.
+// c has room for npad = ceil(n/128)*128 doubles.  strict <- the CDF is strictly increasing.
+__device__ __forceinline__ double warp_cdf(const void* row, int dtype, int n, int npad, double* c,
+                                           double* cdf_out, int lane, int& neg, bool& strict) {
+    const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;     // 16-byte loads need an aligned row
+    double s = 0.0;
+    for (int base = 0; base < npad; base += 128) {
+        const int idx = base + 4 * lane;
+        double v[4];
+        load4(row, dtype, vec, idx, n, v);
+        neg |= (v[0] < 0.0) | (v[1] < 0.0) | (v[2] < 0.0) | (v[3] < 0.0);
+        s += (v[0] + v[1]) + (v[2] + v[3]);
+        *reinterpret_cast<double2*>(c + idx) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(c + idx + 2) = make_double2(v[2], v[3]);
+    }
+    const double amp = warp_sum(s);                                   // :92
+    const double ramp = 1.0 / amp;
+    double carry = 0.0;
+    for (int base = 0; base < npad; base += 128) {
+        const int idx = base + 4 * lane;
+        const double2 a0 = *reinterpret_cast<const double2*>(c + idx);
+        const double2 a1 = *reinterpret_cast<const double2*>(c + idx + 2);
+        const double c0 = div_by(a0.x, amp, ramp);                    // pdf / amp (:93)
+        const double c1 = c0 + div_by(a0.y, amp, ramp);
+        const double c2 = c1 + div_by(a1.x, amp, ramp);
+        const double c3 = c2 + div_by(a1.y, amp, ramp);
+        double inc = c3;                                              // warp inclusive scan of the lane totals
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(kFull, inc, off);
+            if (lane >= off) inc += o;
+        }
+        const double add = carry + (inc - c3);
+        *reinterpret_cast<double2*>(c + idx) = make_double2(add + c0, add + c1);
+        *reinterpret_cast<double2*>(c + idx + 2) = make_double2(add + c2, add + c3);
+        carry += __shfl_sync(kFull, inc, 31);
+    }
+    __syncwarp();
+    const double last = c[n - 1];                                     // cumsum[-1] (:113)
+    __syncwarp();                                                     // every lane has read it before it is rescaled
+    const double rl = 1.0 / last;
+    const bool resc = (last != 1.0);
+    bool ok = true;
+    double prev_hi = -CUDART_INF;                                     // last element of the previous round
+    for (int base = 0; base < npad; base += 128) {
+        const int idx = base + 4 * lane;
+        double2 a0 = *reinterpret_cast<const double2*>(c + idx);
+        double2 a1 = *reinterpret_cast<const double2*>(c + idx + 2);
+        if (resc) {                                                   // cdf / cdf[-1] (:114)
+            a0.x = div_by(a0.x, last, rl); a0.y = div_by(a0.y, last, rl);
+            a1.x = div_by(a1.x, last, rl); a1.y = div_by(a1.y, last, rl);
+            *reinterpret_cast<double2*>(c + idx) = a0;
+            *reinterpret_cast<double2*>(c + idx + 2) = a1;
+        }
+        double left = __shfl_up_sync(kFull, a1.y, 1);
+        if (lane == 0) left = prev_hi;
+        prev_hi = __shfl_sync(kFull, a1.y, 31);
+        ok = ok && (idx >= n || left < a0.x) && (idx + 1 >= n || a0.x < a0.y) &&
+             (idx + 2 >= n || a0.y < a1.x) && (idx + 3 >= n || a1.x < a1.y);
+        if (cdf_out) {
+            if (idx < n) cdf_out[idx] = a0.x;
+            if (idx + 1 < n) cdf_out[idx + 1] = a0.y;
+            if (idx + 2 < n) cdf_out[idx + 2] = a1.x;
+            if (idx + 3 < n) cdf_out[idx + 3] = a1.y;
+        }
+    }
+    strict = __all_sync(kFull, ok);
+    __syncwarp();
+    return amp;
+}
+
+// One lane's share of the merge: knots d0 .. d1-1, source knots [ia, ia1), target knots [ib, ib1).
+//   STRICT: both CDFs strictly increasing -> bisect_left ranks are the running counters
+//           (minus one for a target knot equal to the last consumed source knot);
+//   otherwise equal-value runs are tracked (repeated CDF values = empty bins).
+// With DERIV the per-source-knot E_j^{(p)} are parked in shared memory: slot j of `eA` (which may be
+// the cf array itself: entry j is dead once consumed, and lanes never read outside their own range
+// after the caller's __syncwarp) and of `eB` when both orders are wanted.
+struct MergeOut {
+    double w1, w2, p1, p2, z1, z2, first_c1, first_c2, pc1, pc2, pcf;
+    int pj, common;
+};
+
+template <bool STRICT, bool DERIV>
+__device__ __forceinline__ void lane_merge(const double* cf, const double* cg, const double* xf, const double* xg,
+                                           int n, int m, int d0, int d1, int ia, int ia1, int ib, int ib1,
+                                           double* e1s, double* e2s, int32_t* mo, MergeOut& o) {
+    double tprev = 0.0;
+    double runf_val = CUDART_NAN, rung_val = CUDART_NAN;
+    int runf_len = 0, rung_len = 0;               // lengths of the equal-value runs ending at ia-1 / ib-1
+    if (ia > 0) {
+        runf_val = cf[ia - 1]; runf_len = 1;
+        if (!STRICT) while (ia - 1 - runf_len >= 0 && cf[ia - 1 - runf_len] == runf_val) ++runf_len;
+        tprev = runf_val;
+    }
+    if (ib > 0) {
+        rung_val = cg[ib - 1]; rung_len = 1;
+        if (!STRICT) while (ib - 1 - rung_len >= 0 && cg[ib - 1 - rung_len] == rung_val) ++rung_len;
+        tprev = ia > 0 ? fmax(tprev, rung_val) : rung_val;
+    }
+    // heads and one-ahead prefetch, bounded by the lane's own ranges
+    double va = ia < ia1 ? cf[ia] : CUDART_INF, va1 = ia + 1 < ia1 ? cf[ia + 1] : CUDART_INF;
+    double vb = ib < ib1 ? cg[ib] : CUDART_INF, vb1 = ib + 1 < ib1 ? cg[ib + 1] : CUDART_INF;
+    __syncwarp();                                 // look-back reads done before any lane parks an E_j
+    double w1 = 0.0, w2 = 0.0, p1 = 0.0, p2 = 0.0, z1 = 0.0, z2 = 0.0;
+    double first_c1 = 0.0, first_c2 = 0.0;
+    int pj = -1, common = 0;                      // pending source knot (its E needs the next knot's |dx|^p)
+    double pc1 = 0.0, pc2 = 0.0, pcf = 0.0;
+    for (int k = d0; k < d1; ++k) {
+        const bool src = (va <= vb);              // source first on ties (stable argsort of [cf[:-1], cg], :668-669)
+        const double v = src ? va : vb;
+        int indf, indg;
+        if (STRICT) {
+            indf = ia - ((!src && v == runf_val) ? 1 : 0);       // bisect_left(cf, v) (:671)
+            indg = ib;                                           // bisect_left(cg, v) (:672)
+        } else {
+            const int eqf = (v == runf_val) ? runf_len : 0;
+            const int eqg = (v == rung_val) ? rung_len : 0;
+            indf = ia - eqf;
+            indg = src ? ib : ib - eqg;
+            if (src) runf_len = eqf + 1; else rung_len = eqg + 1;
+            if (!src) rung_val = v;
+        }
+        if (src && ib < m - 1) {                                 // np.intersect1d(cg[:-1], cf[:-1]) (:664)
+            const double nb = ib < ib1 ? vb : cg[ib];            // next target knot (maybe the next lane's)
+            common += (nb == v) ? 1 : 0;
+        }
+        if (mo) mo[k] = src ? ia : n - 1 + ib;
+        const double dx = xf[indf] - xg[indg];                   // :676-677
+        const double dt = v - tprev;                             // :673
+        tprev = v;
+        const double c1 = fabs(dx), c2 = dx * dx;
+        w1 = fma(c1, dt, w1);                                    // :690
+        w2 = fma(c2, dt, w2);                                    // :699-700
+        p1 = fma(dx > 0.0 ? 1.0 : (dx < 0.0 ? -1.0 : 0.0), dt, p1);   // :693
+        p2 = fma(2.0 * dx, dt, p2);                              // :703
+        if (k == d0) { first_c1 = c1; first_c2 = c2; }
+        if (DERIV) {
+            if (pj >= 0) {
+                const double E1 = pc1 - c1, E2 = pc2 - c2;
+                if (e1s) e1s[pj] = E1;
+                if (e2s) e2s[pj] = E2;
+                z1 = fma(pcf, E1, z1); z2 = fma(pcf, E2, z2);
+            }
+            pj = src ? ia : -1; pc1 = c1; pc2 = c2; pcf = v;
+        }
+        if (src) {
+            runf_val = v;
+            ++ia; va = va1; va1 = ia + 1 < ia1 ? cf[ia + 1] : CUDART_INF;
+        } else {
+            ++ib; vb = vb1; vb1 = ib + 1 < ib1 ? cg[ib + 1] : CUDART_INF;
+        }
+    }
+    o.w1 = w1; o.w2 = w2; o.p1 = p1; o.p2 = p2; o.z1 = z1; o.z2 = z2;
+    o.first_c1 = first_c1; o.first_c2 = first_c2; o.pc1 = pc1; o.pc2 = pc2; o.pcf = pcf;
+    o.pj = pj; o.common = common;
+}
+
+__global__ void __launch_bounds__(256) k_ot1d_warp(Ot1dArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = a.n, m = a.m, npad = a.npad, mpad = a.mpad;
+    double* const sx = reinterpret_cast<double*>(smem_raw);
+    const size_t xbytes = a.xshared ? (size_t)(npad + mpad) * 8 : 0;
+    double* const cf = reinterpret_cast<double*>(smem_raw + xbytes + (size_t)warp * a.per_warp);
+    double* const cg = cf + npad;
+    double* wp = cg + mpad;
+    double* const e2buf = a.need_e2 ? wp : nullptr;  if (a.need_e2) wp += npad;
+    double* const xf = a.xshared ? sx : wp;
+    double* const xg = a.xshared ? sx + npad : xf + npad;
+    if (a.xshared) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) xf[i] = a.xf[i];
+        for (int i = threadIdx.x; i < m; i += blockDim.x) xg[i] = a.xg[i];
+        __syncthreads();
+    }
+    const int K = n - 1 + m;
+    const int per = (K + 31) >> 5;
+    const bool want1 = a.deriv && a.dW1 && (a.pmask & 1), want2 = a.deriv && a.dW2 && (a.pmask & 2);
+    const bool deriv = want1 || want2;
+    // E^{(1)} (or the only requested order) overwrites cf in place; a second order goes to e2buf
+    double* const e1s = want1 ? cf : nullptr;
+    double* const e2s = want2 ? (want1 ? e2buf : cf) : nullptr;
+    int st_neg = 0, st_common = 0;
+
+    for (long long b = (long long)blockIdx.x * a.wpc + warp; b < a.B; b += (long long)gridDim.x * a.wpc) {
+        if (!a.xshared) {
+            const double* gxf = a.xf + b * a.xf_stride;
+            const double* gxg = a.xg + b * a.xg_stride;
+            for (int i = lane; i < n; i += 32) xf[i] = gxf[i];
+            for (int i = lane; i < m; i += 32) xg[i] = gxg[i];
+        }
+        const int esz = a.dtype == WFOT_F32 ? 4 : 8;
+        const void* frow = reinterpret_cast<const unsigned char*>(a.f) + b * a.f_stride * esz;
+        const void* grow = reinterpret_cast<const unsigned char*>(a.g) + b * a.g_stride * esz;
+        int negf = 0, negg = 0;
+        bool strictf = false, strictg = false;
+        const double amp = warp_cdf(frow, a.dtype, n, npad, cf, a.cdf_f ? a.cdf_f + b * n : nullptr, lane, negf, strictf);
+        warp_cdf(grow, a.dtype, m, mpad, cg, a.cdf_g ? a.cdf_g + b * m : nullptr, lane, negg, strictg);
+        st_neg += (__any_sync(kFull, negf) ? 1 : 0) + (__any_sync(kFull, negg) ? 1 : 0);
+        __syncwarp();
+
+        // ---- merge-path partition: the first d0 merged knots hold `lo` source knots (source first on ties)
+        const int d0 = min(lane * per, K), d1 = min(d0 + per, K);
+        int lo = max(0, d0 - m), hi = min(d0, n - 1);
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cf[mid] <= cg[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
+        }
+        const int ia = lo, ib = d0 - lo;
+        int ia1 = __shfl_down_sync(kFull, ia, 1);
+        if (lane == 31) ia1 = n - 1;
+        const int ib1 = d1 - ia1;
+
+        // ---- sequential merge of the lane's knots
+        MergeOut mo_;
+        int32_t* const mo = a.merge_order ? a.merge_order + b * K : nullptr;
+        if (strictf && strictg) {
+            if (deriv) lane_merge<true, true>(cf, cg, xf, xg, n, m, d0, d1, ia, ia1, ib, ib1, e1s, e2s, mo, mo_);
+            else lane_merge<true, false>(cf, cg, xf, xg, n, m, d0, d1, ia, ia1, ib, ib1, nullptr, nullptr, mo, mo_);
+        } else {
+            if (deriv) lane_merge<false, true>(cf, cg, xf, xg, n, m, d0, d1, ia, ia1, ib, ib1, e1s, e2s, mo, mo_);
+            else lane_merge<false, false>(cf, cg, xf, xg, n, m, d0, d1, ia, ia1, ib, ib1, nullptr, nullptr, mo, mo_);
+        }
+        st_common += mo_.common;
+        double z1 = mo_.z1, z2 = mo_.z2;
+        if (deriv) {   // the lane's last knot, if a source knot, needs the first |dx|^p of the next lane (0 past the end)
+            double nc1 = __shfl_down_sync(kFull, mo_.first_c1, 1), nc2 = __shfl_down_sync(kFull, mo_.first_c2, 1);
+            if (lane == 31) { nc1 = 0.0; nc2 = 0.0; }
+            if (mo_.pj >= 0) {
+                const double E1 = mo_.pc1 - nc1, E2 = mo_.pc2 - nc2;
+                if (e1s) e1s[mo_.pj] = E1;
+                if (e2s) e2s[mo_.pj] = E2;
+                z1 = fma(mo_.pcf, E1, z1); z2 = fma(mo_.pcf, E2, z2);
+            }
+        }
+        const double w1 = warp_sum(mo_.w1), w2 = warp_sum(mo_.w2), p1 = warp_sum(mo_.p1), p2 = warp_sum(mo_.p2);
+        if (lane == 0) {
+            if (a.W) { if (a.pmask & 1) a.W[2 * b] = w1; if (a.pmask & 2) a.W[2 * b + 1] = w2; }
+            if (a.dpos) { if (a.pmask & 1) a.dpos[2 * b] = p1; if (a.pmask & 2) a.dpos[2 * b + 1] = p2; }
+            if (a.amp_f) a.amp_f[b] = amp;
+        }
+
+        // ---- dW_i = (sum_{j>=i} E_j - sum_j cf_j E_j) / amp   (:682-686,694,704 in O(n) form)
+        if (deriv) {
+            const double Z1 = warp_sum(z1), Z2 = warp_sum(z2);
+            const double ramp = 1.0 / amp;
+            double* const o1 = want1 ? a.dW1 + b * n : nullptr;
+            double* const o2 = want2 ? a.dW2 + b * n : nullptr;
+            __syncwarp();                         // E_j parked by other lanes
+            double carry1 = 0.0, carry2 = 0.0;
+            for (int base = npad - 128; base >= 0; base -= 128) {
+                const int idx = base + 4 * lane;
+                double e1[4] = {0.0, 0.0, 0.0, 0.0}, e2[4] = {0.0, 0.0, 0.0, 0.0};
+                if (e1s) {
+                    const double2 q0 = *reinterpret_cast<const double2*>(e1s + idx);
+                    const double2 q1 = *reinterpret_cast<const double2*>(e1s + idx + 2);
+                    e1[0] = q0.x; e1[1] = q0.y; e1[2] = q1.x; e1[3] = q1.y;
+                }
+                if (e2s) {
+                    const double2 q0 = *reinterpret_cast<const double2*>(e2s + idx);
+                    const double2 q1 = *reinterpret_cast<const double2*>(e2s + idx + 2);
+                    e2[0] = q0.x; e2[1] = q0.y; e2[2] = q1.x; e2[3] = q1.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)       // E_{n-1} = 0 (cf[n-1] is not a knot); slots >= n-1 hold no E
+                    if (idx + i >= n - 1) { e1[i] = 0.0; e2[i] = 0.0; }
+                e1[2] += e1[3]; e1[1] += e1[2]; e1[0] += e1[1];
+                e2[2] += e2[3]; e2[1] += e2[2]; e2[0] += e2[1];
+                double i1 = e1[0], i2 = e2[0];    // warp inclusive SUFFIX scan of the lane totals
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double s1 = __shfl_down_sync(kFull, i1, off), s2 = __shfl_down_sync(kFull, i2, off);
+                    if (lane + off < 32) { i1 += s1; i2 += s2; }
+                }
+                const double add1 = carry1 + (i1 - e1[0]), add2 = carry2 + (i2 - e2[0]);
+                double r1[4], r2[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    r1[i] = div_by((add1 + e1[i]) - Z1, amp, ramp);
+                    r2[i] = div_by((add2 + e2[i]) - Z2, amp, ramp);
+                }
+                const bool full = (idx + 3 < n) && ((n & 1) == 0);      // 16-byte aligned rows of 4
+                if (o1) {
+                    if (full) {
+                        *reinterpret_cast<double2*>(o1 + idx) = make_double2(r1[0], r1[1]);
+                        *reinterpret_cast<double2*>(o1 + idx + 2) = make_double2(r1[2], r1[3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (idx + i < n) o1[idx + i] = r1[i];
+                    }
+                }
+                if (o2) {
+                    if (full) {
+                        *reinterpret_cast<double2*>(o2 + idx) = make_double2(r2[0], r2[1]);
+                        *reinterpret_cast<double2*>(o2 + idx + 2) = make_double2(r2[2], r2[3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (idx + i < n) o2[idx + i] = r2[i];
+                    }
+                }
+                carry1 += __shfl_sync(kFull, i1, 0); carry2 += __shfl_sync(kFull, i2, 0);
+            }
+        }
+        __syncwarp();                             // cf / cg are rewritten by the next pair
+    }
+    if (a.status) {
+        if (lane == 0 && st_neg) atomicAdd(a.status + WFOT_STAT_NEG_PDF, st_neg);
+        const int c = __reduce_add_sync(kFull, st_common);
+        if (lane == 0 && c) atomicAdd(a.status + WFOT_STAT_COMMON_CDF, c);
+    }
+}
+
+}  // namespace wfot
+
+using namespace wfot;
+
+extern "C" int wfot_ot1d_batch(const void* f, const void* g, int in_dtype, const double* xf, const double* xg,
+                               long long f_stride, long long g_stride, long long xf_stride, long long xg_stride,
+                               int n, int m, int B, int pmask, int derivatives, double* W, double* dW1,
+                               double* dW2, double* dpos, double* amp_f, double* cdf_f, double* cdf_g,
+                               int32_t* merge_order, int32_t* status, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!f || !g || !xf || !xg || n < 1 || m < 1 || B <= 0 || pmask < 1 || pmask > 3 ||
+        (in_dtype != WFOT_F32 && in_dtype != WFOT_F64))
+        return WFOT_ERR_INVALID_ARG;
+    Ot1dArgs a;
+    a.f = f; a.g = g; a.dtype = in_dtype; a.xf = xf; a.xg = xg;
+    a.f_stride = f_stride; a.g_stride = g_stride; a.xf_stride = xf_stride; a.xg_stride = xg_stride;
+    a.n = n; a.m = m; a.pmask = pmask; a.deriv = derivatives; a.B = B;
+    a.W = W; a.dW1 = dW1; a.dW2 = dW2; a.dpos = dpos; a.amp_f = amp_f; a.cdf_f = cdf_f; a.cdf_g = cdf_g;
+    a.merge_order = merge_order; a.status = status;
+    a.npad = ((n + 127) / 128) * 128;
+    a.mpad = ((m + 127) / 128) * 128;
+    a.xshared = (xf_stride == 0 && xg_stride == 0) ? 1 : 0;
+    a.need_e2 = (derivatives && dW1 && dW2 && pmask == 3) ? 1 : 0;
+    const size_t xbytes = a.xshared ? (size_t)(a.npad + a.mpad) * 8 : 0;
+    const size_t per_warp = (size_t)(a.npad + a.mpad) * 8 * (a.xshared ? 1 : 2) + (a.need_e2 ? (size_t)a.npad * 8 : 0);
+    a.per_warp = per_warp;
+    const size_t budget = 224 * 1024;               // per SM
+    if (xbytes + per_warp > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
+    // CTAs of wpc warps: as many warps per SM as shared memory allows (<= 16), in 1 or 2 CTAs
+    int best_wpc = 1, best_total = 0;
+    for (int ctas = 1; ctas <= 2; ++ctas) {
+        const size_t per_cta = budget / ctas - 1024;
+        if (per_cta <= xbytes) continue;
+        int wpc = (int)((per_cta - xbytes) / per_warp);
+        if (wpc > 8) wpc = 8;
+        if (wpc < 1) continue;
+        if (wpc * ctas > best_total) { best_total = wpc * ctas; best_wpc = wpc; }
+    }
+    a.wpc = best_wpc;
+    const size_t smem = xbytes + per_warp * (size_t)a.wpc;
+    cudaError_t e = cudaFuncSetAttribute(k_ot1d_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_ot1d_warp)");
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ot1d_warp, 32 * a.wpc, smem);
+    if (e != cudaSuccess || per_sm < 1) return cuda_fail(e, "k_ot1d_warp occupancy");
+    int sms = wfot_device_sm_count();
+    if (sms <= 0) sms = 148;
+    long long grid = (long long)sms * per_sm;
+    const long long need = ((long long)B + a.wpc - 1) / a.wpc;
+    if (grid > need) grid = need;
+    k_ot1d_warp<<<(int)grid, 32 * a.wpc, smem, stream>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_ot1d_batch launch");
+    return WFOT_OK;
+}
