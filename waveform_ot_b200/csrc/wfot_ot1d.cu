@@ -81,15 +81,46 @@ __device__ __forceinline__ double warp_cdf(const void* row, int dtype, int n, in
                                            double* cdf_out, int lane, int& neg, bool& strict) {
     const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;     // 16-byte loads need an aligned row
     double s = 0.0;
-    for (int base = 0; base < npad; base += 128) {
-        const int idx = base + 4 * lane;
-        double v[4];
-        load4(row, dtype, vec, idx, n, v);
-        neg |= (v[0] < 0.0) | (v[1] < 0.0) | (v[2] < 0.0) | (v[3] < 0.0);
-        s += (v[0] + v[1]) + (v[2] + v[3]);
-        *reinterpret_cast<double2*>(c + idx) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(c + idx + 2) = make_double2(v[2], v[3]);
+    double vmin = 0.0;
+    if (dtype == WFOT_F32 && vec) {                                   // 8 x 16-byte loads in flight per lane
+        const float* fr = reinterpret_cast<const float*>(row);
+        for (int base0 = 0; base0 < npad; base0 += 8 * 128) {
+            float4 q[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int idx = base0 + r * 128 + 4 * lane;
+                q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx + 3 < n) q[r] = __ldg(reinterpret_cast<const float4*>(fr + idx));
+                else if (idx < n) {
+                    q[r].x = fr[idx];
+                    if (idx + 1 < n) q[r].y = fr[idx + 1];
+                    if (idx + 2 < n) q[r].z = fr[idx + 2];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int idx = base0 + r * 128 + 4 * lane;
+                if (idx < npad) {
+                    const double v0 = q[r].x, v1 = q[r].y, v2 = q[r].z, v3 = q[r].w;
+                    vmin = fmin(vmin, (double)fminf(fminf(q[r].x, q[r].y), fminf(q[r].z, q[r].w)));
+                    s += (v0 + v1) + (v2 + v3);
+                    *reinterpret_cast<double2*>(c + idx) = make_double2(v0, v1);
+                    *reinterpret_cast<double2*>(c + idx + 2) = make_double2(v2, v3);
+                }
+            }
+        }
+    } else {
+        for (int base = 0; base < npad; base += 128) {
+            const int idx = base + 4 * lane;
+            double v[4];
+            load4(row, dtype, vec, idx, n, v);
+            vmin = fmin(vmin, fmin(fmin(v[0], v[1]), fmin(v[2], v[3])));
+            s += (v[0] + v[1]) + (v[2] + v[3]);
+            *reinterpret_cast<double2*>(c + idx) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(c + idx + 2) = make_double2(v[2], v[3]);
+        }
     }
+    neg |= (vmin < 0.0);
     const double amp = warp_sum(s);                                   // :92
     const double ramp = 1.0 / amp;
     double carry = 0.0;
@@ -146,94 +177,153 @@ __device__ __forceinline__ double warp_cdf(const void* row, int dtype, int n, in
     return amp;
 }
 
-// One lane's share of the merge: knots d0 .. d1-1, source knots [ia, ia1), target knots [ib, ib1).
-//   STRICT: both CDFs strictly increasing -> bisect_left ranks are the running counters
-//           (minus one for a target knot equal to the last consumed source knot);
-//   otherwise equal-value runs are tracked (repeated CDF values = empty bins).
-// With DERIV the per-source-knot E_j^{(p)} are parked in shared memory: slot j of `eA` (which may be
-// the cf array itself: entry j is dead once consumed, and lanes never read outside their own range
-// after the caller's __syncwarp) and of `eB` when both orders are wanted.
-struct MergeOut {
-    double w1, w2, p1, p2, z1, z2, first_c1, first_c2, pc1, pc2, pcf;
-    int pj, common;
+// ------------------------------------------------------------------ the merge
+// Per-lane accumulators shared by the lane's two chains.
+struct Acc {
+    double w1, w2, p1, p2, z1, z2;
+    int common;
 };
 
-template <bool STRICT, bool DERIV>
-__device__ __forceinline__ void lane_merge(const double* cf, const double* cg, const double* xf, const double* xg,
-                                           int n, int m, int d0, int d1, int ia, int ia1, int ib, int ib1,
-                                           double* e1s, double* e2s, int32_t* mo, MergeOut& o) {
-    double tprev = 0.0;
-    double runf_val = CUDART_NAN, rung_val = CUDART_NAN;
-    int runf_len = 0, rung_len = 0;               // lengths of the equal-value runs ending at ia-1 / ib-1
-    if (ia > 0) {
-        runf_val = cf[ia - 1]; runf_len = 1;
-        if (!STRICT) while (ia - 1 - runf_len >= 0 && cf[ia - 1 - runf_len] == runf_val) ++runf_len;
-        tprev = runf_val;
+// One contiguous share ("chain") of the merged knot sequence: source knots [ia, ia1), target knots
+// [ib, ib1).  A lane runs TWO chains in lock step, which gives the scheduler two independent
+// dependency chains per warp (the loop is latency bound: compare -> select -> rank -> x look-up).
+//   STRICT: both CDFs strictly increasing -> the bisect_left ranks (:671-672) are the running counters
+//           (minus one for a target knot equal to the last consumed source knot);
+//   otherwise equal-value runs are tracked (repeated CDF values = empty bins).
+//   E1 / E2: the per-source-knot E_j^{(p)} of the amplitude derivative are parked in shared memory,
+//           slot j of e1s / e2s.  One of them is the cf array itself: entry j is dead once consumed and
+//           a chain never reads outside its own ranges after the __syncwarp that follows init().
+template <bool STRICT, bool E1, bool E2>
+struct Chain {
+    int ia, ia1, ib, ib1, k, pj;
+    double va, vb, tprev, runf_val, rung_val;
+    int runf_len, rung_len;
+    double first_c1, first_c2, pc1, pc2, pcf;
+    bool first;
+
+    __device__ __forceinline__ void init(const double* cf, const double* cg, int k0, int ia_, int ia1_, int ib_, int ib1_) {
+        ia = ia_; ia1 = ia1_; ib = ib_; ib1 = ib1_; k = k0; pj = -1;
+        tprev = 0.0; runf_val = CUDART_NAN; rung_val = CUDART_NAN; runf_len = 0; rung_len = 0;
+        first_c1 = 0.0; first_c2 = 0.0; pc1 = 0.0; pc2 = 0.0; pcf = 0.0; first = true;
+        if (ia > 0) {
+            runf_val = cf[ia - 1]; runf_len = 1;
+            if (!STRICT) while (ia - 1 - runf_len >= 0 && cf[ia - 1 - runf_len] == runf_val) ++runf_len;
+            tprev = runf_val;
+        }
+        if (ib > 0) {
+            rung_val = cg[ib - 1]; rung_len = 1;
+            if (!STRICT) while (ib - 1 - rung_len >= 0 && cg[ib - 1 - rung_len] == rung_val) ++rung_len;
+            tprev = ia > 0 ? fmax(tprev, rung_val) : rung_val;
+        }
+        va = ia < ia1 ? cf[ia] : CUDART_INF;      // heads, bounded by the chain's own ranges
+        vb = ib < ib1 ? cg[ib] : CUDART_INF;
     }
-    if (ib > 0) {
-        rung_val = cg[ib - 1]; rung_len = 1;
-        if (!STRICT) while (ib - 1 - rung_len >= 0 && cg[ib - 1 - rung_len] == rung_val) ++rung_len;
-        tprev = ia > 0 ? fmax(tprev, rung_val) : rung_val;
-    }
-    // heads and one-ahead prefetch, bounded by the lane's own ranges
-    double va = ia < ia1 ? cf[ia] : CUDART_INF, va1 = ia + 1 < ia1 ? cf[ia + 1] : CUDART_INF;
-    double vb = ib < ib1 ? cg[ib] : CUDART_INF, vb1 = ib + 1 < ib1 ? cg[ib + 1] : CUDART_INF;
-    __syncwarp();                                 // look-back reads done before any lane parks an E_j
-    double w1 = 0.0, w2 = 0.0, p1 = 0.0, p2 = 0.0, z1 = 0.0, z2 = 0.0;
-    double first_c1 = 0.0, first_c2 = 0.0;
-    int pj = -1, common = 0;                      // pending source knot (its E needs the next knot's |dx|^p)
-    double pc1 = 0.0, pc2 = 0.0, pcf = 0.0;
-    for (int k = d0; k < d1; ++k) {
+
+    // One merged knot.  Branch-free: both possible next heads are loaded speculatively (their addresses
+    // do not depend on the comparison); everything else is selects and predicated stores.
+    __device__ __forceinline__ void step(const double* cf, const double* cg, const double* xf, const double* xg,
+                                         double* e1s, double* e2s, int32_t* mo, int n, int m, Acc& acc) {
+        const double na = ia + 1 < ia1 ? cf[ia + 1] : CUDART_INF;
+        const double nb = ib + 1 < ib1 ? cg[ib + 1] : CUDART_INF;
         const bool src = (va <= vb);              // source first on ties (stable argsort of [cf[:-1], cg], :668-669)
         const double v = src ? va : vb;
+        const bool tie = !src && (v == runf_val); // target knot equal to the last consumed source knot
         int indf, indg;
         if (STRICT) {
-            indf = ia - ((!src && v == runf_val) ? 1 : 0);       // bisect_left(cf, v) (:671)
+            indf = ia - (tie ? 1 : 0);                           // bisect_left(cf, v) (:671)
             indg = ib;                                           // bisect_left(cg, v) (:672)
         } else {
             const int eqf = (v == runf_val) ? runf_len : 0;
             const int eqg = (v == rung_val) ? rung_len : 0;
             indf = ia - eqf;
             indg = src ? ib : ib - eqg;
-            if (src) runf_len = eqf + 1; else rung_len = eqg + 1;
-            if (!src) rung_val = v;
+            runf_len = src ? eqf + 1 : runf_len;
+            rung_len = src ? rung_len : eqg + 1;
+            rung_val = src ? rung_val : v;
         }
-        if (src && ib < m - 1) {                                 // np.intersect1d(cg[:-1], cf[:-1]) (:664)
-            const double nb = ib < ib1 ? vb : cg[ib];            // next target knot (maybe the next lane's)
-            common += (nb == v) ? 1 : 0;
-        }
+        acc.common += (tie && ib < m - 1) ? 1 : 0;               // np.intersect1d(cg[:-1], cf[:-1]) (:664)
         if (mo) mo[k] = src ? ia : n - 1 + ib;
+        ++k;
         const double dx = xf[indf] - xg[indg];                   // :676-677
         const double dt = v - tprev;                             // :673
         tprev = v;
         const double c1 = fabs(dx), c2 = dx * dx;
-        w1 = fma(c1, dt, w1);                                    // :690
-        w2 = fma(c2, dt, w2);                                    // :699-700
-        p1 = fma(dx > 0.0 ? 1.0 : (dx < 0.0 ? -1.0 : 0.0), dt, p1);   // :693
-        p2 = fma(2.0 * dx, dt, p2);                              // :703
-        if (k == d0) { first_c1 = c1; first_c2 = c2; }
-        if (DERIV) {
-            if (pj >= 0) {
-                const double E1 = pc1 - c1, E2 = pc2 - c2;
-                if (e1s) e1s[pj] = E1;
-                if (e2s) e2s[pj] = E2;
-                z1 = fma(pcf, E1, z1); z2 = fma(pcf, E2, z2);
-            }
-            pj = src ? ia : -1; pc1 = c1; pc2 = c2; pcf = v;
+        acc.w1 = fma(c1, dt, acc.w1);                            // :690
+        acc.w2 = fma(c2, dt, acc.w2);                            // :699-700
+        {   // sign(dx) dt (:693): copy the sign of dx onto dt (dt >= 0), zero when dx == 0
+            const int hi = __double2hiint(dt) ^ (__double2hiint(dx) & 0x80000000);
+            const double sdt = __hiloint2double(hi, __double2loint(dt));
+            acc.p1 += (dx != 0.0) ? sdt : 0.0;
         }
-        if (src) {
-            runf_val = v;
-            ++ia; va = va1; va1 = ia + 1 < ia1 ? cf[ia + 1] : CUDART_INF;
-        } else {
-            ++ib; vb = vb1; vb1 = ib + 1 < ib1 ? cg[ib + 1] : CUDART_INF;
+        acc.p2 = fma(dx + dx, dt, acc.p2);                       // :703
+        if (first) { first_c1 = c1; first_c2 = c2; first = false; }
+        if (E1 || E2) {
+            const double D1 = pc1 - c1, D2 = pc2 - c2;
+            if (pj >= 0) {
+                if (E1) e1s[pj] = D1;
+                if (E2) e2s[pj] = D2;
+            }
+            if (E1) acc.z1 = fma(pcf, D1, acc.z1);
+            if (E2) acc.z2 = fma(pcf, D2, acc.z2);
+            pj = src ? ia : -1; pc1 = c1; pc2 = c2; pcf = src ? v : 0.0;   // pcf = 0 <=> nothing pending
+        }
+        runf_val = src ? v : runf_val;
+        va = src ? na : va;
+        vb = src ? vb : nb;
+        ia += src ? 1 : 0;
+        ib += src ? 0 : 1;
+    }
+
+    // the chain's last knot, if a source knot, needs the first |dx|^p of the NEXT knot (0 past the end)
+    __device__ __forceinline__ void finish(double* e1s, double* e2s, double nc1, double nc2, Acc& acc) {
+        if ((E1 || E2) && pj >= 0) {
+            const double D1 = pc1 - nc1, D2 = pc2 - nc2;
+            if (E1) { e1s[pj] = D1; acc.z1 = fma(pcf, D1, acc.z1); }
+            if (E2) { e2s[pj] = D2; acc.z2 = fma(pcf, D2, acc.z2); }
         }
     }
-    o.w1 = w1; o.w2 = w2; o.p1 = p1; o.p2 = p2; o.z1 = z1; o.z2 = z2;
-    o.first_c1 = first_c1; o.first_c2 = first_c2; o.pc1 = pc1; o.pc2 = pc2; o.pcf = pcf;
-    o.pj = pj; o.common = common;
+};
+
+// merge-path split: how many source knots are among the first d merged knots (source first on ties)
+__device__ __forceinline__ int merge_split(const double* cf, const double* cg, int n, int m, int d) {
+    int lo = max(0, d - m), hi = min(d, n - 1);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cf[mid] <= cg[d - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    return lo;
 }
 
-__global__ void __launch_bounds__(256) k_ot1d_warp(Ot1dArgs a) {
+template <bool STRICT, bool E1, bool E2>
+__device__ __forceinline__ void warp_merge(const double* cf, const double* cg, const double* xf, const double* xg,
+                                           double* e1s, double* e2s, int32_t* mo, int n, int m, int lane, Acc& acc) {
+    const int K = n - 1 + m;
+    const int per = (K + 63) >> 6;                // knots per chain (64 chains per warp)
+    const int dA = min(2 * lane * per, K), dB = min(dA + per, K), dE = min(dB + per, K);
+    const int iaA = merge_split(cf, cg, n, m, dA);
+    const int iaB = merge_split(cf, cg, n, m, dB);
+    int iaE = __shfl_down_sync(kFull, iaA, 1);    // the next lane's first chain starts where this lane's second ends
+    if (lane == 31) iaE = n - 1;
+    Chain<STRICT, E1, E2> A, B;
+    A.init(cf, cg, dA, iaA, iaB, dA - iaA, dB - iaB);
+    B.init(cf, cg, dB, iaB, iaE, dB - iaB, dE - iaE);
+    __syncwarp();                                 // all look-back / split reads done before any lane parks an E_j
+    const int lenA = dB - dA, lenB = dE - dB;     // lenB <= lenA
+    int i = 0;
+    for (; i < lenB; ++i) {
+        A.step(cf, cg, xf, xg, e1s, e2s, mo, n, m, acc);
+        B.step(cf, cg, xf, xg, e1s, e2s, mo, n, m, acc);
+    }
+    for (; i < lenA; ++i) A.step(cf, cg, xf, xg, e1s, e2s, mo, n, m, acc);
+    if (E1 || E2) {
+        double nc1 = __shfl_down_sync(kFull, A.first_c1, 1), nc2 = __shfl_down_sync(kFull, A.first_c2, 1);
+        if (lane == 31) { nc1 = 0.0; nc2 = 0.0; }
+        A.finish(e1s, e2s, B.first_c1, B.first_c2, acc);      // an empty chain has first_c = 0 = |dx|^p past the end
+        B.finish(e1s, e2s, nc1, nc2, acc);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) k_ot1d_warp(Ot1dArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.n, m = a.m, npad = a.npad, mpad = a.mpad;
@@ -241,30 +331,25 @@ __global__ void __launch_bounds__(256) k_ot1d_warp(Ot1dArgs a) {
     const size_t xbytes = a.xshared ? (size_t)(npad + mpad) * 8 : 0;
     double* const cf = reinterpret_cast<double*>(smem_raw + xbytes + (size_t)warp * a.per_warp);
     double* const cg = cf + npad;
-    double* wp = cg + mpad;
-    double* const e2buf = a.need_e2 ? wp : nullptr;  if (a.need_e2) wp += npad;
-    double* const xf = a.xshared ? sx : wp;
-    double* const xg = a.xshared ? sx + npad : xf + npad;
+    double* const e2buf = cg + mpad;              // present only if a.need_e2
+    double* const xown = e2buf + (a.need_e2 ? npad : 0);
+    const double* const xf = a.xshared ? sx : xown;
+    const double* const xg = a.xshared ? sx + npad : xown + npad;
     if (a.xshared) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) xf[i] = a.xf[i];
-        for (int i = threadIdx.x; i < m; i += blockDim.x) xg[i] = a.xg[i];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sx[i] = a.xf[i];
+        for (int i = threadIdx.x; i < m; i += blockDim.x) sx[npad + i] = a.xg[i];
         __syncthreads();
     }
     const int K = n - 1 + m;
-    const int per = (K + 31) >> 5;
     const bool want1 = a.deriv && a.dW1 && (a.pmask & 1), want2 = a.deriv && a.dW2 && (a.pmask & 2);
-    const bool deriv = want1 || want2;
-    // E^{(1)} (or the only requested order) overwrites cf in place; a second order goes to e2buf
-    double* const e1s = want1 ? cf : nullptr;
-    double* const e2s = want2 ? (want1 ? e2buf : cf) : nullptr;
     int st_neg = 0, st_common = 0;
 
     for (long long b = (long long)blockIdx.x * a.wpc + warp; b < a.B; b += (long long)gridDim.x * a.wpc) {
         if (!a.xshared) {
             const double* gxf = a.xf + b * a.xf_stride;
             const double* gxg = a.xg + b * a.xg_stride;
-            for (int i = lane; i < n; i += 32) xf[i] = gxf[i];
-            for (int i = lane; i < m; i += 32) xg[i] = gxg[i];
+            for (int i = lane; i < n; i += 32) xown[i] = gxf[i];
+            for (int i = lane; i < m; i += 32) xown[npad + i] = gxg[i];
         }
         const int esz = a.dtype == WFOT_F32 ? 4 : 8;
         const void* frow = reinterpret_cast<const unsigned char*>(a.f) + b * a.f_stride * esz;
@@ -276,41 +361,25 @@ __global__ void __launch_bounds__(256) k_ot1d_warp(Ot1dArgs a) {
         st_neg += (__any_sync(kFull, negf) ? 1 : 0) + (__any_sync(kFull, negg) ? 1 : 0);
         __syncwarp();
 
-        // ---- merge-path partition: the first d0 merged knots hold `lo` source knots (source first on ties)
-        const int d0 = min(lane * per, K), d1 = min(d0 + per, K);
-        int lo = max(0, d0 - m), hi = min(d0, n - 1);
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (cf[mid] <= cg[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
-        }
-        const int ia = lo, ib = d0 - lo;
-        int ia1 = __shfl_down_sync(kFull, ia, 1);
-        if (lane == 31) ia1 = n - 1;
-        const int ib1 = d1 - ia1;
-
-        // ---- sequential merge of the lane's knots
-        MergeOut mo_;
+        Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0};
         int32_t* const mo = a.merge_order ? a.merge_order + b * K : nullptr;
-        if (strictf && strictg) {
-            if (deriv) lane_merge<true, true>(cf, cg, xf, xg, n, m, d0, d1, ia, ia1, ib, ib1, e1s, e2s, mo, mo_);
-            else lane_merge<true, false>(cf, cg, xf, xg, n, m, d0, d1, ia, ia1, ib, ib1, nullptr, nullptr, mo, mo_);
+        const bool strict = strictf && strictg;
+        // E^{(1)} (or the only requested order) overwrites cf in place; a second order goes to e2buf
+        if (want1 && want2) {
+            if (strict) warp_merge<true, true, true>(cf, cg, xf, xg, cf, e2buf, mo, n, m, lane, acc);
+            else warp_merge<false, true, true>(cf, cg, xf, xg, cf, e2buf, mo, n, m, lane, acc);
+        } else if (want1) {
+            if (strict) warp_merge<true, true, false>(cf, cg, xf, xg, cf, nullptr, mo, n, m, lane, acc);
+            else warp_merge<false, true, false>(cf, cg, xf, xg, cf, nullptr, mo, n, m, lane, acc);
+        } else if (want2) {
+            if (strict) warp_merge<true, false, true>(cf, cg, xf, xg, nullptr, cf, mo, n, m, lane, acc);
+            else warp_merge<false, false, true>(cf, cg, xf, xg, nullptr, cf, mo, n, m, lane, acc);
         } else {
-            if (deriv) lane_merge<false, true>(cf, cg, xf, xg, n, m, d0, d1, ia, ia1, ib, ib1, e1s, e2s, mo, mo_);
-            else lane_merge<false, false>(cf, cg, xf, xg, n, m, d0, d1, ia, ia1, ib, ib1, nullptr, nullptr, mo, mo_);
+            if (strict) warp_merge<true, false, false>(cf, cg, xf, xg, nullptr, nullptr, mo, n, m, lane, acc);
+            else warp_merge<false, false, false>(cf, cg, xf, xg, nullptr, nullptr, mo, n, m, lane, acc);
         }
-        st_common += mo_.common;
-        double z1 = mo_.z1, z2 = mo_.z2;
-        if (deriv) {   // the lane's last knot, if a source knot, needs the first |dx|^p of the next lane (0 past the end)
-            double nc1 = __shfl_down_sync(kFull, mo_.first_c1, 1), nc2 = __shfl_down_sync(kFull, mo_.first_c2, 1);
-            if (lane == 31) { nc1 = 0.0; nc2 = 0.0; }
-            if (mo_.pj >= 0) {
-                const double E1 = mo_.pc1 - nc1, E2 = mo_.pc2 - nc2;
-                if (e1s) e1s[mo_.pj] = E1;
-                if (e2s) e2s[mo_.pj] = E2;
-                z1 = fma(mo_.pcf, E1, z1); z2 = fma(mo_.pcf, E2, z2);
-            }
-        }
-        const double w1 = warp_sum(mo_.w1), w2 = warp_sum(mo_.w2), p1 = warp_sum(mo_.p1), p2 = warp_sum(mo_.p2);
+        st_common += acc.common;
+        const double w1 = warp_sum(acc.w1), w2 = warp_sum(acc.w2), p1 = warp_sum(acc.p1), p2 = warp_sum(acc.p2);
         if (lane == 0) {
             if (a.W) { if (a.pmask & 1) a.W[2 * b] = w1; if (a.pmask & 2) a.W[2 * b + 1] = w2; }
             if (a.dpos) { if (a.pmask & 1) a.dpos[2 * b] = p1; if (a.pmask & 2) a.dpos[2 * b + 1] = p2; }
@@ -318,22 +387,24 @@ __global__ void __launch_bounds__(256) k_ot1d_warp(Ot1dArgs a) {
         }
 
         // ---- dW_i = (sum_{j>=i} E_j - sum_j cf_j E_j) / amp   (:682-686,694,704 in O(n) form)
-        if (deriv) {
-            const double Z1 = warp_sum(z1), Z2 = warp_sum(z2);
+        if (want1 || want2) {
+            const double Z1 = warp_sum(acc.z1), Z2 = warp_sum(acc.z2);
             const double ramp = 1.0 / amp;
             double* const o1 = want1 ? a.dW1 + b * n : nullptr;
             double* const o2 = want2 ? a.dW2 + b * n : nullptr;
+            const double* const e1s = cf;                              // order 1 (or the only order) lives in cf
+            const double* const e2s = (want1 && want2) ? e2buf : cf;
             __syncwarp();                         // E_j parked by other lanes
             double carry1 = 0.0, carry2 = 0.0;
             for (int base = npad - 128; base >= 0; base -= 128) {
                 const int idx = base + 4 * lane;
                 double e1[4] = {0.0, 0.0, 0.0, 0.0}, e2[4] = {0.0, 0.0, 0.0, 0.0};
-                if (e1s) {
+                if (want1) {
                     const double2 q0 = *reinterpret_cast<const double2*>(e1s + idx);
                     const double2 q1 = *reinterpret_cast<const double2*>(e1s + idx + 2);
                     e1[0] = q0.x; e1[1] = q0.y; e1[2] = q1.x; e1[3] = q1.y;
                 }
-                if (e2s) {
+                if (want2) {
                     const double2 q0 = *reinterpret_cast<const double2*>(e2s + idx);
                     const double2 q1 = *reinterpret_cast<const double2*>(e2s + idx + 2);
                     e2[0] = q0.x; e2[1] = q0.y; e2[2] = q1.x; e2[3] = q1.y;
@@ -350,29 +421,29 @@ __global__ void __launch_bounds__(256) k_ot1d_warp(Ot1dArgs a) {
                     if (lane + off < 32) { i1 += s1; i2 += s2; }
                 }
                 const double add1 = carry1 + (i1 - e1[0]), add2 = carry2 + (i2 - e2[0]);
-                double r1[4], r2[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    r1[i] = div_by((add1 + e1[i]) - Z1, amp, ramp);
-                    r2[i] = div_by((add2 + e2[i]) - Z2, amp, ramp);
-                }
-                const bool full = (idx + 3 < n) && ((n & 1) == 0);      // 16-byte aligned rows of 4
+                const bool full = (idx + 3 < n) && ((n & 1) == 0);      // 16-byte aligned groups of 4
                 if (o1) {
+                    double r[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r[i] = div_by((add1 + e1[i]) - Z1, amp, ramp);
                     if (full) {
-                        *reinterpret_cast<double2*>(o1 + idx) = make_double2(r1[0], r1[1]);
-                        *reinterpret_cast<double2*>(o1 + idx + 2) = make_double2(r1[2], r1[3]);
+                        *reinterpret_cast<double2*>(o1 + idx) = make_double2(r[0], r[1]);
+                        *reinterpret_cast<double2*>(o1 + idx + 2) = make_double2(r[2], r[3]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) if (idx + i < n) o1[idx + i] = r1[i];
+                        for (int i = 0; i < 4; ++i) if (idx + i < n) o1[idx + i] = r[i];
                     }
                 }
                 if (o2) {
+                    double r[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r[i] = div_by((add2 + e2[i]) - Z2, amp, ramp);
                     if (full) {
-                        *reinterpret_cast<double2*>(o2 + idx) = make_double2(r2[0], r2[1]);
-                        *reinterpret_cast<double2*>(o2 + idx + 2) = make_double2(r2[2], r2[3]);
+                        *reinterpret_cast<double2*>(o2 + idx) = make_double2(r[0], r[1]);
+                        *reinterpret_cast<double2*>(o2 + idx + 2) = make_double2(r[2], r[3]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) if (idx + i < n) o2[idx + i] = r2[i];
+                        for (int i = 0; i < 4; ++i) if (idx + i < n) o2[idx + i] = r[i];
                     }
                 }
                 carry1 += __shfl_sync(kFull, i1, 0); carry2 += __shfl_sync(kFull, i2, 0);
@@ -415,16 +486,10 @@ extern "C" int wfot_ot1d_batch(const void* f, const void* g, int in_dtype, const
     a.per_warp = per_warp;
     const size_t budget = 224 * 1024;               // per SM
     if (xbytes + per_warp > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
-    // CTAs of wpc warps: as many warps per SM as shared memory allows (<= 16), in 1 or 2 CTAs
-    int best_wpc = 1, best_total = 0;
-    for (int ctas = 1; ctas <= 2; ++ctas) {
-        const size_t per_cta = budget / ctas - 1024;
-        if (per_cta <= xbytes) continue;
-        int wpc = (int)((per_cta - xbytes) / per_warp);
-        if (wpc > 8) wpc = 8;
-        if (wpc < 1) continue;
-        if (wpc * ctas > best_total) { best_total = wpc * ctas; best_wpc = wpc; }
-    }
+    // one persistent CTA per SM with as many warps (= pairs in flight) as shared memory allows, <= 16
+    int best_wpc = (int)((budget - 1024 - xbytes) / per_warp);
+    if (best_wpc > 16) best_wpc = 16;
+    if (best_wpc < 1) return WFOT_ERR_UNSUPPORTED;
     a.wpc = best_wpc;
     const size_t smem = xbytes + per_warp * (size_t)a.wpc;
     cudaError_t e = cudaFuncSetAttribute(k_ot1d_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
