@@ -75,11 +75,104 @@ __device__ __forceinline__ void load4(const void* row, int dtype, bool vec, int 
     }
 }
 
+// Register-resident OTpdf.__init__ for FP32 rows of n <= 1024 (16-byte aligned): the samples stay in
+// registers from the global load to the final CDF value, which is written to shared memory once
+// (the generic path below makes three shared-memory round trips).  Same arithmetic, same order.
+__device__ __forceinline__ double warp_cdf_f32_1k(const float* fr, int n, int npad, double* c, double* cdf_out,
+                                                  int lane, int& neg, bool& strict) {
+    float4 q[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int idx = r * 128 + 4 * lane;
+        q[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx + 3 < n) q[r] = __ldg(reinterpret_cast<const float4*>(fr + idx));
+        else if (idx < n) {
+            q[r].x = fr[idx];
+            if (idx + 1 < n) q[r].y = fr[idx + 1];
+            if (idx + 2 < n) q[r].z = fr[idx + 2];
+        }
+    }
+    double s = 0.0;
+    float vmin = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        vmin = fminf(vmin, fminf(fminf(q[r].x, q[r].y), fminf(q[r].z, q[r].w)));
+        s += ((double)q[r].x + (double)q[r].y) + ((double)q[r].z + (double)q[r].w);
+    }
+    neg |= (vmin < 0.f);
+    const double amp = warp_sum(s);                                   // :92
+    const double ramp = 1.0 / amp;
+    double cv[8][4];
+    double carry = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r * 128 < npad) {
+            const double c0 = div_by((double)q[r].x, amp, ramp);      // pdf / amp (:93)
+            const double c1 = c0 + div_by((double)q[r].y, amp, ramp);
+            const double c2 = c1 + div_by((double)q[r].z, amp, ramp);
+            const double c3 = c2 + div_by((double)q[r].w, amp, ramp);
+            double inc = c3;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double o = __shfl_up_sync(kFull, inc, off);
+                if (lane >= off) inc += o;
+            }
+            const double add = carry + (inc - c3);
+            cv[r][0] = add + c0; cv[r][1] = add + c1; cv[r][2] = add + c2; cv[r][3] = add + c3;
+            carry += __shfl_sync(kFull, inc, 31);
+        } else {
+            cv[r][0] = cv[r][1] = cv[r][2] = cv[r][3] = 0.0;
+        }
+    }
+    // cumsum[-1] (:113): the value held for element n-1
+    const int rn = (n - 1) >> 7, ln = ((n - 1) & 127) >> 2, sn = (n - 1) & 3;
+    double mine = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (r == rn && i == sn) mine = cv[r][i];
+    const double last = __shfl_sync(kFull, mine, ln);
+    const double rl = 1.0 / last;
+    const bool resc = (last != 1.0);
+    bool ok = true;
+    double prev_hi = -CUDART_INF;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r * 128 < npad) {
+            const int idx = r * 128 + 4 * lane;
+            double a0 = cv[r][0], a1 = cv[r][1], a2 = cv[r][2], a3 = cv[r][3];
+            if (resc) {                                               // cdf / cdf[-1] (:114)
+                a0 = div_by(a0, last, rl); a1 = div_by(a1, last, rl);
+                a2 = div_by(a2, last, rl); a3 = div_by(a3, last, rl);
+            }
+            *reinterpret_cast<double2*>(c + idx) = make_double2(a0, a1);
+            *reinterpret_cast<double2*>(c + idx + 2) = make_double2(a2, a3);
+            double left = __shfl_up_sync(kFull, a3, 1);
+            if (lane == 0) left = prev_hi;
+            prev_hi = __shfl_sync(kFull, a3, 31);
+            ok = ok && (idx >= n || left < a0) && (idx + 1 >= n || a0 < a1) &&
+                 (idx + 2 >= n || a1 < a2) && (idx + 3 >= n || a2 < a3);
+            if (cdf_out) {
+                if (idx < n) cdf_out[idx] = a0;
+                if (idx + 1 < n) cdf_out[idx + 1] = a1;
+                if (idx + 2 < n) cdf_out[idx + 2] = a2;
+                if (idx + 3 < n) cdf_out[idx + 3] = a3;
+            }
+        }
+    }
+    strict = __all_sync(kFull, ok);
+    __syncwarp();
+    return amp;
+}
+
 // OTpdf.__init__ for one 1-D density (libs/OTlib.py:91-93,112-114): c[0..n) <- cdf, returns amp.
 // c has room for npad = ceil(n/128)*128 doubles.  strict <- the CDF is strictly increasing.
 __device__ __forceinline__ double warp_cdf(const void* row, int dtype, int n, int npad, double* c,
                                            double* cdf_out, int lane, int& neg, bool& strict) {
     const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;     // 16-byte loads need an aligned row
+    if (dtype == WFOT_F32 && vec && npad <= 1024)
+        return warp_cdf_f32_1k(reinterpret_cast<const float*>(row), n, npad, c, cdf_out, lane, neg, strict);
     double s = 0.0;
     double vmin = 0.0;
     if (dtype == WFOT_F32 && vec) {                                   // 8 x 16-byte loads in flight per lane
@@ -201,7 +294,12 @@ struct Chain {
     double first_c1, first_c2, pc1, pc2, pcf;
     bool first;
 
-    __device__ __forceinline__ void init(const double* cf, const double* cg, int k0, int ia_, int ia1_, int ib_, int ib1_) {
+    double xa, xb, xa_prev;                       // STRICT: x_f[ia], x_g[ib], x_f[ia-1]
+
+    // cf and cg (and x_f, x_g) are contiguous: cg = cf + npad, xg = xf + npad.
+    __device__ __forceinline__ void init(const double* cf, const double* xf, int npad, int k0,
+                                         int ia_, int ia1_, int ib_, int ib1_) {
+        const double* cg = cf + npad;
         ia = ia_; ia1 = ia1_; ib = ib_; ib1 = ib1_; k = k0; pj = -1;
         tprev = 0.0; runf_val = CUDART_NAN; rung_val = CUDART_NAN; runf_len = 0; rung_len = 0;
         first_c1 = 0.0; first_c2 = 0.0; pc1 = 0.0; pc2 = 0.0; pcf = 0.0; first = true;
@@ -217,34 +315,44 @@ struct Chain {
         }
         va = ia < ia1 ? cf[ia] : CUDART_INF;      // heads, bounded by the chain's own ranges
         vb = ib < ib1 ? cg[ib] : CUDART_INF;
+        xa = 0.0; xb = 0.0; xa_prev = 0.0;
+        if (STRICT) {                             // ia <= n-1 and ib <= m-1 always hold here
+            xa = xf[ia]; xb = xf[npad + ib];
+            xa_prev = ia > 0 ? xf[ia - 1] : 0.0;
+        }
     }
 
-    // One merged knot.  Branch-free: both possible next heads are loaded speculatively (their addresses
-    // do not depend on the comparison); everything else is selects and predicated stores.
-    __device__ __forceinline__ void step(const double* cf, const double* cg, const double* xf, const double* xg,
+    // One merged knot, branch-free (selects and predicated stores only).
+    // STRICT: bisect_left(cf, v) is ia (ia-1 for a target knot equal to the last consumed source knot) and
+    // bisect_left(cg, v) is ib, i.e. x_f[indf], x_g[indg] are the x of the two current heads, which travel
+    // with them in registers; the consumed side's next (cdf, x) pair is fetched with one selected index.
+    __device__ __forceinline__ void step(const double* cf, const double* xf, int npad,
                                          double* e1s, double* e2s, int32_t* mo, int n, int m, Acc& acc) {
-        const double na = ia + 1 < ia1 ? cf[ia + 1] : CUDART_INF;
-        const double nb = ib + 1 < ib1 ? cg[ib + 1] : CUDART_INF;
         const bool src = (va <= vb);              // source first on ties (stable argsort of [cf[:-1], cg], :668-669)
         const double v = src ? va : vb;
         const bool tie = !src && (v == runf_val); // target knot equal to the last consumed source knot
-        int indf, indg;
+        double dx;
         if (STRICT) {
-            indf = ia - (tie ? 1 : 0);                           // bisect_left(cf, v) (:671)
-            indg = ib;                                           // bisect_left(cg, v) (:672)
+            dx = (tie ? xa_prev : xa) - xb;                      // :671-672,676-677
         } else {
             const int eqf = (v == runf_val) ? runf_len : 0;
             const int eqg = (v == rung_val) ? rung_len : 0;
-            indf = ia - eqf;
-            indg = src ? ib : ib - eqg;
+            const int indf = ia - eqf;                           // bisect_left(cf, v) (:671)
+            const int indg = src ? ib : ib - eqg;                // bisect_left(cg, v) (:672)
             runf_len = src ? eqf + 1 : runf_len;
             rung_len = src ? rung_len : eqg + 1;
             rung_val = src ? rung_val : v;
+            dx = xf[indf] - xf[npad + indg];                     // :676-677
         }
+        // next head of the consumed side (index into the contiguous [cf | cg] / [x_f | x_g] arrays)
+        const int nxt = src ? ia + 1 : npad + ib + 1;
+        const bool inr = src ? (ia + 1 < ia1) : (ib + 1 < ib1);
+        const double nv = inr ? cf[nxt] : CUDART_INF;
+        double nx = 0.0;
+        if (STRICT) nx = xf[src ? min(ia + 1, n - 1) : npad + min(ib + 1, m - 1)];
         acc.common += (tie && ib < m - 1) ? 1 : 0;               // np.intersect1d(cg[:-1], cf[:-1]) (:664)
         if (mo) mo[k] = src ? ia : n - 1 + ib;
         ++k;
-        const double dx = xf[indf] - xg[indg];                   // :676-677
         const double dt = v - tprev;                             // :673
         tprev = v;
         const double c1 = fabs(dx), c2 = dx * dx;
@@ -268,8 +376,13 @@ struct Chain {
             pj = src ? ia : -1; pc1 = c1; pc2 = c2; pcf = src ? v : 0.0;   // pcf = 0 <=> nothing pending
         }
         runf_val = src ? v : runf_val;
-        va = src ? na : va;
-        vb = src ? vb : nb;
+        if (STRICT) {
+            xa_prev = src ? xa : xa_prev;
+            xa = src ? nx : xa;
+            xb = src ? xb : nx;
+        }
+        va = src ? nv : va;
+        vb = src ? vb : nv;
         ia += src ? 1 : 0;
         ib += src ? 0 : 1;
     }
@@ -295,8 +408,9 @@ __device__ __forceinline__ int merge_split(const double* cf, const double* cg, i
 }
 
 template <bool STRICT, bool E1, bool E2>
-__device__ __forceinline__ void warp_merge(const double* cf, const double* cg, const double* xf, const double* xg,
+__device__ __forceinline__ void warp_merge(const double* cf, const double* xf, int npad,
                                            double* e1s, double* e2s, int32_t* mo, int n, int m, int lane, Acc& acc) {
+    const double* cg = cf + npad;
     const int K = n - 1 + m;
     const int per = (K + 63) >> 6;                // knots per chain (64 chains per warp)
     const int dA = min(2 * lane * per, K), dB = min(dA + per, K), dE = min(dB + per, K);
@@ -305,16 +419,16 @@ __device__ __forceinline__ void warp_merge(const double* cf, const double* cg, c
     int iaE = __shfl_down_sync(kFull, iaA, 1);    // the next lane's first chain starts where this lane's second ends
     if (lane == 31) iaE = n - 1;
     Chain<STRICT, E1, E2> A, B;
-    A.init(cf, cg, dA, iaA, iaB, dA - iaA, dB - iaB);
-    B.init(cf, cg, dB, iaB, iaE, dB - iaB, dE - iaE);
+    A.init(cf, xf, npad, dA, iaA, iaB, dA - iaA, dB - iaB);
+    B.init(cf, xf, npad, dB, iaB, iaE, dB - iaB, dE - iaE);
     __syncwarp();                                 // all look-back / split reads done before any lane parks an E_j
     const int lenA = dB - dA, lenB = dE - dB;     // lenB <= lenA
     int i = 0;
     for (; i < lenB; ++i) {
-        A.step(cf, cg, xf, xg, e1s, e2s, mo, n, m, acc);
-        B.step(cf, cg, xf, xg, e1s, e2s, mo, n, m, acc);
+        A.step(cf, xf, npad, e1s, e2s, mo, n, m, acc);
+        B.step(cf, xf, npad, e1s, e2s, mo, n, m, acc);
     }
-    for (; i < lenA; ++i) A.step(cf, cg, xf, xg, e1s, e2s, mo, n, m, acc);
+    for (; i < lenA; ++i) A.step(cf, xf, npad, e1s, e2s, mo, n, m, acc);
     if (E1 || E2) {
         double nc1 = __shfl_down_sync(kFull, A.first_c1, 1), nc2 = __shfl_down_sync(kFull, A.first_c2, 1);
         if (lane == 31) { nc1 = 0.0; nc2 = 0.0; }
@@ -334,7 +448,6 @@ __global__ void __launch_bounds__(512, 1) k_ot1d_warp(Ot1dArgs a) {
     double* const e2buf = cg + mpad;              // present only if a.need_e2
     double* const xown = e2buf + (a.need_e2 ? npad : 0);
     const double* const xf = a.xshared ? sx : xown;
-    const double* const xg = a.xshared ? sx + npad : xown + npad;
     if (a.xshared) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) sx[i] = a.xf[i];
         for (int i = threadIdx.x; i < m; i += blockDim.x) sx[npad + i] = a.xg[i];
@@ -366,17 +479,17 @@ __global__ void __launch_bounds__(512, 1) k_ot1d_warp(Ot1dArgs a) {
         const bool strict = strictf && strictg;
         // E^{(1)} (or the only requested order) overwrites cf in place; a second order goes to e2buf
         if (want1 && want2) {
-            if (strict) warp_merge<true, true, true>(cf, cg, xf, xg, cf, e2buf, mo, n, m, lane, acc);
-            else warp_merge<false, true, true>(cf, cg, xf, xg, cf, e2buf, mo, n, m, lane, acc);
+            if (strict) warp_merge<true, true, true>(cf, xf, npad, cf, e2buf, mo, n, m, lane, acc);
+            else warp_merge<false, true, true>(cf, xf, npad, cf, e2buf, mo, n, m, lane, acc);
         } else if (want1) {
-            if (strict) warp_merge<true, true, false>(cf, cg, xf, xg, cf, nullptr, mo, n, m, lane, acc);
-            else warp_merge<false, true, false>(cf, cg, xf, xg, cf, nullptr, mo, n, m, lane, acc);
+            if (strict) warp_merge<true, true, false>(cf, xf, npad, cf, nullptr, mo, n, m, lane, acc);
+            else warp_merge<false, true, false>(cf, xf, npad, cf, nullptr, mo, n, m, lane, acc);
         } else if (want2) {
-            if (strict) warp_merge<true, false, true>(cf, cg, xf, xg, nullptr, cf, mo, n, m, lane, acc);
-            else warp_merge<false, false, true>(cf, cg, xf, xg, nullptr, cf, mo, n, m, lane, acc);
+            if (strict) warp_merge<true, false, true>(cf, xf, npad, nullptr, cf, mo, n, m, lane, acc);
+            else warp_merge<false, false, true>(cf, xf, npad, nullptr, cf, mo, n, m, lane, acc);
         } else {
-            if (strict) warp_merge<true, false, false>(cf, cg, xf, xg, nullptr, nullptr, mo, n, m, lane, acc);
-            else warp_merge<false, false, false>(cf, cg, xf, xg, nullptr, nullptr, mo, n, m, lane, acc);
+            if (strict) warp_merge<true, false, false>(cf, xf, npad, nullptr, nullptr, mo, n, m, lane, acc);
+            else warp_merge<false, false, false>(cf, xf, npad, nullptr, nullptr, mo, n, m, lane, acc);
         }
         st_common += acc.common;
         const double w1 = warp_sum(acc.w1), w2 = warp_sum(acc.w2), p1 = warp_sum(acc.p1), p2 = warp_sum(acc.p2);
