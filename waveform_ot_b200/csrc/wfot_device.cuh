@@ -328,7 +328,7 @@ __device__ __forceinline__ LaneBlock lane_block(const FootMap& m, int f, int lan
 // Exact pruning (must be called by all 32 lanes of a converged warp; `fp` is the bounding box of
 // the warp's pixels).  Tiles are visited outwards from the one nearest in time to the footprint
 // centre.  A tile is skipped when the distance `lb` between its bounding box and the footprint
-// satisfies (lb - 4e-6)^2 (1 - 4e-6) > max over the warp's pixels of the running minimum b1:
+// satisfies lb (1 - 2e-6) - 4e-6 > sqrt(max over the warp's pixels of the running minimum b1):
 // every FP32 distance of such a tile exceeds b1 + tau32(b1) of every pixel of the warp (the FP32
 // rounding tolerance is 1.25e-6 absolute + 1.5e-7 relative in distance units, see tau32), so the
 // tile can neither hold the FP64 nearest segment nor a near-tie the resolve step has to look at.
@@ -356,7 +356,8 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
         for (int i = 0; i < ntiles && ct < ntiles - 1 && tb.bbox[ct].y < xc; ++i) ++ct;
         for (int i = 0; i < ntiles && ct > 0 && tb.bbox[ct].x > xc; ++i) --ct;
     }
-    float wmax = kBig;   // max over the warp's pixels of b1 (warp-uniform)
+    // thr2 = ((sqrt(wmax) + 4e-6) / (1 - 2e-6))^2: a tile whose squared box distance exceeds it cannot matter
+    float thr2 = kBig;   // from wmax = max over the warp's pixels of b1 (warp-uniform), updated per evaluated tile
     const int nsteps = 2 * max(ct, ntiles - 1 - ct) + 1;
     bool ldone = false, rdone = false;   // time-ordered tables: nothing farther out on that side can matter
     for (int step = 0; step < nsteps; ++step) {
@@ -370,10 +371,9 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
             const float4 bb = tb.bbox[tile];
             const float dx = fmaxf(0.f, fmaxf(bb.x - fp.x1, fp.x0 - bb.y));
             const float dy = fmaxf(0.f, fmaxf(bb.z - fp.y1, fp.y0 - bb.w));
-            const float lb = fmaxf(sqrtf(__fmaf_rn(dx, dx, dy * dy)) - 4.0e-6f, 0.f);
-            if (lb * lb * 0.999996f > wmax) {
-                const float lx = fmaxf(dx - 4.0e-6f, 0.f);
-                if (tb.mono && step > 0 && lx * lx * 0.999996f > wmax) { if (right) rdone = true; else ldone = true; }
+            const float dx2 = dx * dx;
+            if (__fmaf_rn(dy, dy, dx2) > thr2) {
+                if (tb.mono && dx2 > thr2) { if (right) rdone = true; else ldone = true; }
                 continue;
             }
         }
@@ -431,7 +431,9 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
             mx = fmaxf(mx, b1[k]);
         }
         // non-negative floats order like their bit patterns: one REDUX gives the warp maximum
-        wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
+        const float wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
+        const float tq = (sqrtf(wmax) + 4.0e-6f) * 1.000002f;
+        thr2 = tq * tq;
     }
 }
 

@@ -127,8 +127,10 @@ __device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* p
     a.s_idx[k] = hit.s;
 }
 
-template <int R>
-__global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
+// NT threads per CTA: 256 for large grids; 128 (4 CTAs per SM) for small windows, where the per-window
+// phases are short and more co-resident windows hide the block barriers between them.
+template <int R, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) k_misfit_grad(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         if (tid == 0) { s_hdr->degenerate = 0; s_hdr->nonmono = 0; s_qcount[0] = 0; s_qcount[1] = 0; }
         if (a.grad) {      // P4 accumulates into these rows with L2 reductions
             double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
-            for (int j = tid; j < 2 * a.nt; j += 256) g0[j] = 0.0;
+            for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
             __threadfence();
         }
         __syncthreads();
@@ -154,8 +156,8 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         const WinHdr hdr = *s_hdr;
         tb.mono = (hdr.nonmono == 0);
         degen += (tid == 0) ? hdr.degenerate : 0;
-        for (int i = tid; i < a.ntg; i += 256) s_xt[i] = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, i, a.ntg);
-        for (int i = tid; i < a.nug; i += 256) s_xu[i] = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, i, a.nug);
+        for (int i = tid; i < a.ntg; i += NT) s_xt[i] = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, i, a.ntg);
+        for (int i = tid; i < a.nug; i += NT) s_xu[i] = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, i, a.nug);
         __syncthreads();
 
         // ---------------- P1: nearest segment per pixel.  Warps draw footprints from a shared counter
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         __syncthreads();
         {
             const int nq = min(*s_qcount, kFQCap);
-            for (int e = warp; e < nq; e += 8) {
+            for (int e = warp; e < nq; e += NT / 32) {
                 const FQEntry qe = s_queue[e];
                 const int it = qe.pix % a.ntg, iu = qe.pix / a.ntg;
                 PixelHit hit;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         // ---------------- P2: marginals of the normalised density (fixed summation order;
         //                  8 independent loads in flight per thread)
         double part = 0.0;
-        for (int c = tid; c < a.ntg; c += 256) {
+        for (int c = tid; c < a.ntg; c += NT) {
             const double* col = a.s_pdf + slab + c;
             double s0 = 0.0;
             int iu = 0;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
             part += s0;
         }
         const double A = block_sum(part, s_red);                        // OTpdf.amp (OTlib.py:92)
-        for (int iu = warp; iu < a.nug; iu += 8) {
+        for (int iu = warp; iu < a.nug; iu += NT / 32) {
             const double* row = a.s_pdf + slab + (size_t)iu * a.ntg;
             double s0 = 0.0;
             for (int c = lane; c < a.ntg; c += 32) s0 += __ldcg(row + c);
@@ -237,27 +239,27 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
             for (int off = 16; off > 0; off >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, off);
             if (lane == 0) s_margu[iu] = s0 / A;                        // OTlib.py:93,156
         }
-        for (int c = tid; c < a.ntg; c += 256) s_margt[c] = s_margt[c] / A;     // OTlib.py:93,155
+        for (int c = tid; c < a.ntg; c += NT) s_margt[c] = s_margt[c] / A;     // OTlib.py:93,155
         __syncthreads();
 
         // ---------------- P3: 1-D OT per marginal
         const size_t trow = a.tgt_per_window ? (size_t)b : 0;
         OtScratch sc{s_cf, s_tk, s_dx, s_E, s_posf, s_red};
-        for (int c = tid; c < a.ntg; c += 256) s_cf[c] = s_margt[c];
+        for (int c = tid; c < a.ntg; c += NT) s_cf[c] = s_margt[c];
         __syncthreads();
         const OtResult rt = block_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, a.ntg, s_xt,
                                        a.tgt_x_t + trow * a.ntg, a.pmask,
                                        (a.pmask & 1) ? s_Rt : nullptr, (a.pmask & 2) ? s_Rt : nullptr, nullptr);
         double gp = 0.0;
-        for (int c = tid; c < a.ntg; c += 256) gp += s_margt[c] * s_Rt[c];
+        for (int c = tid; c < a.ntg; c += NT) gp += s_margt[c] * s_Rt[c];
         const double Gt = block_sum(gp, s_red);                         // <dwpmargX, pbar> (OTlib.py:1144)
-        for (int c = tid; c < a.nug; c += 256) s_cf[c] = s_margu[c];
+        for (int c = tid; c < a.nug; c += NT) s_cf[c] = s_margu[c];
         __syncthreads();
         const OtResult ru = block_ot1d(sc, a.nug, a.tgt_cdf_u + trow * a.nug, a.nug, s_xu,
                                        a.tgt_x_u + trow * a.nug, a.pmask,
                                        (a.pmask & 1) ? s_Ru : nullptr, (a.pmask & 2) ? s_Ru : nullptr, nullptr);
         gp = 0.0;
-        for (int c = tid; c < a.nug; c += 256) gp += s_margu[c] * s_Ru[c];
+        for (int c = tid; c < a.nug; c += NT) gp += s_margu[c] * s_Ru[c];
         const double Gu = block_sum(gp, s_red);                         // OTlib.py:1145
         common += (tid == 0) ? (rt.common + ru.common) : 0;
         if (tid == 0) {
@@ -273,10 +275,10 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
         //                  zeroed in P0.
         if (a.grad) {
             // chain vectors: (R - <R, pbar>)/A  (OTlib.py:1144-1147)
-            for (int c = tid; c < a.ntg; c += 256) s_Rt[c] = (s_Rt[c] - Gt) / A;
-            for (int c = tid; c < a.nug; c += 256) s_Ru[c] = (s_Ru[c] - Gu) / A;
+            for (int c = tid; c < a.ntg; c += NT) s_Rt[c] = (s_Rt[c] - Gt) / A;
+            for (int c = tid; c < a.nug; c += NT) s_Ru[c] = (s_Ru[c] - Gu) / A;
             const double scale = -1.0 / (a.lambda * hdr.du);             // FingerprintLib.py:228,376-378
-            for (int j = tid; j < a.nt; j += 256) {
+            for (int j = tid; j < a.nt; j += NT) {
                 double chain = scale;
                 if (a.transform) {   // d(un)/du, ricker_util.py:273,393-397
                     const double wj = load_sample(a.w, a.dtype, (long long)b * a.nt + j);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256, 2) k_misfit_grad(FusedArgs a) {
             __syncthreads();
             double* const gt = a.grad + ((size_t)b * 2) * a.nt;
             double* const gu = gt + a.nt;
-            for (int c = tid; c < a.ntg; c += 256) {
+            for (int c = tid; c < a.ntg; c += NT) {
                 const double ct = s_Rt[c];
                 int cur = -1;
                 double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
@@ -392,13 +394,13 @@ static int rows_per_thread() {
 }
 
 template <typename K>
-static int resident_ctas(K kernel, size_t smem, int* per_sm_out) {
+static int resident_ctas(K kernel, size_t smem, int* per_sm_out, int threads = 256) {
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) return -1;
     if (per_sm < 1) return -1;
     if (per_sm_out) *per_sm_out = per_sm;
     return sms * per_sm;
@@ -446,7 +448,10 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     if (smem > 227 * 1024) return WFOT_ERR_UNSUPPORTED;
     int per_sm = 0;
     const int R = rows_per_thread();
-    int ctas = (R == 4) ? resident_ctas(k_misfit_grad<4>, smem, &per_sm) : resident_ctas(k_misfit_grad<8>, smem, &per_sm);
+    const bool small = (R == 4) && ((long long)nug * ntg <= 16384);      // small windows: 128-thread CTAs, 4 per SM
+    int ctas = small ? resident_ctas(k_misfit_grad<4, 128>, smem, &per_sm, 128)
+                     : (R == 4) ? resident_ctas(k_misfit_grad<4, 256>, smem, &per_sm)
+                                : resident_ctas(k_misfit_grad<8, 256>, smem, &per_sm);
     if (ctas < 1) return cuda_fail(cudaGetLastError(), "k_misfit_grad occupancy");
     if (ctas > B) ctas = B;
     const size_t npix = (size_t)nug * ntg;
@@ -460,8 +465,9 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     a.s_wa = (double*)p;    p += (size_t)ctas * npix * 8;
     a.s_wb = (double*)p;    p += (size_t)ctas * npix * 8;
     a.s_idx = (int32_t*)p;
-    if (R == 4) k_misfit_grad<4><<<ctas, 256, smem, stream>>>(a);
-    else k_misfit_grad<8><<<ctas, 256, smem, stream>>>(a);
+    if (small) k_misfit_grad<4, 128><<<ctas, 128, smem, stream>>>(a);
+    else if (R == 4) k_misfit_grad<4, 256><<<ctas, 256, smem, stream>>>(a);
+    else k_misfit_grad<8, 256><<<ctas, 256, smem, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_misfit_grad_batch launch");
     return WFOT_OK;
