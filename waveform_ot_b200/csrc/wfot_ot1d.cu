@@ -286,15 +286,17 @@ struct Acc {
 //   E1 / E2: the per-source-knot E_j^{(p)} of the amplitude derivative are parked in shared memory,
 //           slot j of e1s / e2s.  One of them is the cf array itself: entry j is dead once consumed and
 //           a chain never reads outside its own ranges after the __syncwarp that follows init().
-template <bool STRICT, bool E1, bool E2>
+// Template flags: PM = orders whose W_p^p / translation derivative are accumulated (1, 2 or 3);
+// EM = orders whose amplitude derivative is wanted (subset of PM); MO = write the merge order.
+template <bool STRICT, int PM, int EM, bool MO>
 struct Chain {
+    static constexpr bool E1 = (EM & 1) != 0, E2 = (EM & 2) != 0;
     int ia, ia1, ib, ib1, k, pj;
     double va, vb, tprev, runf_val, rung_val;
     int runf_len, rung_len;
     double first_c1, first_c2, pc1, pc2, pcf;
     bool first;
-
-    double xa, xb, xa_prev;                       // STRICT: x_f[ia], x_g[ib], x_f[ia-1]
+    double xa, xb;                                // STRICT: x_f[ia], x_g[ib] travel with the heads
 
     // cf and cg (and x_f, x_g) are contiguous: cg = cf + npad, xg = xf + npad.
     __device__ __forceinline__ void init(const double* cf, const double* xf, int npad, int k0,
@@ -315,26 +317,36 @@ struct Chain {
         }
         va = ia < ia1 ? cf[ia] : CUDART_INF;      // heads, bounded by the chain's own ranges
         vb = ib < ib1 ? cg[ib] : CUDART_INF;
-        xa = 0.0; xb = 0.0; xa_prev = 0.0;
+        xa = 0.0; xb = 0.0;
         if (STRICT) {                             // ia <= n-1 and ib <= m-1 always hold here
             xa = xf[ia]; xb = xf[npad + ib];
-            xa_prev = ia > 0 ? xf[ia - 1] : 0.0;
+            if ((E1 || E2) && (ia < ia1 || ib < ib1)) {      // |dx|^p of the chain's first knot (for the previous chain)
+                const bool src = (va <= vb);
+                const bool tie = !src && ia > 0 && (vb == tprev);
+                const double dx = (tie ? xf[ia - 1] : xa) - xb;
+                first_c1 = fabs(dx); first_c2 = dx * dx;
+            }
         }
     }
 
-    // One merged knot, branch-free (selects and predicated stores only).
-    // STRICT: bisect_left(cf, v) is ia (ia-1 for a target knot equal to the last consumed source knot) and
-    // bisect_left(cg, v) is ib, i.e. x_f[indf], x_g[indg] are the x of the two current heads, which travel
-    // with them in registers; the consumed side's next (cdf, x) pair is fetched with one selected index.
+    // One merged knot, branch-free (selects and predicated loads / stores only).
+    // STRICT: bisect_left(cf, v) is ia (ia-1 for a target knot equal to the last consumed source knot,
+    // which is then the previous knot: v == tprev) and bisect_left(cg, v) is ib, i.e. x_f[indf], x_g[indg]
+    // are the x of the two current heads, which travel with them in registers; the consumed side's next
+    // (cdf, x) pair is fetched with one selected index.
     __device__ __forceinline__ void step(const double* cf, const double* xf, int npad,
                                          double* e1s, double* e2s, int32_t* mo, int n, int m, Acc& acc) {
         const bool src = (va <= vb);              // source first on ties (stable argsort of [cf[:-1], cg], :668-669)
         const double v = src ? va : vb;
-        const bool tie = !src && (v == runf_val); // target knot equal to the last consumed source knot
+        bool tie;
         double dx;
         if (STRICT) {
-            dx = (tie ? xa_prev : xa) - xb;                      // :671-672,676-677
+            tie = !src && ia > 0 && (v == tprev);
+            double xs = xa;
+            if (tie) xs = xf[ia - 1];                            // rare: predicated load
+            dx = xs - xb;                                        // :671-672,676-677
         } else {
+            tie = !src && (v == runf_val);        // target knot equal to the last consumed source knot
             const int eqf = (v == runf_val) ? runf_len : 0;
             const int eqg = (v == rung_val) ? rung_len : 0;
             const int indf = ia - eqf;                           // bisect_left(cf, v) (:671)
@@ -342,6 +354,7 @@ struct Chain {
             runf_len = src ? eqf + 1 : runf_len;
             rung_len = src ? rung_len : eqg + 1;
             rung_val = src ? rung_val : v;
+            runf_val = src ? v : runf_val;
             dx = xf[indf] - xf[npad + indg];                     // :676-677
         }
         // next head of the consumed side (index into the contiguous [cf | cg] / [x_f | x_g] arrays)
@@ -351,20 +364,22 @@ struct Chain {
         double nx = 0.0;
         if (STRICT) nx = xf[src ? min(ia + 1, n - 1) : npad + min(ib + 1, m - 1)];
         acc.common += (tie && ib < m - 1) ? 1 : 0;               // np.intersect1d(cg[:-1], cf[:-1]) (:664)
-        if (mo) mo[k] = src ? ia : n - 1 + ib;
-        ++k;
+        if (MO) { mo[k] = src ? ia : n - 1 + ib; ++k; }
         const double dt = v - tprev;                             // :673
         tprev = v;
         const double c1 = fabs(dx), c2 = dx * dx;
-        acc.w1 = fma(c1, dt, acc.w1);                            // :690
-        acc.w2 = fma(c2, dt, acc.w2);                            // :699-700
-        {   // sign(dx) dt (:693): copy the sign of dx onto dt (dt >= 0), zero when dx == 0
+        if (PM & 1) {
+            acc.w1 = fma(c1, dt, acc.w1);                        // :690
+            // sign(dx) dt (:693): copy the sign of dx onto dt (dt >= 0), zero when dx == 0
             const int hi = __double2hiint(dt) ^ (__double2hiint(dx) & 0x80000000);
             const double sdt = __hiloint2double(hi, __double2loint(dt));
             acc.p1 += (dx != 0.0) ? sdt : 0.0;
         }
-        acc.p2 = fma(dx + dx, dt, acc.p2);                       // :703
-        if (first) { first_c1 = c1; first_c2 = c2; first = false; }
+        if (PM & 2) {
+            acc.w2 = fma(c2, dt, acc.w2);                        // :699-700
+            acc.p2 = fma(dx, dt, acc.p2);                        // :703 (doubled once at the end: exact)
+        }
+        if (!STRICT && first) { first_c1 = c1; first_c2 = c2; first = false; }
         if (E1 || E2) {
             const double D1 = pc1 - c1, D2 = pc2 - c2;
             if (pj >= 0) {
@@ -373,11 +388,11 @@ struct Chain {
             }
             if (E1) acc.z1 = fma(pcf, D1, acc.z1);
             if (E2) acc.z2 = fma(pcf, D2, acc.z2);
-            pj = src ? ia : -1; pc1 = c1; pc2 = c2; pcf = src ? v : 0.0;   // pcf = 0 <=> nothing pending
+            pj = src ? ia : -1; pcf = src ? v : 0.0;             // pcf = 0 <=> nothing pending
+            if (E1) pc1 = c1;
+            if (E2) pc2 = c2;
         }
-        runf_val = src ? v : runf_val;
         if (STRICT) {
-            xa_prev = src ? xa : xa_prev;
             xa = src ? nx : xa;
             xb = src ? xb : nx;
         }
@@ -407,7 +422,7 @@ __device__ __forceinline__ int merge_split(const double* cf, const double* cg, i
     return lo;
 }
 
-template <bool STRICT, bool E1, bool E2>
+template <bool STRICT, int PM, int EM, bool MO>
 __device__ __forceinline__ void warp_merge(const double* cf, const double* xf, int npad,
                                            double* e1s, double* e2s, int32_t* mo, int n, int m, int lane, Acc& acc) {
     const double* cg = cf + npad;
@@ -418,7 +433,8 @@ __device__ __forceinline__ void warp_merge(const double* cf, const double* xf, i
     const int iaB = merge_split(cf, cg, n, m, dB);
     int iaE = __shfl_down_sync(kFull, iaA, 1);    // the next lane's first chain starts where this lane's second ends
     if (lane == 31) iaE = n - 1;
-    Chain<STRICT, E1, E2> A, B;
+    constexpr bool E1 = (EM & 1) != 0, E2 = (EM & 2) != 0;
+    Chain<STRICT, PM, EM, MO> A, B;
     A.init(cf, xf, npad, dA, iaA, iaB, dA - iaA, dB - iaB);
     B.init(cf, xf, npad, dB, iaB, iaE, dB - iaB, dE - iaE);
     __syncwarp();                                 // all look-back / split reads done before any lane parks an E_j
@@ -434,6 +450,43 @@ __device__ __forceinline__ void warp_merge(const double* cf, const double* xf, i
         if (lane == 31) { nc1 = 0.0; nc2 = 0.0; }
         A.finish(e1s, e2s, B.first_c1, B.first_c2, acc);      // an empty chain has first_c = 0 = |dx|^p past the end
         B.finish(e1s, e2s, nc1, nc2, acc);
+    }
+}
+
+// dW_i = (sum_{j>=i} E_j - Z) / amp for one order: warp suffix scan over the parked E_j (slots >= n-1
+// hold no E: cf[n-1] is not a knot), 16-byte coalesced stores.
+__device__ __forceinline__ void suffix_phase(const double* es, double* out, double Z, double amp, int n, int npad,
+                                             int lane) {
+    const double ramp = 1.0 / amp;
+    double carry = 0.0;
+    for (int base = npad - 128; base >= 0; base -= 128) {
+        const int idx = base + 4 * lane;
+        const double2 q0 = *reinterpret_cast<const double2*>(es + idx);
+        const double2 q1 = *reinterpret_cast<const double2*>(es + idx + 2);
+        double e[4] = {q0.x, q0.y, q1.x, q1.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (idx + i >= n - 1) e[i] = 0.0;
+        e[2] += e[3]; e[1] += e[2]; e[0] += e[1];
+        double inc = e[0];                        // warp inclusive SUFFIX scan of the lane totals
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_down_sync(kFull, inc, off);
+            if (lane + off < 32) inc += o;
+        }
+        const double add = carry + (inc - e[0]);
+        double r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = div_by((add + e[i]) - Z, amp, ramp);
+        if ((idx + 3 < n) && ((n & 1) == 0)) {    // 16-byte aligned groups of 4
+            *reinterpret_cast<double2*>(out + idx) = make_double2(r[0], r[1]);
+            *reinterpret_cast<double2*>(out + idx + 2) = make_double2(r[2], r[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (idx + i < n) out[idx + i] = r[i];
+        }
+        carry += __shfl_sync(kFull, inc, 0);
     }
 }
 
@@ -477,22 +530,26 @@ __global__ void __launch_bounds__(512, 1) k_ot1d_warp(Ot1dArgs a) {
         Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0};
         int32_t* const mo = a.merge_order ? a.merge_order + b * K : nullptr;
         const bool strict = strictf && strictg;
-        // E^{(1)} (or the only requested order) overwrites cf in place; a second order goes to e2buf
-        if (want1 && want2) {
-            if (strict) warp_merge<true, true, true>(cf, xf, npad, cf, e2buf, mo, n, m, lane, acc);
-            else warp_merge<false, true, true>(cf, xf, npad, cf, e2buf, mo, n, m, lane, acc);
-        } else if (want1) {
-            if (strict) warp_merge<true, true, false>(cf, xf, npad, cf, nullptr, mo, n, m, lane, acc);
-            else warp_merge<false, true, false>(cf, xf, npad, cf, nullptr, mo, n, m, lane, acc);
-        } else if (want2) {
-            if (strict) warp_merge<true, false, true>(cf, xf, npad, nullptr, cf, mo, n, m, lane, acc);
-            else warp_merge<false, false, true>(cf, xf, npad, nullptr, cf, mo, n, m, lane, acc);
-        } else {
-            if (strict) warp_merge<true, false, false>(cf, xf, npad, nullptr, nullptr, mo, n, m, lane, acc);
-            else warp_merge<false, false, false>(cf, xf, npad, nullptr, nullptr, mo, n, m, lane, acc);
-        }
+        // Specialisations: accumulated orders PM, derivative orders EM, merge-order output.  With the
+        // merge order requested (a parity / debugging output) the general PM = 3 variant runs.
+        int pm = a.pmask, em = (want1 ? 1 : 0) | (want2 ? 2 : 0);
+        if (mo) { pm = 3; em = em ? 3 : 0; }
+        // E^{(1)} (or the only order) overwrites cf in place; with both orders E^{(2)} goes to e2buf
+        double* const e1s = cf;
+        double* const e2s = (em == 3) ? e2buf : cf;
+#define WFOT_MERGE(S, P, E, M) warp_merge<S, P, E, M>(cf, xf, npad, e1s, e2s, mo, n, m, lane, acc)
+#define WFOT_MERGE_S(P, E, M) do { if (strict) WFOT_MERGE(true, P, E, M); else WFOT_MERGE(false, P, E, M); } while (0)
+        if (mo) { if (em) WFOT_MERGE_S(3, 3, true); else WFOT_MERGE_S(3, 0, true); }
+        else if (pm == 1) { if (em) WFOT_MERGE_S(1, 1, false); else WFOT_MERGE_S(1, 0, false); }
+        else if (pm == 2) { if (em) WFOT_MERGE_S(2, 2, false); else WFOT_MERGE_S(2, 0, false); }
+        else if (em == 3) WFOT_MERGE_S(3, 3, false);
+        else if (em == 2) WFOT_MERGE_S(3, 2, false);
+        else if (em == 1) WFOT_MERGE_S(3, 1, false);
+        else WFOT_MERGE_S(3, 0, false);
+#undef WFOT_MERGE_S
+#undef WFOT_MERGE
         st_common += acc.common;
-        const double w1 = warp_sum(acc.w1), w2 = warp_sum(acc.w2), p1 = warp_sum(acc.p1), p2 = warp_sum(acc.p2);
+        const double w1 = warp_sum(acc.w1), w2 = warp_sum(acc.w2), p1 = warp_sum(acc.p1), p2 = 2.0 * warp_sum(acc.p2);
         if (lane == 0) {
             if (a.W) { if (a.pmask & 1) a.W[2 * b] = w1; if (a.pmask & 2) a.W[2 * b + 1] = w2; }
             if (a.dpos) { if (a.pmask & 1) a.dpos[2 * b] = p1; if (a.pmask & 2) a.dpos[2 * b + 1] = p2; }
@@ -500,67 +557,10 @@ __global__ void __launch_bounds__(512, 1) k_ot1d_warp(Ot1dArgs a) {
         }
 
         // ---- dW_i = (sum_{j>=i} E_j - sum_j cf_j E_j) / amp   (:682-686,694,704 in O(n) form)
-        if (want1 || want2) {
-            const double Z1 = warp_sum(acc.z1), Z2 = warp_sum(acc.z2);
-            const double ramp = 1.0 / amp;
-            double* const o1 = want1 ? a.dW1 + b * n : nullptr;
-            double* const o2 = want2 ? a.dW2 + b * n : nullptr;
-            const double* const e1s = cf;                              // order 1 (or the only order) lives in cf
-            const double* const e2s = (want1 && want2) ? e2buf : cf;
+        if (em) {
             __syncwarp();                         // E_j parked by other lanes
-            double carry1 = 0.0, carry2 = 0.0;
-            for (int base = npad - 128; base >= 0; base -= 128) {
-                const int idx = base + 4 * lane;
-                double e1[4] = {0.0, 0.0, 0.0, 0.0}, e2[4] = {0.0, 0.0, 0.0, 0.0};
-                if (want1) {
-                    const double2 q0 = *reinterpret_cast<const double2*>(e1s + idx);
-                    const double2 q1 = *reinterpret_cast<const double2*>(e1s + idx + 2);
-                    e1[0] = q0.x; e1[1] = q0.y; e1[2] = q1.x; e1[3] = q1.y;
-                }
-                if (want2) {
-                    const double2 q0 = *reinterpret_cast<const double2*>(e2s + idx);
-                    const double2 q1 = *reinterpret_cast<const double2*>(e2s + idx + 2);
-                    e2[0] = q0.x; e2[1] = q0.y; e2[2] = q1.x; e2[3] = q1.y;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)       // E_{n-1} = 0 (cf[n-1] is not a knot); slots >= n-1 hold no E
-                    if (idx + i >= n - 1) { e1[i] = 0.0; e2[i] = 0.0; }
-                e1[2] += e1[3]; e1[1] += e1[2]; e1[0] += e1[1];
-                e2[2] += e2[3]; e2[1] += e2[2]; e2[0] += e2[1];
-                double i1 = e1[0], i2 = e2[0];    // warp inclusive SUFFIX scan of the lane totals
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const double s1 = __shfl_down_sync(kFull, i1, off), s2 = __shfl_down_sync(kFull, i2, off);
-                    if (lane + off < 32) { i1 += s1; i2 += s2; }
-                }
-                const double add1 = carry1 + (i1 - e1[0]), add2 = carry2 + (i2 - e2[0]);
-                const bool full = (idx + 3 < n) && ((n & 1) == 0);      // 16-byte aligned groups of 4
-                if (o1) {
-                    double r[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) r[i] = div_by((add1 + e1[i]) - Z1, amp, ramp);
-                    if (full) {
-                        *reinterpret_cast<double2*>(o1 + idx) = make_double2(r[0], r[1]);
-                        *reinterpret_cast<double2*>(o1 + idx + 2) = make_double2(r[2], r[3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) if (idx + i < n) o1[idx + i] = r[i];
-                    }
-                }
-                if (o2) {
-                    double r[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) r[i] = div_by((add2 + e2[i]) - Z2, amp, ramp);
-                    if (full) {
-                        *reinterpret_cast<double2*>(o2 + idx) = make_double2(r[0], r[1]);
-                        *reinterpret_cast<double2*>(o2 + idx + 2) = make_double2(r[2], r[3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) if (idx + i < n) o2[idx + i] = r[i];
-                    }
-                }
-                carry1 += __shfl_sync(kFull, i1, 0); carry2 += __shfl_sync(kFull, i2, 0);
-            }
+            if (want1) suffix_phase(e1s, a.dW1 + b * n, warp_sum(acc.z1), amp, n, npad, lane);
+            if (want2) suffix_phase(e2s, a.dW2 + b * n, warp_sum(acc.z2), amp, n, npad, lane);
         }
         __syncwarp();                             // cf / cg are rewritten by the next pair
     }
@@ -593,7 +593,7 @@ extern "C" int wfot_ot1d_batch(const void* f, const void* g, int in_dtype, const
     a.npad = ((n + 127) / 128) * 128;
     a.mpad = ((m + 127) / 128) * 128;
     a.xshared = (xf_stride == 0 && xg_stride == 0) ? 1 : 0;
-    a.need_e2 = (derivatives && dW1 && dW2 && pmask == 3) ? 1 : 0;
+    a.need_e2 = (derivatives && ((dW1 && dW2 && pmask == 3) || (merge_order && (dW1 || dW2)))) ? 1 : 0;
     const size_t xbytes = a.xshared ? (size_t)(a.npad + a.mpad) * 8 : 0;
     const size_t per_warp = (size_t)(a.npad + a.mpad) * 8 * (a.xshared ? 1 : 2) + (a.need_e2 ? (size_t)a.npad * 8 : 0);
     a.per_warp = per_warp;
