@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4736, help="windows per GPU per step (32 per SM)")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="windows timed for cpu_baseline (N=1, rank 0)")
+    ap.add_argument("--cpu-sample", type=int, default=12, help="windows timed for cpu_baseline (N=1, rank 0)")
+    ap.add_argument("--secondary", type=int, default=1,
+                    help="also time the other BASELINE.json configs' kernels (N=1, a few ms each)")
     return ap.parse_args()
 
 
@@ -169,6 +171,75 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- other configs (N=1)
+def secondary_configs(dev):
+    """Device-resident kernel timings of BASELINE.json configs[0..3]'s shapes (not the headline):
+    cfg1/cfg3 shape (256 samples -> 80 x 512), cfg4 shape (61 samples -> 79 x 61, arctan transform),
+    cfg2 (1-D OT, n = m = 1024).  CUDA events, best of 3 after a warm-up call."""
+    import torch
+    from waveform_ot_b200 import _cabi as C
+    from waveform_ot_b200 import batch as B
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def best(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        b = 1e30
+        for _ in range(reps):
+            s.record(); fn(); e.record(); torch.cuda.synchronize()
+            b = min(b, s.elapsed_time(e))
+        return b
+
+    out = {}
+    for name, nt, nug, ntg, nb, lam, grad, transform in (
+            ("cfg1_shape_misfit_grad", 256, 80, 512, 8192, 0.03, True, False),
+            ("cfg3_shape_misfit_only", 256, 80, 512, 8192, 0.03, False, False),
+            ("cfg4_shape_misfit_grad_arctan", 61, 79, 61, 30 * 2048, 0.04, True, True)):
+        w = make_windows_device(nb, nt, 77, dev)
+        obs = make_windows_device(1, nt, 5, dev)
+        t = torch.linspace(0, 1, nt, device=dev, dtype=torch.float32)
+        grid = (0.0, 1.0, -1.3, 1.3, nug, ntg)
+        if transform:
+            up = ((obs.double() + 1.3) + (obs.double() - 1.3)) / 2.6
+            tg = B.Target.from_waveform(t.double(), 0.5 + torch.atan(up) / np.pi, (0.0, 1.0, 0.0, 1.0, nug, ntg), nug, ntg, lam)
+        else:
+            tg = B.Target.from_waveform(t, obs[0], grid, nug, ntg, lam)
+        g = B.pack_grids(grid)
+        ws = torch.empty(C.lib.wfot_misfit_grad_workspace_bytes(nb, nt, nug, ntg), dtype=torch.uint8, device=dev)
+        st = B.Status()
+        ms = best(lambda: B.misfit_grad_batch(t, w, g, nug, ntg, lam, tg, workspace=ws, want_grad=grad,
+                                              transform=transform, status=st))
+        pairs = float(nug) * ntg * (nt - 1) * nb
+        out[name] = {"windows": nb, "ms": ms, "evals_per_s": nb / ms * 1e3,
+                     "algorithmic_tflops": ALG_FLOP_PER_PAIR * pairs / ms / 1e9}
+    # cfg2: batched 1-D OT, W2 + dW2/df + d/dx0 on random densities (FP32 in, FP64 out), C ABI called directly
+    n, nb = 1024, 100000
+    f = torch.rand(nb, n, device=dev) + 1e-3
+    gq = torch.rand(nb, n, device=dev) + 1e-3
+    x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
+    W = torch.zeros(nb, 2, dtype=torch.float64, device=dev)
+    dpos = torch.zeros(nb, 2, dtype=torch.float64, device=dev)
+    dW1 = torch.empty(nb, n, dtype=torch.float64, device=dev)
+    dW2 = torch.empty(nb, n, dtype=torch.float64, device=dev)
+    amp = torch.empty(nb, dtype=torch.float64, device=dev)
+    st = B.Status()
+    peak = None
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    for name, pm, moved in (("cfg2_ot1d_W2_dW2", 2, 4 * 2 * n + 8 * n + 40), ("cfg2_ot1d_W12_dW1_dW2", 3, 4 * 2 * n + 16 * n + 40)):
+        ms = best(lambda: C.check(C.lib.wfot_ot1d_batch(
+            C.ptr(f), C.ptr(gq), C.F32, C.ptr(x), C.ptr(x), n, n, 0, 0, n, n, nb, pm, 1, C.ptr(W),
+            C.ptr(dW1) if pm & 1 else None, C.ptr(dW2), C.ptr(dpos), C.ptr(amp), None, None, None, C.ptr(st.t), None)))
+        out[name] = {"pairs": nb, "ms": ms, "mpairs_per_s": nb / ms / 1e3,
+                     "roofline": {"bound": "hbm", "achieved": nb * 12288 / ms / 1e6, "peak": peak, "unit": "GB/s",
+                                  "frac": (nb * 12288 / ms / 1e6 / peak) if peak else None,
+                                  "algorithmic_bytes_per_pair": 12288, "moved_bytes_per_pair": moved,
+                                  "moved_gbs": nb * moved / ms / 1e6,
+                                  "note": "FP64 outputs: the kernel is instruction-issue bound, not HBM bound (DESIGN.md 3.4)"}}
+    return out
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -339,6 +410,8 @@ def run_ours(args):
             "clocks": clocks,
             "status_counters": {"slow_pixels": int(st[4]), "common_cdf": int(st[1]), "zero_dist": int(st[2])},
         }
+        if world == 1 and args.secondary:
+            line["secondary"] = secondary_configs(dev)
         if world == 1 and args.cpu_sample > 0:
             v, dt = cpu_eval_rate(args.cpu_sample, 1)
             line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
