@@ -173,6 +173,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _ricker_obs():
+    """Observed double Ricker wavelet of Ricker_Figs_1_7.ipynb cell 10 (noise free): host NumPy, input data only."""
+    f = 1.0 * 25 * 4 / 128
+    t = np.arange(-2.0, (4 - 4 / 128) / 2, 4 / 128)
+    w = (1.0 - 2.0 * np.pi ** 2 * f ** 2 * t ** 2) * np.exp(-np.pi ** 2 * f ** 2 * t ** 2)
+    return np.linspace(-2.0, 2.0, 256), 1.6 * np.concatenate((w, w))
+
+
 # ----------------------------------------------------------------------------- other configs (N=1)
 def secondary_configs(dev):
     """Device-resident kernel timings of BASELINE.json configs[0..3]'s shapes (not the headline):
@@ -213,6 +221,20 @@ def secondary_configs(dev):
         pairs = float(nug) * ntg * (nt - 1) * nb
         out[name] = {"windows": nb, "ms": ms, "evals_per_s": nb / ms * 1e3,
                      "algorithmic_tflops": ALG_FLOP_PER_PAIR * pairs / ms / 1e9}
+    # cfg3 end to end: 512 x 512 (time shift x amplitude) misfit surface, Ricker forward model generated on the
+    # device, W1 and W2 marginal misfits of every model against one observed window, results back on the host
+    from waveform_ot_b200 import adapters
+    to, wo = _ricker_obs()
+    grid3 = (-2.0, 2.0, -1.8, 4.2, 80, 512)
+    tgt3 = adapters.make_target(to, wo, grid3, 0.03)
+    tsh, amp = np.linspace(-4, 4, 512), np.linspace(0.2, 4, 512)
+    adapters.misfit_surface(tsh[:8], amp[:8], 1.0, tgt3, grid3, 0.03)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    adapters.misfit_surface(tsh, amp, 1.0, tgt3, grid3, 0.03)
+    dt3 = time.perf_counter() - t0
+    out["cfg3_surface_512x512_W1_and_W2"] = {"models": 512 * 512, "seconds": dt3, "models_per_s": 512 * 512 / dt3,
+                                            "note": "wall clock incl. on-device forward model, 2 fused passes (W1, W2), D2H"}
     # cfg2: batched 1-D OT, W2 + dW2/df + d/dx0 on random densities (FP32 in, FP64 out), C ABI called directly
     n, nb = 1024, 100000
     f = torch.rand(nb, n, device=dev) + 1e-3

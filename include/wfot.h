@@ -152,6 +152,14 @@ int wfot_pdfderiv_batch(const double* pdf, const double* dfield, const int32_t* 
                         int B, int npix, int nt, double lambda, int q,
                         double* out, void* stream);
 
+/* ---- Ricker forward model ------------------------
+ * Replaces ru.rickerwavelet(tpert, amp, f, trange=(t0,t1), deriv=...) for noise-free
+ * waveforms: libs/ricker_util.py:22-30, 38-89.  params (M, 3) FP64 rows = (tpert, amp, f).
+ * Outputs: t (M, 256) sample times, w (M, 256) amplitudes, dw (M, 3, 256) (NULL = no
+ * derivatives) = d(w)/d(time offset, amplitude, frequency factor) (:84-86). */
+int wfot_ricker_batch(const double* params, int M, double t0, double t1,
+                      double* t, double* w, double* dw, void* stream);
+
 /* ---- fused misfit + gradient (throughput path) -------------------------------
  * One "evaluation" per window: fingerprint -> marginals -> W_p^p per marginal ->
  * d/d(waveform amplitudes) per marginal and d/d(window position), nothing but

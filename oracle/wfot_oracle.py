@@ -505,19 +505,47 @@ def misfit_grad_window(t, w, grid, target: Pdf, lambdav=0.04, distfunc="W2",
 # --------------------------------------------------------------------------
 
 
-def ricker(f, length=0.128, dt=0.001):
-    """libs/ricker_util.py:22-30 (no derivative)."""
+def ricker(f, length=0.128, dt=0.001, deriv=False):
+    """libs/ricker_util.py:22-30."""
     t = np.arange(-length / 2, (length - dt) / 2, dt)
-    a = 1.0 - 2.0 * (np.pi ** 2) * (f ** 2) * (t ** 2)
-    return t, a * np.exp(-(np.pi ** 2) * (f ** 2) * (t ** 2))
+    a = (1.0 - 2.0 * (np.pi ** 2) * (f ** 2) * (t ** 2))
+    b = np.exp(-(np.pi ** 2) * (f ** 2) * (t ** 2))
+    y = a * b
+    if deriv:                                                     # :27-29
+        dw = b * (-4.0 * (np.pi ** 2) * (f) * (t ** 2)) + a * (-(np.pi ** 2) * (2 * f) * (t ** 2) * b)
+        return t, y, dw
+    return t, y
 
 
-def rickerwavelet(tpert, amp, f, trange=(-2.0, 2.0)):
-    """Noise-free double Ricker wavelet, libs/ricker_util.py:62-70,89."""
-    _, w = ricker(f * 25 * 4 / 128, length=4, dt=4 / 128)
-    wp = amp * np.concatenate((w, w))
-    tp = np.linspace(trange[0], trange[1], len(wp))
+def rickerwavelet(tpert, amp, f, trange=(-2.0, 2.0), deriv=False):
+    """Noise-free double Ricker wavelet and its derivatives w.r.t. (time offset, amplitude, frequency
+    factor), libs/ricker_util.py:62-70,81-89 (sigma_amp = 0, removejitter = True)."""
+    freq = f * 25 * 4 / 128                                       # :62
+    if deriv:
+        _, w, dw = ricker(freq, length=4, dt=4 / 128, deriv=True)
+    else:
+        _, w = ricker(freq, length=4, dt=4 / 128)
+    wp = amp * np.concatenate((w, w))                             # :65
+    tp = np.linspace(trange[0], trange[1], len(wp))               # :70
+    if deriv:
+        dwpd = np.zeros((3, len(wp)))
+        dwpd[0] = -np.gradient(wp, tp[1] - tp[0])                 # :84
+        dwpd[1] = np.concatenate((w, w))                          # :85
+        dwpd[2] = amp * np.concatenate((dw, dw)) * 25 * 4 / 128   # :86
+        return tp + tpert, wp, dwpd
     return tp + tpert, wp
+
+
+def ricker_optfunc(x, target: "Pdf", distfunc, trange, grid, lambdav, alpha=0.5, theta=45.0):
+    """libs/ricker_util.py:373-404 (optfunc, transform=False): weighted marginal misfit and its gradient
+    w.r.t. the three Ricker parameters; deriv[0] is the window-position derivative (:402)."""
+    tpos, wpos, dw = rickerwavelet(x[0], x[1], x[2], trange=trange, deriv=True)
+    W, dr, dg, _, _ = misfit_grad_window(tpos, wpos, grid, target, lambdav=lambdav, distfunc=distfunc, theta=theta)
+    w2 = alpha * W[0] + (1 - alpha) * W[1]                        # :390
+    dgs = alpha * dg[0] + (1 - alpha) * dg[1]                     # :392
+    deriv = alpha * dw.dot(dr[0]) + (1 - alpha) * dw.dot(dr[1])   # :399-401
+    deriv[0] = dgs                                                # :402
+    return w2, deriv
 
 
 def random_walk_windows(B, nt, seed=5, dtype=np.float32):

@@ -130,6 +130,29 @@ def main():
     d.update(raw_wp=wp, raw_wo=wo, u0=u0, u1=u1)
     np.savez_compressed(os.path.join(HERE, "cmt_window.npz"), **d)
 
+    # ---- (6) Ricker forward model + derivatives and the full optfunc chain
+    #          (libs/ricker_util.py:38-89, 373-404; Ricker_Figs_3_8.ipynb cells 14/26/32 set-up, noise free)
+    params = np.array([[0.0, 1.6, 1.0], [4.5, 1.6, 0.8], [5.0, 3.0, 0.5], [-1.3, 0.7, 1.4], [0.35, 2.2, 1.1]])
+    T, Wv, DW = [], [], []
+    for tp_, a_, f_ in params:
+        t_, w_, dw_ = ru.rickerwavelet(tp_, a_, f_, trange=[-2., 2.], deriv=True)
+        T.append(t_); Wv.append(w_); DW.append(dw_)
+    grid = (-2, 2, -1.8, 4.2, 40, 128)
+    lam, alpha = 0.03, 0.5
+    to, wo = ru.rickerwavelet(0.0, 1.6, 1.0, trange=[-2., 2.])
+    wfo, tgt = ru.BuildOTobjfromWaveform(to, wo, grid, lambdav=lam)
+    X = np.array([[0.7, 1.3, 0.8], [-0.4, 2.0, 1.2], [1.5, 1.0, 0.9]])
+    ru.ricker_util_opt.init()          # module-global history lists optfunc appends to (notebooks do this too)
+    F, G = [], []
+    for x in X:
+        data = [tgt, 'W2', [-2., 2.], grid, lam, False, alpha, 45.0]
+        w2, dv = ru.optfunc(x, data)
+        F.append(w2); G.append(dv)
+    np.savez_compressed(os.path.join(HERE, "ricker_forward.npz"), params=params, t=np.array(T), w=np.array(Wv),
+                        dw=np.array(DW), grid=np.array(grid, dtype=np.float64), lam=lam, alpha=alpha, to=to, wo=wo,
+                        X=X, F=np.array(F), G=np.array(G))
+    print("ricker_forward", np.array(F), np.array(G)[0])
+
 
 if __name__ == "__main__":
     main()

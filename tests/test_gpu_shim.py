@@ -156,3 +156,53 @@ def test_cmt_models_adapter(mods):
         assert mis[m] == pytest.approx(tot, rel=1e-7)
         np.testing.assert_allclose(dr[m], drm, rtol=1e-5, atol=1e-7 * np.abs(drm).max())
         np.testing.assert_allclose(dmis[m], J[m].dot(drm.reshape(-1)), rtol=1e-5, atol=1e-7 * np.abs(dmis[m]).max())
+
+
+def test_ricker_forward_batch_golden(mods, golden):
+    """wfot_ricker_batch against the reference's rickerwavelet(..., deriv=True) (libs/ricker_util.py:38-89):
+    sample times bit-exact, amplitudes / derivatives to a few ulp (CUDA exp vs libm exp)."""
+    from waveform_ot_b200 import batch as B
+    g = golden("ricker_forward")
+    r = B.ricker_batch(g["params"], (-2.0, 2.0), deriv=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(r["t"].cpu().numpy(), g["t"])
+    np.testing.assert_allclose(r["w"].cpu().numpy(), g["w"], rtol=4e-16, atol=1e-300)
+    scale = np.abs(g["dw"]).max(axis=2, keepdims=True)
+    np.testing.assert_allclose(r["dw"].cpu().numpy(), g["dw"], rtol=1e-13, atol=1e-15 * scale.max())
+
+
+def test_optfunc_ricker_batch_golden(mods, golden):
+    """ru.optfunc (libs/ricker_util.py:373-404) for a batch of models, all on the device."""
+    _, _, adapters = mods
+    g = golden("ricker_forward")
+    grid = _grid(g)
+    lam, alpha = float(g["lam"]), float(g["alpha"])
+    target = adapters.make_target(g["to"], g["wo"], grid, lam)
+    data = [target, "W2", (-2.0, 2.0), grid, lam, False, alpha, 45.0]
+    w2, deriv = adapters.optfunc_ricker_batch(g["X"], data)
+    np.testing.assert_allclose(w2, g["F"], rtol=1e-9)
+    np.testing.assert_allclose(deriv, g["G"], rtol=1e-7, atol=1e-10)
+    # single-model host-forward variant agrees
+    w2s, ds = adapters.optfunc_ricker(g["X"][1], data, lambda x, tr: O.rickerwavelet(x[0], x[1], x[2], trange=tr, deriv=True))
+    assert w2s == pytest.approx(float(g["F"][1]), rel=1e-9)
+    np.testing.assert_allclose(ds, g["G"][1], rtol=1e-7, atol=1e-10)
+
+
+def test_misfit_surface_vs_oracle(mods):
+    """Ricker_Figs_1_7.ipynb cells 34/38 (misfit surface over time shift x amplitude), small grid."""
+    _, _, adapters = mods
+    grid = (-2.0, 2.0, -1.8, 4.2, 24, 96)
+    lam = 0.03
+    to, wo = O.rickerwavelet(0.0, 1.6, 1.0)
+    target = adapters.make_target(to, wo, grid, lam)
+    ts, am = np.array([-1.5, 0.4, 2.0]), np.array([0.5, 1.7])
+    W1, W2 = adapters.misfit_surface(ts, am, 1.0, target, grid, lam)
+    _, tgt = O.build_ot_from_waveform(to, wo, grid, lambdav=lam)
+    for i, tsh in enumerate(ts):
+        for j, a in enumerate(am):
+            tp, wp = O.rickerwavelet(tsh, a, 1.0)
+            _, src = O.build_ot_from_waveform(tp, wp, grid, lambdav=lam)
+            w1 = O.marg_wasserstein(src, tgt, "W1", returnmargW=True)[0]
+            w2 = O.marg_wasserstein(src, tgt, "W2", returnmargW=True)[0]
+            np.testing.assert_allclose(W1[i, j], w1, rtol=1e-9)
+            np.testing.assert_allclose(W2[i, j], w2, rtol=1e-9)

@@ -143,3 +143,18 @@ def test_error_behaviour():
         O.wasser(p, O.otpdf(np.ones(5), x), "W2", derivatives=True)
     with pytest.raises(O.TargetSource2DShapeError):
         O.marg_wasserstein(p, p)
+
+
+def test_ricker_forward_and_optfunc_fixture(golden):
+    """Forward model + parameter derivatives bit-for-bit, optfunc chain to 1e-12 (libs/ricker_util.py:38-89,373-404)."""
+    g = golden("ricker_forward")
+    for i, (tp, a, f) in enumerate(g["params"]):
+        t, w, dw = O.rickerwavelet(tp, a, f, deriv=True)
+        np.testing.assert_array_equal(t, g["t"][i])
+        np.testing.assert_array_equal(w, g["w"][i])
+        np.testing.assert_array_equal(dw, g["dw"][i])
+    grid = tuple(g["grid"][:4]) + (int(g["grid"][4]), int(g["grid"][5]))
+    _, tg = O.build_ot_from_waveform(g["to"], g["wo"], grid, lambdav=float(g["lam"]))
+    f_, g_ = O.ricker_optfunc(g["X"][0], tg, "W2", (-2.0, 2.0), grid, float(g["lam"]), float(g["alpha"]))
+    assert f_ == pytest.approx(float(g["F"][0]), rel=1e-12)
+    np.testing.assert_allclose(g_, g["G"][0], rtol=1e-10, atol=1e-14)

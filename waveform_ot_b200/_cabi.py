@@ -52,6 +52,7 @@ SIGNATURES = {
     "wfot_misfit_grad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "wfot_misfit_grad_batch": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _d, _i, _i, _i,
                                          _p, _p, _p, _p, _i, _p, _p, _p, _p, _sz, _p, _p]),
+    "wfot_ricker_batch": (C.c_int, [_p, _i, _d, _d, _p, _p, _p, _p]),
     "wfot_chain_batch": (C.c_int, [_p, _p, _i, _i, _i, _ll, _p, _p]),
     "wfot_sum_windows_workspace_bytes": (_sz, [_i]),
     "wfot_sum_windows": (C.c_int, [_p, _ll, _i, _p, _p, _sz, _p]),

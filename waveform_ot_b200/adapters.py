@@ -124,3 +124,47 @@ def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfu
         dmis = _B.chain_batch(J, dr.reshape(M, nr * nc * nt).contiguous())        # :296
     torch.cuda.current_stream().synchronize()
     return mis.cpu().numpy(), None if dmis is None else dmis.cpu().numpy(), dr.reshape(M, nr, nc, nt).cpu().numpy()
+
+
+def optfunc_ricker_batch(X, data):
+    """libs/ricker_util.py:373-404 (optfunc) for M trial models at once, everything on the device:
+    forward model + derivatives (wfot_ricker_batch), fused fingerprint / OT / gradient, chain rule.
+    X (M, 3) rows (t0, amplitude, frequency factor); data as for optfunc_ricker (with transform the target
+    must come from make_target(..., transform=True); the kernel applies the arctan transform and its
+    derivative, :393-397).  Returns w2 (M,), deriv (M, 3) as NumPy."""
+    import torch
+    target, distfunc, trange, grid, lambdav, transform, alpha, theta = data
+    t0, t1, u0, u1, Nu, Nt = grid
+    tant = 1.0 if theta == 45.0 else float(np.tan(np.pi * theta / 180.0))
+    fw = _B.ricker_batch(X, trange, deriv=True)
+    r = _B.misfit_grad_batch(fw["t"], fw["w"], (t0, t1, u0, u1, Nu, Nt), int(Nu), int(Nt), lambdav, target,
+                             distfunc=distfunc, tantheta=tant, transform=transform)
+    W, gr = r["W"], r["grad"]
+    w2 = alpha * W[:, 0] + (1 - alpha) * W[:, 1]                                   # :390
+    dr = alpha * gr[:, 0] + (1 - alpha) * gr[:, 1]                                 # :399-401 (linear in dr)
+    deriv = _B.chain_batch(fw["dw"], dr.contiguous())                              # dw.dot(dr)
+    deriv[:, 0] = alpha * r["dwg"] / (tant * (t1 - t0))                            # :333,392,402 (dgM[1] = 0)
+    torch.cuda.current_stream().synchronize()
+    return w2.cpu().numpy(), deriv.cpu().numpy()
+
+
+def misfit_surface(tshifts, amps, f, target, grid, lambdav, trange=(-2.0, 2.0), theta=45.0, chunk=65536):
+    """Misfit surface of Ricker_Figs_1_7.ipynb cells 34/38: W1 and W2 marginal misfits of the double Ricker
+    wavelet for every (time shift, amplitude) pair against one observed window, generated and evaluated on
+    the device.  Returns W1, W2 of shape (len(tshifts), len(amps), 2) = [W^t, W^u] as NumPy."""
+    import torch
+    t0, t1, u0, u1, Nu, Nt = grid
+    tant = 1.0 if theta == 45.0 else float(np.tan(np.pi * theta / 180.0))
+    ts, am = np.meshgrid(np.asarray(tshifts, dtype=np.float64), np.asarray(amps, dtype=np.float64), indexing="ij")
+    P = np.stack([ts.ravel(), am.ravel(), np.full(ts.size, float(f))], axis=1)
+    out = {"W1": [], "W2": []}
+    g = _B.pack_grids((t0, t1, u0, u1, Nu, Nt), tant)
+    for a in range(0, P.shape[0], chunk):
+        fw = _B.ricker_batch(P[a:a + chunk], trange)
+        for d in ("W1", "W2"):
+            r = _B.misfit_grad_batch(fw["t"], fw["w"], g, int(Nu), int(Nt), lambdav, target, distfunc=d,
+                                     want_grad=False)
+            out[d].append(r["W"])
+    torch.cuda.current_stream().synchronize()
+    shp = (len(tshifts), len(amps), 2)
+    return torch.cat(out["W1"]).cpu().numpy().reshape(shp), torch.cat(out["W2"]).cpu().numpy().reshape(shp)

@@ -301,6 +301,21 @@ def chain_batch(J, dr):
     return out
 
 
+def ricker_batch(params, trange=(-2.0, 2.0), deriv=False):
+    """rickerwavelet(tpert, amp, f, trange, deriv) for M parameter rows (libs/ricker_util.py:38-89,
+    noise free).  Returns device tensors t (M,256), w (M,256) and, with deriv, dw (M,3,256)."""
+    dev = _device()
+    params = _as_device(params, torch.float64).reshape(-1, 3).contiguous()
+    M = params.shape[0]
+    f64 = dict(dtype=torch.float64, device=dev)
+    t = torch.empty((M, 256), **f64)
+    w = torch.empty((M, 256), **f64)
+    dw = torch.empty((M, 3, 256), **f64) if deriv else None
+    C.check(C.lib.wfot_ricker_batch(C.ptr(params), M, float(trange[0]), float(trange[1]), C.ptr(t), C.ptr(w),
+                                    C.ptr(dw), _stream()), "wfot_ricker_batch")
+    return dict(t=t, w=w, dw=dw, _keepalive=(params,))
+
+
 def sum_windows(x):
     """Deterministic FP64 sum over the leading (window) axis of a device tensor (B, ...)."""
     dev = _device()

@@ -130,7 +130,7 @@ __device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* p
 // NT threads per CTA: 256 for large grids; 128 (4 CTAs per SM) for small windows, where the per-window
 // phases are short and more co-resident windows hide the block barriers between them.
 template <int R, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 4) k_misfit_grad(FusedArgs a) {
+__global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -413,12 +413,12 @@ using namespace wfot;
 extern "C" {
 
 // Scratch: 28 bytes per pixel per resident CTA.  Sized for the largest grid the
-// device can co-schedule (SM count x 4 CTAs) so the query needs no device call.
+// device can co-schedule (SM count x 8 CTAs) so the query needs no device call.
 size_t wfot_misfit_grad_workspace_bytes(int B, int nt, int nug, int ntg) {
     if (B <= 0 || nt < 2 || nug < 1 || ntg < 1) return 0;
     int sms = wfot_device_sm_count();
     if (sms <= 0) sms = 148;
-    size_t ctas = (size_t)sms * 4;
+    size_t ctas = (size_t)sms * 8;
     if ((size_t)B < ctas) ctas = (size_t)B;
     return ctas * (size_t)nug * ntg * 28 + 256;
 }
@@ -448,10 +448,16 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     if (smem > 227 * 1024) return WFOT_ERR_UNSUPPORTED;
     int per_sm = 0;
     const int R = rows_per_thread();
-    const bool small = (R == 4) && ((long long)nug * ntg <= 16384);      // small windows: 128-thread CTAs, 4 per SM
-    int ctas = small ? resident_ctas(k_misfit_grad<4, 128>, smem, &per_sm, 128)
-                     : (R == 4) ? resident_ctas(k_misfit_grad<4, 256>, smem, &per_sm)
-                                : resident_ctas(k_misfit_grad<8, 256>, smem, &per_sm);
+    // small windows: 128-thread CTAs (4 per SM), tiny ones 64-thread CTAs (8 per SM)
+    const char* ent = getenv("WFOT_DEV_NT");
+    int nthreads = 256;
+    if (R == 4 && (long long)nug * ntg <= 16384) nthreads = 128;
+    if (R == 4 && (long long)nug * ntg <= 8192) nthreads = 64;
+    if (R == 4 && ent) nthreads = atoi(ent) == 64 ? 64 : atoi(ent) == 128 ? 128 : 256;
+    int ctas = nthreads == 64 ? resident_ctas(k_misfit_grad<4, 64>, smem, &per_sm, 64)
+             : nthreads == 128 ? resident_ctas(k_misfit_grad<4, 128>, smem, &per_sm, 128)
+             : (R == 4) ? resident_ctas(k_misfit_grad<4, 256>, smem, &per_sm)
+                        : resident_ctas(k_misfit_grad<8, 256>, smem, &per_sm);
     if (ctas < 1) return cuda_fail(cudaGetLastError(), "k_misfit_grad occupancy");
     if (ctas > B) ctas = B;
     const size_t npix = (size_t)nug * ntg;
@@ -465,7 +471,8 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     a.s_wa = (double*)p;    p += (size_t)ctas * npix * 8;
     a.s_wb = (double*)p;    p += (size_t)ctas * npix * 8;
     a.s_idx = (int32_t*)p;
-    if (small) k_misfit_grad<4, 128><<<ctas, 128, smem, stream>>>(a);
+    if (nthreads == 64) k_misfit_grad<4, 64><<<ctas, 64, smem, stream>>>(a);
+    else if (nthreads == 128) k_misfit_grad<4, 128><<<ctas, 128, smem, stream>>>(a);
     else if (R == 4) k_misfit_grad<4, 256><<<ctas, 256, smem, stream>>>(a);
     else k_misfit_grad<8, 256><<<ctas, 256, smem, stream>>>(a);
     cudaError_t e = cudaGetLastError();

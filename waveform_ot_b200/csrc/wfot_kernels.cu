@@ -332,6 +332,48 @@ __global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__
     out[c] = s;
 }
 
+// ============================================================ k_ricker
+// Noise-free double Ricker wavelet and its derivatives w.r.t. (time offset, amplitude, frequency
+// factor): libs/ricker_util.py:22-30 (ricker) and :62-70,81-89 (rickerwavelet, sigma_amp = 0,
+// removejitter = True), in the reference's order of elementary operations.  One block per model,
+// one thread per sample (2 x 128 samples, length = 4, dt = 4/128 as hard-wired at :63).
+__global__ void __launch_bounds__(256) k_ricker(const double* __restrict__ params, int M, double t0, double t1,
+                                                double pi2, double* __restrict__ tout, double* __restrict__ wout,
+                                                double* __restrict__ dwout) {
+    __shared__ double swp[256];
+    const int mI = blockIdx.x, i = threadIdx.x;
+    if (mI >= M) return;
+    const double tpert = params[3 * (size_t)mI], amp = params[3 * (size_t)mI + 1], ff = params[3 * (size_t)mI + 2];
+    const double f = __ddiv_rn(__dmul_rn(__dmul_rn(ff, 25.0), 4.0), 128.0);            // :62
+    const double tr = __dadd_rn(__dmul_rn((double)(i & 127), 0.03125), -2.0);          // np.arange(-2, ., 4/128) (:23)
+    const double f2 = __dmul_rn(f, f), t2 = __dmul_rn(tr, tr);
+    const double a = __dsub_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(2.0, pi2), f2), t2));   // :24
+    const double b = exp(__dmul_rn(__dmul_rn(-pi2, f2), t2));                             // :25
+    const double y = __dmul_rn(a, b);                                                      // :26
+    const double wp = __dmul_rn(amp, y);                                                   // :65
+    const double step = __ddiv_rn(__dsub_rn(t1, t0), 255.0);                               // np.linspace (:70)
+    const double tp = (i == 255) ? t1 : __dadd_rn(__dmul_rn((double)i, step), t0);
+    const size_t o = (size_t)mI * 256 + i;
+    tout[o] = __dadd_rn(tp, tpert);                                                        // :87,89
+    wout[o] = wp;
+    if (dwout) {
+        swp[i] = wp;
+        __syncthreads();
+        const double h = __dsub_rn(__dadd_rn(step, t0), t0);                               // tp[1] - tp[0] (:84)
+        double gr;                                                                         // np.gradient, edge_order 1
+        if (i == 0) gr = __ddiv_rn(__dsub_rn(swp[1], swp[0]), h);
+        else if (i == 255) gr = __ddiv_rn(__dsub_rn(swp[255], swp[254]), h);
+        else gr = __ddiv_rn(__dsub_rn(swp[i + 1], swp[i - 1]), __dmul_rn(2.0, h));
+        const double e1 = __dmul_rn(__dmul_rn(__dmul_rn(-4.0, pi2), f), t2);               // :28
+        const double g1 = __dmul_rn(__dmul_rn(__dmul_rn(-pi2, __dmul_rn(2.0, f)), t2), b);
+        const double dwf = __dadd_rn(__dmul_rn(b, e1), __dmul_rn(a, g1));
+        double* d = dwout + (size_t)mI * 3 * 256;
+        d[i] = -gr;                                                                        // :84
+        d[256 + i] = y;                                                                    // :85
+        d[512 + i] = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(amp, dwf), 25.0), 4.0), 128.0);   // :86
+    }
+}
+
 // ============================================================ FP32 peak probe
 template <int PACKED>
 __global__ void __launch_bounds__(256) k_peak(int iters, float* sink) {
@@ -501,6 +543,17 @@ int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M, lon
     k_chain<<<blocks, 256, 0, stream>>>(J, dr, P, L, M, J_stride_models, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_chain_batch launch");
+    return WFOT_OK;
+}
+
+int wfot_ricker_batch(const double* params, int M, double t0, double t1, double* t, double* w, double* dw,
+                      void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!params || !t || !w || M <= 0) return WFOT_ERR_INVALID_ARG;
+    const double pi = 3.141592653589793;
+    k_ricker<<<M, 256, 0, stream>>>(params, M, t0, t1, pi * pi, t, w, dw);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_ricker_batch launch");
     return WFOT_OK;
 }
 
