@@ -55,7 +55,7 @@ enum wfot_stat_slot {
     WFOT_STAT_DEGENERATE_SEG = 3, /* zero-length segment        (libs/FingerprintLib.py:257, 0/0) */
     WFOT_STAT_SLOW_PIXELS = 4,    /* pixels resolved by the full FP64 rescan (diagnostic) */
     WFOT_STAT_SCAN_TILES = 6,     /* slots 6-7: 64-bit count of (warp, segment tile) pairs the pruned scan
-                                     evaluated, in units of 4096 (pixel, segment) pairs (diagnostic) */
+                                     evaluated, in units of 2048 (pixel, segment) pairs (diagnostic) */
     WFOT_STAT_SLOTS = 8
 };
 

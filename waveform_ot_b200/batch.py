@@ -80,8 +80,8 @@ class Status:
 
     def scan_pairs(self):
         """Executed (pixel, segment) pairs of the pruned scan (64-bit counter in slots 6-7,
-        kept by the kernels in units of 4096 pairs)."""
-        return 4096 * int(self.t.cpu().numpy()[C.STAT_SCAN_TILES:C.STAT_SCAN_TILES + 2].view("int64")[0])
+        kept by the kernels in units of 2048 pairs)."""
+        return 2048 * int(self.t.cpu().numpy()[C.STAT_SCAN_TILES:C.STAT_SCAN_TILES + 2].view("int64")[0])
 
 
 def fingerprint_batch(t, w, grids, nug, ntg, lambdav, q=None, tantheta=1.0, fpgrids=None,

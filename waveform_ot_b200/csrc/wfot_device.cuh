@@ -15,7 +15,7 @@
 //         D     = perp^2 + sat(|along| - h)^2          (h = half segment length)
 //     which is the clamped point-to-segment distance of
 //     libs/FingerprintLib.py:256-259 written in the segment's own frame.
-//     Only the running minimum per tile of kTile segments is kept.
+//     Only the running minimum per tile of T segments is kept.
 //   * resolve_pixel(): re-walks the winning tile, and evaluates every segment
 //     whose FP32 distance is within the rounding tolerance of the minimum in
 //     FP64 with exactly the reference's sequence of elementary operations, so
@@ -31,7 +31,10 @@
 
 namespace wfot {
 
-constexpr int kTile = 16;          // segments per argmin tile
+constexpr int kTilePad = 16;        // the segment table is padded to a multiple of this
+constexpr int kTileMin = 8;         // smallest argmin tile (sizes the per-tile bounding-box array)
+// The argmin tile size T (segments per tile) is a template parameter of the scan / resolve functions:
+// 16 for long waveforms, 8 for short ones (fewer FP32 re-evaluations per pixel, finer pruning).
 constexpr float kBig = 3.0e38f;    // "no distance yet"
 constexpr float kPadD = 5.0f;      // squared distance produced by padding segments (> any real one)
 
@@ -71,9 +74,10 @@ struct WinHdr {
 struct SegTable {
     const float4* A;   // {ex, ey, -am, -bm}   e = unit direction, am = mid.e, bm = mid x e (scaled)
     const float* H;    // half length (scaled)
-    const float4* bbox;   // per tile of kTile segments: {xlo, xhi, ylo, yhi} of its vertices (scaled frame)
+    const float4* bbox;   // per tile of `tile` segments: {xlo, xhi, ylo, yhi} of its vertices (scaled frame)
     int S;             // real segments
-    int Spad;          // padded to a multiple of kTile
+    int Spad;          // padded to a multiple of kTilePad
+    int tile;          // segments per tile (8 or 16)
     bool mono;         // sample times are non-decreasing: tiles are ordered along the time axis
 };
 
@@ -147,14 +151,15 @@ struct PixelHit {
 // afterwards in ascending segment order (strict '<' keeps np.argmin's first-minimum rule),
 // so lanes of a warp do not serialise on each other's candidates.
 // Returns false if the pixel must go to the full rescan.
-// FP32 re-evaluation of the 16 segments of one tile for one pixel: bit j set <=> D32(segment) <= thr.
+// FP32 re-evaluation of the T segments of one tile for one pixel: bit j set <=> D32(segment) <= thr.
 // Padding segments evaluate to kPadD > thr, so no bounds check is needed.
+template <int T>
 __device__ __forceinline__ unsigned tile_mask(const SegTable& tb, int tile, float px, float py, float thr) {
-    const float4* __restrict__ A = tb.A + tile * kTile;
-    const float4* __restrict__ H4 = reinterpret_cast<const float4*>(tb.H + tile * kTile);
+    const float4* __restrict__ A = tb.A + tile * T;
+    const float4* __restrict__ H4 = reinterpret_cast<const float4*>(tb.H + tile * T);
     unsigned mask = 0u;
 #pragma unroll
-    for (int q4 = 0; q4 < kTile / 4; ++q4) {
+    for (int q4 = 0; q4 < T / 4; ++q4) {
         const float4 h = H4[q4];
         const float hh[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
@@ -174,36 +179,38 @@ __device__ __forceinline__ unsigned tile_mask(const SegTable& tb, int tile, floa
 
 // FP64 reference-order evaluation of the candidate segments of one tile, ascending (strict '<'
 // keeps np.argmin's first-minimum rule across calls made in ascending tile order).
+template <int T>
 __device__ __forceinline__ void eval_candidates(const double2* __restrict__ pn, int tile, unsigned mask,
                                                 double px, double py, PixelHit& hit) {
     while (mask) {
         const int j = __ffs((int)mask) - 1;
         mask &= mask - 1u;
         double D, l;
-        eval64(pn, tile * kTile + j, px, py, D, l);
-        if (D < hit.D) { hit.D = D; hit.lam = l; hit.s = tile * kTile + j; }
+        eval64(pn, tile * T + j, px, py, D, l);
+        if (D < hit.D) { hit.D = D; hit.lam = l; hit.s = tile * T + j; }
     }
 }
 
+template <int T>
 __device__ __forceinline__ bool resolve_pixel(const SegTable& tb, const double2* __restrict__ pn,
                                               float pxl, float pyl, double px, double py,
                                               float b1, int t1, float b2, float b3, PixelHit& hit) {
     const float thr = b1 + tau32(b1);
-    hit.D = CUDART_INF; hit.lam = 0.0; hit.s = t1 * kTile;
+    hit.D = CUDART_INF; hit.lam = 0.0; hit.s = t1 * T;
     if (b2 > thr) {                                   // the common case: one tile
-        eval_candidates(pn, t1, tile_mask(tb, t1, pxl, pyl, thr), px, py, hit);
+        eval_candidates<T>(pn, t1, tile_mask<T>(tb, t1, pxl, pyl, thr), px, py, hit);
         return true;
     }
     if (b3 <= thr) return false;
     // exactly one other tile holds a candidate: resolved here only if it is a neighbour of t1
-    const int ntiles = tb.Spad / kTile;
-    const unsigned m0 = (t1 > 0) ? tile_mask(tb, t1 - 1, pxl, pyl, thr) : 0u;
-    const unsigned m2 = (t1 + 1 < ntiles) ? tile_mask(tb, t1 + 1, pxl, pyl, thr) : 0u;
+    const int ntiles = tb.Spad / T;
+    const unsigned m0 = (t1 > 0) ? tile_mask<T>(tb, t1 - 1, pxl, pyl, thr) : 0u;
+    const unsigned m2 = (t1 + 1 < ntiles) ? tile_mask<T>(tb, t1 + 1, pxl, pyl, thr) : 0u;
     if ((m0 | m2) == 0u) return false;
-    const unsigned m1 = tile_mask(tb, t1, pxl, pyl, thr);
-    if (m0) eval_candidates(pn, t1 - 1, m0, px, py, hit);
-    eval_candidates(pn, t1, m1, px, py, hit);
-    if (m2) eval_candidates(pn, t1 + 1, m2, px, py, hit);
+    const unsigned m1 = tile_mask<T>(tb, t1, pxl, pyl, thr);
+    if (m0) eval_candidates<T>(pn, t1 - 1, m0, px, py, hit);
+    eval_candidates<T>(pn, t1, m1, px, py, hit);
+    if (m2) eval_candidates<T>(pn, t1 + 1, m2, px, py, hit);
     return true;
 }
 
@@ -332,7 +339,7 @@ __device__ __forceinline__ LaneBlock lane_block(const FootMap& m, int f, int lan
 // every FP32 distance of such a tile exceeds b1 + tau32(b1) of every pixel of the warp (the FP32
 // rounding tolerance is 1.25e-6 absolute + 1.5e-7 relative in distance units, see tau32), so the
 // tile can neither hold the FP64 nearest segment nor a near-tie the resolve step has to look at.
-template <int R>
+template <int R, int T>
 __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& fp, float px0, float px1,
                                            const float (&py)[R],
                                            float (&b1)[2 * R], int (&t1)[2 * R], float (&b2)[2 * R],
@@ -344,7 +351,7 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
     for (int i = 0; i < R / 2; ++i) y2[i] = pack2(py[2 * i], py[2 * i + 1]);
 #pragma unroll
     for (int k = 0; k < 2 * R; ++k) { b1[k] = kBig; b2[k] = kBig; b3[k] = kBig; t1[k] = 0; }
-    const int ntiles = tb.Spad / kTile;
+    const int ntiles = tb.Spad / T;
     // start tile: the one whose time span holds the footprint centre (segments are normally time ordered;
     // any start is correct, a poor one only prunes less)
     int ct;
@@ -381,10 +388,10 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
         float tm[2 * R];
 #pragma unroll
         for (int k = 0; k < 2 * R; ++k) tm[k] = kBig;
-        const float4* __restrict__ A = tb.A + tile * kTile;
-        const float* __restrict__ H = tb.H + tile * kTile;
+        const float4* __restrict__ A = tb.A + tile * T;
+        const float* __restrict__ H = tb.H + tile * T;
 #pragma unroll 2
-        for (int j = 0; j < kTile; j += 2) {
+        for (int j = 0; j < T; j += 2) {
             const float4 a0 = A[j], a1 = A[j + 1];
             const float2 hh = *reinterpret_cast<const float2*>(H + j);
             // per column: P = px*ex - am, Q = px*ey - bm (both columns in one packed op)
@@ -465,7 +472,8 @@ struct PrepOut {
     double2* pn;    // [nt]
     float4* A;      // [Spad]  {ex, ey, -am, -bm}
     float* H;       // [Spad]
-    float4* bbox;   // [Spad / kTile]  per-tile vertex bounding boxes (scaled frame)
+    float4* bbox;   // [Spad / tile]  per-tile vertex bounding boxes (scaled frame)
+    int tile;       // segments per tile (8 or 16)
     float* pxs;     // [ntg]  scaled local pixel time coordinates
     float* pys;     // [nug]
     WinHdr* hdr;    // [1]
@@ -527,7 +535,7 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
     frexp(diag > 0.0 ? diag : 1.0, &ex);           // diag = m * 2^ex, m in [0.5, 1)
     const double sigma = ldexp(1.0, -ex);
     const int S = nt - 1;
-    const int Spad = ((S + kTile - 1) / kTile) * kTile;
+    const int Spad = ((S + kTilePad - 1) / kTilePad) * kTilePad;
     int degen = 0, nonmono = 0;
     for (int s = tid; s < Spad; s += nth) {
         float4 A;
@@ -551,8 +559,8 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
         }
         o.A[s] = A; o.H[s] = h;
     }
-    for (int tile = tid; tile < Spad / kTile; tile += nth) {
-        const int s0 = tile * kTile, s1 = min(s0 + kTile, S);      // vertices s0 .. s1 inclusive
+    for (int tile = tid; tile < Spad / o.tile; tile += nth) {
+        const int s0 = min(tile * o.tile, S), s1 = min(s0 + o.tile, S);      // vertices s0 .. s1 inclusive
         double xlo = CUDART_INF, xhi = -CUDART_INF, ylo = CUDART_INF, yhi = -CUDART_INF;
         for (int j = s0; j <= s1; ++j) {
             const double2 p = o.pn[j];

@@ -49,7 +49,7 @@ __host__ __device__ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad,
     const int ubase = o;
     L.A = take(Spad * 16);
     L.H = take(Spad * 4);
-    L.bbox = take((Spad / kTile) * 16);
+    L.bbox = take((Spad / kTileMin) * 16);
     const int uend_scan = o;
     o = ubase;
     L.cf = take(nmax * 8);
@@ -129,14 +129,14 @@ __device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* p
 
 // NT threads per CTA: 256 for large grids; 128 (4 CTAs per SM) for small windows, where the per-window
 // phases are short and more co-resident windows hide the block barriers between them.
-template <int R, int NT>
+template <int R, int NT, int T>
 __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     const size_t slab = (size_t)blockIdx.x * npix;
-    SegTable tb{s_A, s_H, s_bbox, S, a.Spad, false};
+    SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T, false};
     int zero_dist = 0, slow = 0, common = 0, degen = 0, tiles = 0;
 
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
             __threadfence();
         }
         __syncthreads();
-        PrepOut po{s_pn, s_A, s_H, s_bbox, s_pxs, s_pys, s_hdr};
+        PrepOut po{s_pn, s_A, s_H, s_bbox, tb.tile, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
         __syncthreads();
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
             for (int r = 0; r < R; ++r) py[r] = s_pys[min(rg * R + r, a.nug - 1)];
             float b1[2 * R], b2[2 * R], b3[2 * R];
             int t1[2 * R];
-            scan_block<R>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles);
+            scan_block<R, T>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles);
             if (!lb.owns) continue;
             float lb1[2 * R], lb2[2 * R], lb3[2 * R];
             int lt1[2 * R];
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
                 const float kb1 = lb1[k];
                 const double pyd = s_xu[iu];
                 PixelHit hit;
-                if (!resolve_pixel(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, kb1, lt1[k], lb2[k], lb3[k], hit)) {
+                if (!resolve_pixel<T>(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, kb1, lt1[k], lb2[k], lb3[k], hit)) {
                     const int qi = atomicAdd(s_qcount, 1);
                     if (qi < kFQCap) { s_queue[qi] = FQEntry{iu * a.ntg + it, kb1}; continue; }
                     ++slow;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
         if (degen) atomicAdd(a.status + WFOT_STAT_DEGENERATE_SEG, degen);
         if (lane == 0 && tiles)
             atomicAdd(reinterpret_cast<unsigned long long*>(a.status + WFOT_STAT_SCAN_TILES),
-                      (unsigned long long)tiles * (R / 4));
+                      (unsigned long long)tiles * (R / 4) * (T / 8));
     }
 }
 
@@ -345,12 +345,12 @@ __global__ void __launch_bounds__(256, 2) k_scan_probe(FusedArgs a, float* out) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     const int tid = threadIdx.x, S = a.nt - 1;
-    SegTable tb{s_A, s_H, s_bbox, S, a.Spad, false};
+    SegTable tb{s_A, s_H, s_bbox, S, a.Spad, 16, false};
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
         if (tid == 0) { s_hdr->degenerate = 0; s_hdr->nonmono = 0; }
         __syncthreads();
-        PrepOut po{s_pn, s_A, s_H, s_bbox, s_pxs, s_pys, s_hdr};
+        PrepOut po{s_pn, s_A, s_H, s_bbox, tb.tile, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, 0, po, s_red, nullptr);
         __syncthreads();
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256, 2) k_scan_probe(FusedArgs a, float* out) 
             for (int r = 0; r < R; ++r) py[r] = s_pys[min(rg * R + r, a.nug - 1)];
             float b1[2 * R], b2[2 * R], b3[2 * R];
             int t1[2 * R];
-            scan_block<R>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles);
+            scan_block<R, 16>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles);
             if (!lb.owns) continue;
 #pragma unroll
             for (int k = 0; k < 2 * R; ++k) {
@@ -454,10 +454,13 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     if (R == 4 && (long long)nug * ntg <= 16384) nthreads = 128;
     if (R == 4 && (long long)nug * ntg <= 8192) nthreads = 64;
     if (R == 4 && ent) nthreads = atoi(ent) == 64 ? 64 : atoi(ent) == 128 ? 128 : 256;
-    int ctas = nthreads == 64 ? resident_ctas(k_misfit_grad<4, 64>, smem, &per_sm, 64)
-             : nthreads == 128 ? resident_ctas(k_misfit_grad<4, 128>, smem, &per_sm, 128)
-             : (R == 4) ? resident_ctas(k_misfit_grad<4, 256>, smem, &per_sm)
-                        : resident_ctas(k_misfit_grad<8, 256>, smem, &per_sm);
+    const int T = tile_for(nt);
+    int ctas;
+#define WFOT_OCC(RR, NN, TT) resident_ctas(k_misfit_grad<RR, NN, TT>, smem, &per_sm, NN)
+    if (R == 8) ctas = WFOT_OCC(8, 256, 16);
+    else if (T == 8) ctas = nthreads == 64 ? WFOT_OCC(4, 64, 8) : nthreads == 128 ? WFOT_OCC(4, 128, 8) : WFOT_OCC(4, 256, 8);
+    else ctas = nthreads == 64 ? WFOT_OCC(4, 64, 16) : nthreads == 128 ? WFOT_OCC(4, 128, 16) : WFOT_OCC(4, 256, 16);
+#undef WFOT_OCC
     if (ctas < 1) return cuda_fail(cudaGetLastError(), "k_misfit_grad occupancy");
     if (ctas > B) ctas = B;
     const size_t npix = (size_t)nug * ntg;
@@ -471,10 +474,11 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     a.s_wa = (double*)p;    p += (size_t)ctas * npix * 8;
     a.s_wb = (double*)p;    p += (size_t)ctas * npix * 8;
     a.s_idx = (int32_t*)p;
-    if (nthreads == 64) k_misfit_grad<4, 64><<<ctas, 64, smem, stream>>>(a);
-    else if (nthreads == 128) k_misfit_grad<4, 128><<<ctas, 128, smem, stream>>>(a);
-    else if (R == 4) k_misfit_grad<4, 256><<<ctas, 256, smem, stream>>>(a);
-    else k_misfit_grad<8, 256><<<ctas, 256, smem, stream>>>(a);
+#define WFOT_LAUNCH(RR, NN, TT) k_misfit_grad<RR, NN, TT><<<ctas, NN, smem, stream>>>(a)
+    if (R == 8) WFOT_LAUNCH(8, 256, 16);
+    else if (T == 8) { if (nthreads == 64) WFOT_LAUNCH(4, 64, 8); else if (nthreads == 128) WFOT_LAUNCH(4, 128, 8); else WFOT_LAUNCH(4, 256, 8); }
+    else { if (nthreads == 64) WFOT_LAUNCH(4, 64, 16); else if (nthreads == 128) WFOT_LAUNCH(4, 128, 16); else WFOT_LAUNCH(4, 256, 16); }
+#undef WFOT_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_misfit_grad_batch launch");
     return WFOT_OK;

@@ -16,18 +16,20 @@ struct FpWorkspace {
     double2* pn;     // [chunk][nt]
     float4* A;       // [chunk][Spad]  {ex, ey, -am, -bm}
     float* H;        // [chunk][Spad]
-    float4* bbox;    // [chunk][Spad / kTile]
+    float4* bbox;    // [chunk][Spad / kTileMin]
     float* pxs;      // [chunk][ntg_pad]
     float* pys;      // [chunk][nug_pad]
     int Spad, ntg_pad, nug_pad;
 };
 
-inline int seg_pad(int nt) { return ((nt - 1 + kTile - 1) / kTile) * kTile; }
+inline int seg_pad(int nt) { return ((nt - 1 + kTilePad - 1) / kTilePad) * kTilePad; }
+// argmin tile size: short waveforms use 8-segment tiles (fewer FP32 re-evaluations per pixel, finer pruning)
+inline int tile_for(int nt) { return (nt - 1 <= 256) ? 8 : 16; }
 inline int pad4(int n) { return (n + 3) & ~3; }
 
 inline size_t fp_workspace_per_window(int nt, int nug, int ntg) {
     const size_t Spad = (size_t)seg_pad(nt);
-    return 128 + (size_t)nt * 16 + Spad * 21 + (size_t)(pad4(ntg) + pad4(nug)) * 4;
+    return 128 + (size_t)nt * 16 + Spad * 20 + (Spad / kTileMin) * 16 + (size_t)(pad4(ntg) + pad4(nug)) * 4;
 }
 
 inline FpWorkspace fp_workspace_carve(void* base, int chunk, int nt, int nug, int ntg) {
@@ -40,7 +42,7 @@ inline FpWorkspace fp_workspace_carve(void* base, int chunk, int nt, int nug, in
     ws.pn = (double2*)p;   p += (size_t)chunk * nt * 16;
     ws.A = (float4*)p;     p += (size_t)chunk * ws.Spad * 16;
     ws.H = (float*)p;      p += (size_t)chunk * ws.Spad * 4;
-    ws.bbox = (float4*)p;  p += (size_t)chunk * ws.Spad;
+    ws.bbox = (float4*)p;  p += (size_t)chunk * (ws.Spad / kTileMin) * 16;
     ws.pxs = (float*)p;    p += (size_t)chunk * ws.ntg_pad * 4;
     ws.pys = (float*)p;
     return ws;

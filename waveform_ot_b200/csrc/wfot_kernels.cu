@@ -27,7 +27,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct PrepArgs {
     const void* t; const void* w; int dtype; long long t_stride; int nt;
     const wfot_grid* grids; int n_grids; long long b0; int nug, ntg; int transform;
-    FpWorkspace ws; double* pn_out; int32_t* status;
+    FpWorkspace ws; double* pn_out; int32_t* status; int tile;
 };
 
 __global__ void __launch_bounds__(256) k_prep(PrepArgs a) {
@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs a) {
     o.pn = a.ws.pn + (size_t)wl * a.nt;
     o.A = a.ws.A + (size_t)wl * a.ws.Spad;
     o.H = a.ws.H + (size_t)wl * a.ws.Spad;
-    o.bbox = a.ws.bbox + (size_t)wl * (a.ws.Spad / kTile);
+    o.bbox = a.ws.bbox + (size_t)wl * (a.ws.Spad / kTileMin);
+    o.tile = a.tile;
     o.pxs = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
     o.pys = a.ws.pys + (size_t)wl * a.ws.nug_pad;
     o.hdr = a.ws.hdr + wl;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void emit_pixel(const FpArgs& a, const double2* pn, c
     }
 }
 
-template <int R>
+template <int R, int T>
 __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wl = blockIdx.y;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     const int Spad = a.ws.Spad, S = a.nt - 1;
     float4* sA = reinterpret_cast<float4*>(smem_raw);
     float4* sBB = sA + Spad;
-    float* sH = reinterpret_cast<float*>(sBB + Spad / kTile);
+    float* sH = reinterpret_cast<float*>(sBB + Spad / kTileMin);
     float* sPx = sH + Spad;
     float* sPy = sPx + a.ws.ntg_pad;
     QEntry* queue = reinterpret_cast<QEntry*>(sPy + a.ws.nug_pad);
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
         const float4* gA = a.ws.A + (size_t)wl * Spad;
         const float* gH = a.ws.H + (size_t)wl * Spad;
         for (int i = tid; i < Spad; i += 256) { sA[i] = gA[i]; sH[i] = gH[i]; }
-        const float4* gBB = a.ws.bbox + (size_t)wl * (Spad / kTile);
-        for (int i = tid; i < Spad / kTile; i += 256) sBB[i] = gBB[i];
+        const float4* gBB = a.ws.bbox + (size_t)wl * (Spad / kTileMin);
+        for (int i = tid; i < Spad / T; i += 256) sBB[i] = gBB[i];
         const float* gx = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
         const float* gy = a.ws.pys + (size_t)wl * a.ws.nug_pad;
         for (int i = tid; i < a.ntg; i += 256) sPx[i] = gx[i];
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     }
     __syncthreads();
     const double2* pn = a.ws.pn + (size_t)wl * a.nt;
-    SegTable tb{sA, sH, sBB, S, Spad, hdr.nonmono == 0};
+    SegTable tb{sA, sH, sBB, S, Spad, T, hdr.nonmono == 0};
     const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(sPx[a.ntg - 1] - sPx[0]), fabsf(sPy[a.nug - 1] - sPy[0]));
     const int foot = blockIdx.x * 8 + (tid >> 5);     // one warp per footprint (warp-uniform)
     int zero_dist = 0, slow = 0, tiles = 0;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
         for (int r = 0; r < R; ++r) py[r] = sPy[min(rg * R + r, a.nug - 1)];
         float b1[2 * R], b2[2 * R], b3[2 * R];
         int t1[2 * R];
-        scan_block<R>(tb, lb.fp, sPx[it0], sPx[it1], py, b1, t1, b2, b3, tiles);
+        scan_block<R, T>(tb, lb.fp, sPx[it0], sPx[it1], py, b1, t1, b2, b3, tiles);
         if (lb.owns) {
         // The epilogue is deliberately NOT unrolled (FP64 division/exp per pixel would
         // multiply the code size by 2R); the scan results move to local arrays first.
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
             const double px = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, it, a.ntg);
             const double pyd = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, iu, a.nug);
             PixelHit hit;
-            if (!resolve_pixel(tb, pn, sPx[it], sPy[iu], px, pyd, kb1, lt1[k], lb2[k], lb3[k], hit)) {
+            if (!resolve_pixel<T>(tb, pn, sPx[it], sPy[iu], px, pyd, kb1, lt1[k], lb2[k], lb3[k], hit)) {
                 const int qi = atomicAdd(&qcount, 1);   // far-apart near-tie: all-segment rescan
                 if (qi < kQCap) { queue[qi] = QEntry{it, iu, kb1, 0.f}; continue; }
                 ++slow;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
         if (slow) atomicAdd(a.status + WFOT_STAT_SLOW_PIXELS, slow);
         if ((tid & 31) == 0 && tiles)
             atomicAdd(reinterpret_cast<unsigned long long*>(a.status + WFOT_STAT_SCAN_TILES),
-                      (unsigned long long)tiles * (R / 4));
+                      (unsigned long long)tiles * (R / 4) * (T / 8));
     }
 }
 
@@ -472,17 +473,20 @@ int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long
     if (chunk > kFpChunk) chunk = kFpChunk;
     FpWorkspace ws = fp_workspace_carve((void*)base, chunk, nt, nug, ntg);
     constexpr int R = 4;
-    const size_t smem = (size_t)ws.Spad * 21 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
+    const size_t smem = (size_t)ws.Spad * 20 + (size_t)(ws.Spad / kTileMin) * 16 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
     if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(k_fingerprint<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int T = tile_for(nt);
+    cudaError_t e = T == 8 ? cudaFuncSetAttribute(k_fingerprint<R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(k_fingerprint<R, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_fingerprint)");
     const int gx = (max_footprints<R>(ntg, nug) + 7) / 8;     // 8 warps = 8 footprints per CTA
     for (long long b0 = 0; b0 < B; b0 += chunk) {
         const int nb = (int)((B - b0) < chunk ? (B - b0) : chunk);
-        PrepArgs pa{t, w, in_dtype, t_stride, nt, grids, n_grids, b0, nug, ntg, 0, ws, pn, status};
+        PrepArgs pa{t, w, in_dtype, t_stride, nt, grids, n_grids, b0, nug, ntg, 0, ws, pn, status, T};
         k_prep<<<nb, 256, 0, stream>>>(pa);
         FpArgs fa{ws, nt, b0, nug, ntg, lambda, q, dfield, iray, lray, xray, pdf, dddy, status};
-        k_fingerprint<R><<<dim3(gx, nb), 256, smem, stream>>>(fa);
+        if (T == 8) k_fingerprint<R, 8><<<dim3(gx, nb), 256, smem, stream>>>(fa);
+        else k_fingerprint<R, 16><<<dim3(gx, nb), 256, smem, stream>>>(fa);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_fingerprint_batch launch");
