@@ -114,16 +114,10 @@ struct FusedArgs {
     int* const s_qcount = reinterpret_cast<int*>(smem_raw + (L).qcount)
 
 // pixel -> scratch: density and the two gradient weights of its nearest segment
-// (misfit-only calls need the density alone: no nearest point, no d(d)/dw, one store instead of four)
 __device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* pn, size_t slab,
                                             int it, int iu, const PixelHit& hit, double py, int& zero_dist) {
-    const size_t k = slab + (size_t)iu * a.ntg + it;
-    if (!a.grad) {
-        const double d = __dsqrt_rn(hit.D);                        // FingerprintLib.py:263
-        a.s_pdf[k] = (a.q == 2) ? exp(-(d * d) / a.lambda) : exp(-fabs(d) / a.lambda);   // :174,176
-        return;
-    }
     const PixelVals v = pixel_values(pn, hit, py, a.lambda, a.q);
+    const size_t k = slab + (size_t)iu * a.ntg + it;
     double wgt = v.pdf * v.g;                                  // pdf * dddx_y (FingerprintLib.py:355)
     if (a.q == 2) wgt *= 2.0 * fabs(v.d);                      // :214-217
     zero_dist += (v.d == 0.0);
