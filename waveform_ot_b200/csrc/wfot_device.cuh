@@ -365,22 +365,23 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
     }
     // thr2 = ((sqrt(wmax) + 4e-6) / (1 - 2e-6))^2: a tile whose squared box distance exceeds it cannot matter
     float thr2 = kBig;   // from wmax = max over the warp's pixels of b1 (warp-uniform), updated per evaluated tile
-    const int nsteps = 2 * max(ct, ntiles - 1 - ct) + 1;
-    bool ldone = false, rdone = false;   // time-ordered tables: nothing farther out on that side can matter
-    for (int step = 0; step < nsteps; ++step) {
-        const int dd = (step + 1) >> 1;
-        const bool right = (step & 1);
-        const int tile = right ? ct + dd : ct - dd;
-        if (right ? rdone : ldone) { if (ldone && rdone) break; continue; }
-        if (tile < 0) { ldone = true; continue; }
-        if (tile >= ntiles) { rdone = true; continue; }
+    // walk outwards from ct, alternating sides: r = next tile on the right (starts AT ct), l = next on the left;
+    // on a time-ordered table a side is closed (r = ntiles / l = -1) once the time gap alone exceeds the bound
+    int l = ct - 1, r = ct;
+    bool go_right = true;
+    while (l >= 0 || r < ntiles) {
+        const bool right = (r < ntiles) && (go_right || l < 0);
+        const int tile = right ? r : l;
+        r += right ? 1 : 0;
+        l -= right ? 0 : 1;
+        go_right = !right;
         {
             const float4 bb = tb.bbox[tile];
             const float dx = fmaxf(0.f, fmaxf(bb.x - fp.x1, fp.x0 - bb.y));
             const float dy = fmaxf(0.f, fmaxf(bb.z - fp.y1, fp.y0 - bb.w));
             const float dx2 = dx * dx;
             if (__fmaf_rn(dy, dy, dx2) > thr2) {
-                if (tb.mono && dx2 > thr2) { if (right) rdone = true; else ldone = true; }
+                if (tb.mono && dx2 > thr2) { if (right) r = ntiles; else l = -1; }
                 continue;
             }
         }
