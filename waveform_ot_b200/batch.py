@@ -256,9 +256,11 @@ def pixel_axes(pn, grids_dev, nug, ntg):
 
 def misfit_grad_batch(t, w, grids, nug, ntg, lambdav, target: Target, distfunc="W2", q=None,
                       tantheta=1.0, fpgrids=None, transform=False, want_grad=True, status=None,
-                      workspace=None):
+                      workspace=None, out=None):
     """Fused evaluation of B windows: returns W (B,2) [W^t, W^u], grad (B,2,nt), dwg (B,)
-    (dW^t/d(translation) in normalised time units).  Inputs may already be device tensors."""
+    (dW^t/d(translation) in normalised time units).  Inputs may already be device tensors.
+    `workspace` / `out` (a previous result dict) let a caller that streams batches of one shape
+    through the library re-use the scratch and result buffers instead of allocating per call."""
     dev = _device()
     w = _as_device(w)
     if w.dim() == 1:
@@ -269,9 +271,13 @@ def misfit_grad_batch(t, w, grids, nug, ntg, lambdav, target: Target, distfunc="
     g = grids if isinstance(grids, torch.Tensor) else pack_grids(grids, tantheta, fpgrids)
     pmask = {"W1": C.W1, "W2": C.W2}[distfunc]
     f64 = dict(dtype=torch.float64, device=dev)
-    W = torch.empty((B, 2), **f64)
-    grad = torch.empty((B, 2, nt), **f64) if want_grad else None
-    dwg = torch.empty(B, **f64)
+    if out is not None and out["W"].shape == (B, 2) and (not want_grad or (out.get("grad") is not None
+                                                                          and out["grad"].shape == (B, 2, nt))):
+        W, grad, dwg = out["W"], (out["grad"] if want_grad else None), out["dwg"]
+    else:
+        W = torch.empty((B, 2), **f64)
+        grad = torch.empty((B, 2, nt), **f64) if want_grad else None
+        dwg = torch.empty(B, **f64)
     wsb = C.lib.wfot_misfit_grad_workspace_bytes(B, nt, nug, ntg)
     ws = workspace if workspace is not None and workspace.numel() >= wsb else \
         torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -316,14 +322,16 @@ def ricker_batch(params, trange=(-2.0, 2.0), deriv=False):
     return dict(t=t, w=w, dw=dw, _keepalive=(params,))
 
 
-def sum_windows(x):
+def sum_windows(x, out=None, workspace=None):
     """Deterministic FP64 sum over the leading (window) axis of a device tensor (B, ...)."""
     dev = _device()
     x = x.contiguous()
     B = x.shape[0]
     Cn = x[0].numel()
-    out = torch.empty(x.shape[1:], dtype=torch.float64, device=dev)
+    if out is None:
+        out = torch.empty(x.shape[1:], dtype=torch.float64, device=dev)
     wsb = C.lib.wfot_sum_windows_workspace_bytes(Cn)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    ws = workspace if workspace is not None and workspace.numel() >= wsb else \
+        torch.empty(wsb, dtype=torch.uint8, device=dev)
     C.check(C.lib.wfot_sum_windows(C.ptr(x), B, Cn, C.ptr(out), C.ptr(ws), wsb, _stream()), "wfot_sum_windows")
     return out
