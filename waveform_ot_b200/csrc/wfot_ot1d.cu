@@ -46,6 +46,17 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// explicit shared-space accesses with 32-bit addresses (the merge loop's pointers otherwise drag generic ->
+// shared address arithmetic through every step)
+__device__ __forceinline__ double lds64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
 // x / d with r = RN(1/d): one multiply and a fused residual correction
 __device__ __forceinline__ double div_by(double x, double d, double r) {
     const double q = x * r;
@@ -334,8 +345,9 @@ struct Chain {
     // which is then the previous knot: v == tprev) and bisect_left(cg, v) is ib, i.e. x_f[indf], x_g[indg]
     // are the x of the two current heads, which travel with them in registers; the consumed side's next
     // (cdf, x) pair is fetched with one selected index.
-    __device__ __forceinline__ void step(const double* cf, const double* xf, int npad,
-                                         double* e1s, double* e2s, int32_t* mo, int n, int m, Acc& acc) {
+    // cfa / xfa / e1a / e2a: 32-bit shared-memory byte addresses of [cf | cg], [x_f | x_g] and the E arrays.
+    __device__ __forceinline__ void step(uint32_t cfa, uint32_t xfa, int npad,
+                                         uint32_t e1a, uint32_t e2a, int32_t* mo, int n, int m, Acc& acc) {
         const bool src = (va <= vb);              // source first on ties (stable argsort of [cf[:-1], cg], :668-669)
         const double v = src ? va : vb;
         bool tie;
@@ -343,7 +355,7 @@ struct Chain {
         if (STRICT) {
             tie = !src && ia > 0 && (v == tprev);
             double xs = xa;
-            if (tie) xs = xf[ia - 1];                            // rare: predicated load
+            if (tie) xs = lds64(xfa + 8u * (unsigned)(ia - 1));  // rare: predicated load
             dx = xs - xb;                                        // :671-672,676-677
         } else {
             tie = !src && (v == runf_val);        // target knot equal to the last consumed source knot
@@ -355,14 +367,15 @@ struct Chain {
             rung_len = src ? rung_len : eqg + 1;
             rung_val = src ? rung_val : v;
             runf_val = src ? v : runf_val;
-            dx = xf[indf] - xf[npad + indg];                     // :676-677
+            dx = lds64(xfa + 8u * (unsigned)indf) - lds64(xfa + 8u * (unsigned)(npad + indg));   // :676-677
         }
         // next head of the consumed side (index into the contiguous [cf | cg] / [x_f | x_g] arrays)
         const int nxt = src ? ia + 1 : npad + ib + 1;
         const bool inr = src ? (ia + 1 < ia1) : (ib + 1 < ib1);
-        const double nv = inr ? cf[nxt] : CUDART_INF;
+        double nv = CUDART_INF;
+        if (inr) nv = lds64(cfa + 8u * (unsigned)nxt);
         double nx = 0.0;
-        if (STRICT) nx = xf[src ? min(ia + 1, n - 1) : npad + min(ib + 1, m - 1)];
+        if (STRICT) nx = lds64(xfa + 8u * (unsigned)(src ? min(ia + 1, n - 1) : npad + min(ib + 1, m - 1)));
         acc.common += (tie && ib < m - 1) ? 1 : 0;               // np.intersect1d(cg[:-1], cf[:-1]) (:664)
         if (MO) { mo[k] = src ? ia : n - 1 + ib; ++k; }
         const double dt = v - tprev;                             // :673
@@ -383,8 +396,8 @@ struct Chain {
         if (E1 || E2) {
             const double D1 = pc1 - c1, D2 = pc2 - c2;
             if (pj >= 0) {
-                if (E1) e1s[pj] = D1;
-                if (E2) e2s[pj] = D2;
+                if (E1) sts64(e1a + 8u * (unsigned)pj, D1);
+                if (E2) sts64(e2a + 8u * (unsigned)pj, D2);
             }
             if (E1) acc.z1 = fma(pcf, D1, acc.z1);
             if (E2) acc.z2 = fma(pcf, D2, acc.z2);
@@ -403,11 +416,11 @@ struct Chain {
     }
 
     // the chain's last knot, if a source knot, needs the first |dx|^p of the NEXT knot (0 past the end)
-    __device__ __forceinline__ void finish(double* e1s, double* e2s, double nc1, double nc2, Acc& acc) {
+    __device__ __forceinline__ void finish(uint32_t e1a, uint32_t e2a, double nc1, double nc2, Acc& acc) {
         if ((E1 || E2) && pj >= 0) {
             const double D1 = pc1 - nc1, D2 = pc2 - nc2;
-            if (E1) { e1s[pj] = D1; acc.z1 = fma(pcf, D1, acc.z1); }
-            if (E2) { e2s[pj] = D2; acc.z2 = fma(pcf, D2, acc.z2); }
+            if (E1) { sts64(e1a + 8u * (unsigned)pj, D1); acc.z1 = fma(pcf, D1, acc.z1); }
+            if (E2) { sts64(e2a + 8u * (unsigned)pj, D2); acc.z2 = fma(pcf, D2, acc.z2); }
         }
     }
 };
@@ -439,17 +452,21 @@ __device__ __forceinline__ void warp_merge(const double* cf, const double* xf, i
     B.init(cf, xf, npad, dB, iaB, iaE, dB - iaB, dE - iaE);
     __syncwarp();                                 // all look-back / split reads done before any lane parks an E_j
     const int lenA = dB - dA, lenB = dE - dB;     // lenB <= lenA
+    const uint32_t cfa = (uint32_t)__cvta_generic_to_shared(cf), xfa = (uint32_t)__cvta_generic_to_shared(xf);
+    const uint32_t e1a = E1 ? (uint32_t)__cvta_generic_to_shared(e1s) : 0u;
+    const uint32_t e2a = E2 ? (uint32_t)__cvta_generic_to_shared(e2s) : 0u;
     int i = 0;
+#pragma unroll 2
     for (; i < lenB; ++i) {
-        A.step(cf, xf, npad, e1s, e2s, mo, n, m, acc);
-        B.step(cf, xf, npad, e1s, e2s, mo, n, m, acc);
+        A.step(cfa, xfa, npad, e1a, e2a, mo, n, m, acc);
+        B.step(cfa, xfa, npad, e1a, e2a, mo, n, m, acc);
     }
-    for (; i < lenA; ++i) A.step(cf, xf, npad, e1s, e2s, mo, n, m, acc);
+    for (; i < lenA; ++i) A.step(cfa, xfa, npad, e1a, e2a, mo, n, m, acc);
     if (E1 || E2) {
         double nc1 = __shfl_down_sync(kFull, A.first_c1, 1), nc2 = __shfl_down_sync(kFull, A.first_c2, 1);
         if (lane == 31) { nc1 = 0.0; nc2 = 0.0; }
-        A.finish(e1s, e2s, B.first_c1, B.first_c2, acc);      // an empty chain has first_c = 0 = |dx|^p past the end
-        B.finish(e1s, e2s, nc1, nc2, acc);
+        A.finish(e1a, e2a, B.first_c1, B.first_c2, acc);      // an empty chain has first_c = 0 = |dx|^p past the end
+        B.finish(e1a, e2a, nc1, nc2, acc);
     }
 }
 
