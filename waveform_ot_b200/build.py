@@ -26,17 +26,32 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile every translation unit in parallel (nvcc -c), then link libwfot.so."""
     if not force and not needs_build():
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    from concurrent.futures import ThreadPoolExecutor
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + (["-Xptxas", "-v"] if verbose else [])
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-shared", "-o", LIB] + srcs + ["-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in srcs]
+
+    def cc(args):
+        src, obj = args
+        return subprocess.run([_nvcc()] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        results = list(ex.map(cc, zip(srcs, objs)))
+    for r in results:
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+    if any(r.returncode != 0 for r in results):
+        raise RuntimeError("nvcc failed building libwfot.so")
+    r = subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libwfot.so")
+        raise RuntimeError("nvcc failed linking libwfot.so")
     return LIB
 
 
