@@ -3,7 +3,8 @@ usage: prof_fp.py <windows> <fp|fused|both> [cfg5|cfg1|cfg4]"""
 import sys
 import torch
 sys.path.insert(0, ".")
-from oracle import wfot_oracle as O
+sys.path.insert(0, "scripts")
+import _inputs as O
 from waveform_ot_b200 import batch as B
 
 SHAPES = {"cfg5": (1024, 256, 256, 0.04), "cfg1": (256, 80, 512, 0.03), "cfg4": (61, 79, 61, 0.04)}

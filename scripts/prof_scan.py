@@ -1,6 +1,7 @@
 import sys, torch
 sys.path.insert(0, ".")
-from oracle import wfot_oracle as O
+sys.path.insert(0, "scripts")
+import _inputs as O
 from waveform_ot_b200 import _cabi as C, batch as B
 nt, nug, ntg = 1024, 256, 256
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 296

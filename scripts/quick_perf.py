@@ -7,7 +7,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from oracle import wfot_oracle as O
+sys.path.insert(0, "scripts")
+import _inputs as O
 from waveform_ot_b200 import _cabi as C
 from waveform_ot_b200 import batch as B
 
