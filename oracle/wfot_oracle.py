@@ -319,7 +319,7 @@ def merge_cdfs(cf, cg):
 
 
 def wasser(source: Pdf, target: Pdf, distfunc="W12", derivatives=False,
-           checkCommonCDF=False, ignoreCommonCDFerror=False, return_merge=False):
+           checkCommonCDF=False, ignoreCommonCDFerror=False, return_merge=False, returnplan=False):
     """W_p^p (p=1,2), d/d(un-normalised source amplitudes), d/d(translation);
     libs/OTlib.py:643-706.  Output list order as the reference's (:688-706)."""
     if not isinstance(distfunc, str):
@@ -353,8 +353,53 @@ def wasser(source: Pdf, target: Pdf, distfunc="W12", derivatives=False,
         if derivatives:
             out.append(np.dot(Diffdtk, dsq))
             out.append(np.dot(2.0 * (xft - xgt), dtk))
+    if returnplan:                                                # :718-740 (memory=True form)
+        H = np.zeros((n, target.n))
+        np.add.at(H, (indf, indg), dtk)
+        out.append(H)
+        if derivatives:
+            dH = np.zeros((n, n, target.n))
+            for j in range(len(dtk)):
+                dH[:, indf[j], indg[j]] += Diffdtk[:, j]
+            out.append(dH)
     if return_merge:
         return out, (tkarg, indf, indg)
+    return out
+
+
+def set_sliced(P: Pdf, Nproj, org):
+    """libs/OTlib.py:119-144: projections of the 2-D point masses onto Nproj directions about `org`."""
+    if P.type != "2D":
+        raise TargetSource2DShapeError()
+    f = P.pdf.reshape((P.n))
+    theta = np.linspace(0.1745, np.pi, Nproj + 1)[:-1]            # :132-133
+    r = np.array([np.cos(theta), np.sin(theta)])
+    a = (P.x - org).reshape((P.n, 2))                             # :135-136
+    fxp = np.dot(a, r).T                                          # :137
+    order = np.argsort(fxp)                                       # :138
+    P.proj = [otpdf(f[order[i]], fxp[i][order[i]]) for i in range(Nproj)]   # :139
+    P.angles, P.psorted, P.nproj = theta, order, Nproj
+    return P
+
+
+def sliced_wasserstein(source: Pdf, target: Pdf, Nproj, distfunc="W2", derivatives=False, origin=(0.5, 0.5)):
+    """libs/OTlib.py:1156-1318 with returnplan=False, calcWplan=False, calcAvgW=True:
+    [wsliced] or [wsliced, dwsliced (nx, ny)]."""
+    origin = np.asarray(origin, dtype=np.float64)
+    set_sliced(source, Nproj, origin)                             # :1209-1212
+    set_sliced(target, Nproj, origin)
+    dwp = np.zeros(source.n)
+    wp = 0.0
+    for i in range(Nproj):                                        # :1237-1291
+        wout = wasser(source.proj[i], target.proj[i], distfunc, derivatives=derivatives, checkCommonCDF=True)
+        wp += wout[0]
+        if derivatives:
+            dwp[source.psorted[i]] += wout[1]                     # :1280
+    out = [wp / Nproj]                                            # :1306
+    if derivatives:
+        dwp -= np.dot(dwp, source.pdf.reshape(source.n))          # :1308-1310
+        dwp /= source.amp
+        out.append(dwp.reshape((source.nx, source.ny)) / Nproj)
     return out
 
 

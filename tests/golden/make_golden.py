@@ -153,6 +153,31 @@ def main():
                         X=X, F=np.array(F), G=np.array(G))
     print("ricker_forward", np.array(F), np.array(G)[0])
 
+    # ---- (7) sliced Wasserstein (libs/OTlib.py:119-144,1156-1318) and the transport plan of wasser (:718-740)
+    rng = np.random.default_rng(314)
+    nx, ny = 7, 9
+    X, Y = np.meshgrid(np.linspace(0, 1, ny), np.linspace(0, 1, nx))
+    pos = np.stack([X, Y], axis=-1)
+    f = rng.random((nx, ny)) + 0.05
+    g = rng.random((nx, ny)) + 0.05
+    out = {}
+    for d in ("W1", "W2"):
+        s, t = OT.OTpdf((f, pos)), OT.OTpdf((g, pos))
+        r = OT.SlicedWasserstein(s, t, 6, distfunc=d, derivatives=True)
+        out["sw_" + d], out["dsw_" + d] = r[0], r[1]
+    s, t = OT.OTpdf((f, pos)), OT.OTpdf((g, pos))
+    out["sw_noderiv"] = OT.SlicedWasserstein(s, t, 4, distfunc="W2")[0]
+    fx, gx = np.linspace(3, 14, 6), np.linspace(7, 18, 6)
+    f1 = np.array([.2, .01, .18, .21, .2, .2])
+    g1 = np.array([.18, .07, .2, .05, .27, .23])
+    s1, t1 = OT.OTpdf((f1, fx)), OT.OTpdf((g1, gx))
+    w = OT.wasser(s1, t1, 'W2', returnplan=True, derivatives=True)
+    out.update(plan_f=f1, plan_g=g1, plan_fx=fx, plan_gx=gx, plan_W2=w[0], plan_dW2=w[1], plan_dpos=w[2],
+               plan_H=w[3], plan_dH=w[4])
+    w2 = OT.wasser(s1, t1, 'W1', returnplan=True)
+    out.update(plan_W1=w2[0], plan_H_nod=w2[1])
+    np.savez_compressed(os.path.join(HERE, "sliced_plan.npz"), f=f, g=g, pos=pos, **out)
+
 
 if __name__ == "__main__":
     main()

@@ -46,7 +46,7 @@ def test_point_mass_demo(mods):
     with pytest.raises(OT.PDFShapeError):
         OT.OTpdf((f, fx[:5]))
     with pytest.raises(NotImplementedError):
-        OT.wasser(source, target, returnplan=True)
+        OT.wasser(source, target, distfunc=np.ones((6, 6)))
 
 
 @pytest.mark.parametrize("case", ["small_q1", "small_q2", "small_theta", "small_fpgrid", "ricker_cfg1"])
@@ -206,3 +206,38 @@ def test_misfit_surface_vs_oracle(mods):
             w2 = O.marg_wasserstein(src, tgt, "W2", returnmargW=True)[0]
             np.testing.assert_allclose(W1[i, j], w1, rtol=1e-9)
             np.testing.assert_allclose(W2[i, j], w2, rtol=1e-9)
+
+
+def test_sliced_wasserstein_golden(mods, golden):
+    """OT.SlicedWasserstein (libs/OTlib.py:119-144,1156-1318): all slices through one batched 1-D OT launch."""
+    _, OT, _ = mods
+    g = golden("sliced_plan")
+    for d in ("W1", "W2"):
+        s, t = OT.OTpdf((g["f"], g["pos"])), OT.OTpdf((g["g"], g["pos"]))
+        r = OT.SlicedWasserstein(s, t, 6, distfunc=d, derivatives=True)
+        assert len(r) == 2 and r[1].shape == g["f"].shape
+        assert r[0] == pytest.approx(float(g["sw_" + d]), rel=1e-11)
+        np.testing.assert_allclose(r[1], g["dsw_" + d], rtol=1e-8, atol=1e-13)
+        assert len(s.proj) == 6 and s.proj[0].n == g["f"].size and s.psorted.shape == (6, g["f"].size)
+    s, t = OT.OTpdf((g["f"], g["pos"])), OT.OTpdf((g["g"], g["pos"]))
+    assert OT.SlicedWasserstein(s, t, 4, distfunc="W2")[0] == pytest.approx(float(g["sw_noderiv"]), rel=1e-11)
+    with pytest.raises(NotImplementedError):
+        OT.SlicedWasserstein(s, t, 4, returnplan=True)
+    pickle.loads(pickle.dumps(s))                       # stays picklable after setSliced
+
+
+def test_transport_plan_golden(mods, golden):
+    """wasser(returnplan=True) (libs/OTlib.py:718-740): plan and its amplitude derivative."""
+    _, OT, _ = mods
+    g = golden("sliced_plan")
+    s, t = OT.OTpdf((g["plan_f"], g["plan_fx"])), OT.OTpdf((g["plan_g"], g["plan_gx"]))
+    w = OT.wasser(s, t, 'W2', returnplan=True, derivatives=True)
+    assert len(w) == 5
+    assert w[0] == pytest.approx(float(g["plan_W2"]), rel=1e-12)
+    np.testing.assert_allclose(w[1], g["plan_dW2"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(w[3], g["plan_H"], atol=1e-15)
+    np.testing.assert_allclose(w[4], g["plan_dH"], atol=1e-13)
+    w = OT.wasser(s, t, 'W1', returnplan=True)
+    assert len(w) == 2 and w[0] == pytest.approx(float(g["plan_W1"]), rel=1e-12)
+    np.testing.assert_allclose(w[1], g["plan_H_nod"], atol=1e-15)
+    assert w[1].sum() == pytest.approx(1.0, abs=1e-14)

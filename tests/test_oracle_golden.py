@@ -158,3 +158,16 @@ def test_ricker_forward_and_optfunc_fixture(golden):
     f_, g_ = O.ricker_optfunc(g["X"][0], tg, "W2", (-2.0, 2.0), grid, float(g["lam"]), float(g["alpha"]))
     assert f_ == pytest.approx(float(g["F"][0]), rel=1e-12)
     np.testing.assert_allclose(g_, g["G"][0], rtol=1e-10, atol=1e-14)
+
+
+def test_sliced_wasserstein_and_plan_fixture(golden):
+    """Sliced Wasserstein (libs/OTlib.py:119-144,1156-1318) and the transport plan of wasser (:718-740)."""
+    g = golden("sliced_plan")
+    for d in ("W1", "W2"):
+        r = O.sliced_wasserstein(O.otpdf(g["f"], g["pos"]), O.otpdf(g["g"], g["pos"]), 6, d, derivatives=True)
+        assert r[0] == pytest.approx(float(g["sw_" + d]), rel=1e-13)
+        np.testing.assert_allclose(r[1], g["dsw_" + d], rtol=1e-11, atol=1e-15)
+    w = O.wasser(O.otpdf(g["plan_f"], g["plan_fx"]), O.otpdf(g["plan_g"], g["plan_gx"]), "W2", derivatives=True,
+                 returnplan=True)
+    np.testing.assert_allclose(w[3], g["plan_H"], atol=1e-15)
+    np.testing.assert_allclose(w[4], g["plan_dH"], atol=1e-14)

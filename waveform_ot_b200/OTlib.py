@@ -4,9 +4,13 @@ reference's signatures, return-list layouts and exception classes
 (libs/OTlib.py:34-75, 82-163, 596-716, 1055-1154); the arithmetic runs in
 libwfot.so on the GPU.
 
-Out of scope (NotImplementedError): transport plans (``returnplan``), user
-supplied cost matrices (``distfunc`` as ndarray/tuple), sliced Wasserstein,
-LP / Sinkhorn / POT cross-checks, barycentres, plotting.
+Also provided (diagnostics rather than the inversion
+hot loop): ``OTpdf.setSliced`` / ``SlicedWasserstein`` (all slices in ONE
+batched 1-D OT launch) and the transport plan of ``wasser(returnplan=True)``.
+
+Out of scope (NotImplementedError): user supplied cost matrices (``distfunc``
+as ndarray/tuple), plans averaged over slices (``SlicedWasserstein(returnplan /
+calcWplan)``), LP / Sinkhorn / POT cross-checks, barycentres, plotting.
 """
 from __future__ import annotations
 
@@ -129,7 +133,32 @@ class OTpdf(object):
         return self._cdf
 
     def setSliced(self, Nproj, org):
-        raise NotImplementedError("waveform_ot_b200: sliced Wasserstein is out of scope (SURVEY section 2 #13)")
+        """libs/OTlib.py:119-144: projections of the 2-D point masses onto Nproj directions about `org`.
+        The projection and its argsort are host NumPy exactly as in the reference (the order of nearly equal
+        projected positions must be the reference's); the per-slice OTpdf objects of `self.proj` are built
+        lazily because SlicedWasserstein() feeds the sorted slices to one batched kernel launch."""
+        if self.type != '2D':
+            raise TargetSource2DShapeError
+        self.nproj = Nproj
+        self.origin = org
+        f = self.pdf.reshape((self.n))                                # :130
+        theta = np.linspace(0.1745, np.pi, Nproj + 1)[:-1]            # :131-132
+        r = np.array([np.cos(theta), np.sin(theta)])
+        a = (self.x - org).reshape((self.n, 2))                       # :134-135
+        fxp = np.dot(a, r).T                                          # :136
+        fxpargsort = np.argsort(fxp)                                  # :137
+        self._slice_f = np.take_along_axis(np.broadcast_to(f, fxp.shape), fxpargsort, axis=1)
+        self._slice_x = np.take_along_axis(fxp, fxpargsort, axis=1)
+        self._proj = None
+        self.angles = theta
+        self.psorted = fxpargsort
+        self.calcproj = False
+
+    @property
+    def proj(self):
+        if getattr(self, "_proj", None) is None:                      # :138 (one OTpdf per projection)
+            self._proj = [OTpdf((self._slice_f[i], self._slice_x[i])) for i in range(self.nproj)]
+        return self._proj
 
     def setMarginals(self):
         """libs/OTlib.py:146-163."""
@@ -145,6 +174,7 @@ class OTpdf(object):
     def __getstate__(self):
         st = dict(self.__dict__)
         st.pop("_marg_dev", None)
+        st["_proj"] = None
         st["_raw_dev"] = None
         return st
 
@@ -165,8 +195,6 @@ def wasser(source, target, distfunc='W12', proj=-1, returnplan=False, derivative
     amplitudes and source translation; libs/OTlib.py:596-716.  Return list as the reference:
     [W1, dW1, dW1_pos, W2, dW2, dW2_pos] restricted to the requested entries."""
     calcW1, calcW2 = _checkdistfunc(distfunc)
-    if returnplan:
-        raise NotImplementedError("waveform_ot_b200: transport plans are out of scope (SURVEY section 2 #11)")
     if source.type != '1D' or target.type != '1D':
         raise NotImplementedError("waveform_ot_b200: wasser() takes 1-D OTpdf objects")
     if derivatives and source.n != target.n:
@@ -174,7 +202,8 @@ def wasser(source, target, distfunc='W12', proj=-1, returnplan=False, derivative
         raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,) "
                          % (source.n, target.n, source.n))
     name = 'W12' if (calcW1 and calcW2) else ('W1' if calcW1 else 'W2')
-    r = _B.ot1d_batch(source._raw, target._raw, source.x, target.x, name, derivatives=derivatives)
+    r = _B.ot1d_batch(source._raw, target._raw, source.x, target.x, name, derivatives=derivatives,
+                      want_cdf=returnplan, want_merge=returnplan)
     _sync()
     st = r["status"].read()
     if (derivatives or checkCommonCDF) and st[1] and not ignoreCommonCDFerror:      # :663-666
@@ -190,6 +219,90 @@ def wasser(source, target, distfunc='W12', proj=-1, returnplan=False, derivative
         out += [W[1]]
         if derivatives:
             out += [r["dW2"][0].cpu().numpy(), r["dpos"][0, 1].item()]
+    if returnplan:
+        out += _transport_plan(r, source, target, derivatives)
+    return out
+
+
+def _transport_plan(r, source, target, derivatives):
+    """Optimal plan H and (with derivatives) dH/d(un-normalised source amplitudes); libs/OTlib.py:718-740.
+    Built on the device from the kernel's CDFs and merge order with torch index arithmetic: a diagnostic
+    output whose size (n x m, n x n x m) is its cost, not part of the inversion hot loop."""
+    import torch
+    n, m = source.n, target.n
+    cf, cg, order = r["cdf_f"][0], r["cdf_g"][0], r["merge_order"][0].long()
+    a = torch.cat([cf[:-1], cg])                                   # :668
+    tk = a[order]                                                  # :670
+    indf = torch.searchsorted(cf, tk, right=False)                 # bisect_left (:671-672)
+    indg = torch.searchsorted(cg, tk, right=False)
+    dtk = torch.cat([tk[:1], tk[1:] - tk[:-1]])                    # :673
+    H = torch.zeros((n, m), dtype=torch.float64, device=cf.device)
+    H.index_put_((indf, indg), dtk, accumulate=True)               # :720-723
+    out = [H.cpu().numpy()]
+    if derivatives:
+        Bm = torch.triu(torch.ones((n, m), dtype=torch.float64, device=cf.device))     # :682-686
+        Cm = (Bm - cf) / float(r["amp"][0])
+        D = torch.cat([Cm[:, :-1], torch.zeros((n, m), dtype=torch.float64, device=cf.device)], dim=1)
+        Difftk = D[:, order]
+        Diffdtk = torch.cat([Difftk[:, :1], Difftk[:, 1:] - Difftk[:, :-1]], dim=1)
+        dH = torch.zeros((n, n * m), dtype=torch.float64, device=cf.device)
+        dH.index_add_(1, indf * m + indg, Diffdtk)                  # :731-733
+        out += [dH.reshape(n, n, m).cpu().numpy()]
+    return out
+
+
+def SlicedWasserstein(source, target, Nproj, distfunc='W2', derivatives=False, returnplan=False, verbose=False,
+                      returnProjpoints=False, calcWplan=False, calcAvgW=True, origin=[0.5, 0.5], memory=False):
+    """Sliced Wasserstein distance between two 2-D PDFs; libs/OTlib.py:1156-1318.  All Nproj 1-D problems
+    (every pixel is a point mass: n = nx*ny knots per slice) go through ONE batched launch of the 1-D OT
+    kernel.  Returns [wsliced] or [wsliced, dwsliced (nx, ny)] (+ projected points with returnProjpoints)."""
+    import torch
+    if source.type != '2D':
+        raise TargetSource2DShapeError
+    if target.type != '2D':
+        raise TargetSource2DShapeError
+    if returnplan or calcWplan:
+        raise NotImplementedError("waveform_ot_b200: slice-averaged transport plans are not provided")
+    calcW1, calcW2 = _checkdistfunc(distfunc)
+    if calcW1 and calcW2:
+        raise SlicedWassersteinError("distfunc must be 'W1' or 'W2'")
+    if derivatives and source.n != target.n:
+        raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,) "
+                         % (source.n, target.n, source.n))
+    origin = np.asarray(origin, dtype=np.float64)
+    if source.calcproj or source.nproj != Nproj:
+        source.setSliced(Nproj, origin)                               # :1209-1210
+    if target.calcproj or target.nproj != Nproj:
+        target.setSliced(Nproj, origin)
+    r = _B.ot1d_batch(source._slice_f, target._slice_f, source._slice_x, target._slice_x, distfunc,
+                      derivatives=derivatives)
+    _sync()
+    st = r["status"].read()
+    if st[1]:                                                         # wasser(..., checkCommonCDF=True) (:1266-1270)
+        raise TargetSourceCDFError([])
+    k = 0 if calcW1 else 1
+    wp = float(r["W"][:, k].sum())                                    # :1288
+    out = []
+    if calcAvgW:
+        out += [wp / Nproj]                                           # :1306
+        if derivatives:
+            dw = r["dW1"] if calcW1 else r["dW2"]                     # (Nproj, n), slice order
+            dwp = torch.zeros(source.n, dtype=torch.float64, device=dw.device)
+            dwp.index_add_(0, torch.from_numpy(source.psorted.reshape(-1)).to(dw.device), dw.reshape(-1))   # :1280
+            dwp = dwp.cpu().numpy()
+            dwp -= np.dot(dwp, source.pdf.reshape(source.n))          # :1308-1310
+            dwp /= source.amp
+            out += [dwp.reshape((source.nx, source.ny)) / Nproj]
+    if returnProjpoints:                                              # :1219-1229
+        theta = source.angles
+        fproj = np.zeros((Nproj, 2, source.n))
+        gproj = np.zeros((Nproj, 2, target.n))
+        for i in range(Nproj):
+            fproj[i, 0] = origin[0] + source._slice_x[i] * np.cos(theta[i])
+            fproj[i, 1] = origin[1] + source._slice_x[i] * np.sin(theta[i])
+            gproj[i, 0] = origin[0] + target._slice_x[i] * np.cos(theta[i])
+            gproj[i, 1] = origin[1] + target._slice_x[i] * np.sin(theta[i])
+        out += [fproj] + [gproj]
     return out
 
 
