@@ -444,3 +444,36 @@ def test_ot1d_empty_bins_and_unequal_lengths(B):
     np.testing.assert_allclose(r["dW1"][0].cpu().numpy()[pos], out[1][pos], rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(r["dW2"][0].cpu().numpy()[pos], out[4][pos], rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(r["dpos"][0].cpu().numpy(), [out[2], out[5]], rtol=1e-12, atol=1e-14)
+
+
+def test_fused_gradient_vs_finite_differences(B):
+    """Oracle-independent check in the spirit of the reference's ru.check_dwduFD (libs/ricker_util.py:554-580):
+    central finite differences of the fused misfit w.r.t. single waveform samples and w.r.t. a time shift
+    against the analytic gradient / window-position derivative."""
+    rng = np.random.default_rng(2)
+    nt, nug, ntg, lam = 120, 64, 96, 0.05
+    t = np.linspace(0.0, 2.0, nt)
+    wo = np.sin(3 * t) * np.exp(-((t - 1.0) ** 2)) + 0.05 * rng.standard_normal(nt).cumsum()
+    wp = 0.8 * np.sin(3 * (t - 0.15)) * np.exp(-((t - 1.1) ** 2))
+    grid = (0.0, 2.0, -1.5, 1.5, nug, ntg)
+    tg = B.Target.from_waveform(t, wo, grid, nug, ntg, lam)
+    r = B.misfit_grad_batch(t, wp, grid, nug, ntg, lam, tg, distfunc="W2")
+    grad = r["grad"][0].cpu().numpy()                     # (2, nt)
+    dwg = float(r["dwg"][0])
+    h = 1e-6
+    js = [7, 33, 60, 61, 95, 110]
+    pert = np.repeat(wp[None], 2 * len(js), axis=0)
+    for k, j in enumerate(js):
+        pert[2 * k, j] += h
+        pert[2 * k + 1, j] -= h
+    W = B.misfit_grad_batch(t, pert, grid, nug, ntg, lam, tg, distfunc="W2", want_grad=False)["W"].cpu().numpy()
+    scale = np.abs(grad).max(axis=1)
+    for k, j in enumerate(js):
+        fd = (W[2 * k] - W[2 * k + 1]) / (2 * h)          # [dW^t/dw_j, dW^u/dw_j]
+        np.testing.assert_allclose(fd, grad[:, j], rtol=1e-5, atol=1e-6 * float(scale.max()))
+    # window position: shifting the waveform in time by dt moves the normalised window by dt/(t1 - t0)
+    ht = 1e-6
+    Ws = B.misfit_grad_batch(np.stack([t + ht, t - ht]), np.stack([wp, wp]), grid, nug, ntg, lam, tg,
+                             distfunc="W2", want_grad=False)["W"].cpu().numpy()
+    fd_t = (Ws[0, 0] - Ws[1, 0]) / (2 * ht)
+    assert fd_t == pytest.approx(dwg / (grid[1] - grid[0]), rel=1e-5, abs=1e-10)
