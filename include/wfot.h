@@ -86,9 +86,10 @@ int wfot_device_cc(void);
 /* ---- fingerprint (materialising path) ------------------------------------
  * Replaces waveformFP.__init__ + calcpdf(method='Enumerate') + wdist +
  * wdistderiv: libs/FingerprintLib.py:53-115, 117-177, 230-269, 333-385.
- * FP32 brute-force argmin over all segments, exact FP64 re-evaluation (in the
- * reference's operation order) of every near-minimal candidate, so `iray`
- * equals the reference's np.argmin first-minimum index.
+ * FP32 argmin over the segments with exact pruning of segment tiles that cannot
+ * hold the minimum, then exact FP64 re-evaluation (in the reference's operation
+ * order) of every near-minimal candidate, so `iray` equals the reference's
+ * np.argmin first-minimum index and dfield / lray / xray are bit-identical.
  * Any output pointer may be NULL (not materialised).  Outputs are FP64:
  *   pn     (B, nt, 2)   normalised sample coordinates            (:110)
  *   dfield (B, nug, ntg) nearest distance                        (:265)
