@@ -4,16 +4,17 @@
 //
 // One CTA owns one window at a time (grid = resident CTAs, windows strided):
 //   P0  prep_window            FP64 normalisation + FP32 segment table -> shared memory
-//   P1  scan_block + resolve   nearest segment per pixel (FP32 brute force, FP64 exact
-//                              tie resolution); per pixel {iray, pdf, wa, wb} go to a
-//                              per-CTA scratch slab (28 B/pixel, L2-resident, re-used
-//                              for every window the CTA processes)
+//   P1  scan_block + resolve   nearest segment per pixel (FP32 scan with exact tile pruning over
+//                              warp footprints drawn from a shared counter, FP64 exact tie
+//                              resolution); per pixel {iray, pdf, wa, wb} go to a per-CTA
+//                              scratch slab (28 B/pixel, re-used for every window of the CTA)
 //   P2  marginals              fixed-order column / row sums of pdf -> time / amplitude
 //                              marginals of the normalised density (OTlib.py:92-93,155-156)
 //   P3  block_ot1d x 2         CDF scan, merge, W_p^p, dW/df, dW/dx0 per marginal
 //                              (OTlib.py:596-706) and <dW, pbar> (OTlib.py:1141,1144-1145)
 //   P4  gradient assembly      sum_k pdf_k (R_k - Rbar)/A dd_k/dw_j keyed by iray
-//                              (FingerprintLib.py:205-228), run-combined per pixel column
+//                              (FingerprintLib.py:205-228), run-combined per pixel column,
+//                              accumulated with FP64 reductions in L2
 // Reference chain replaced: ricker_util.py:386-388 (BuildOTobjfromWaveform ->
 // CalcWasserWaveform(deriv=True, returnmarg=True)).
 #include <cuda_runtime.h>
