@@ -477,3 +477,39 @@ def test_fused_gradient_vs_finite_differences(B):
                              distfunc="W2", want_grad=False)["W"].cpu().numpy()
     fd_t = (Ws[0, 0] - Ws[1, 0]) / (2 * ht)
     assert fd_t == pytest.approx(dwg / (grid[1] - grid[0]), rel=1e-5, abs=1e-10)
+
+
+def test_fingerprint_random_shapes_stress(B):
+    """30 random windows (2..420 samples, grids of 1..140 points per axis, non-uniform / uniform sampling,
+    plateaus, fpgrid, theta != 45 deg): indices, distances and segment parameters bit-exact against the oracle."""
+    rng = np.random.default_rng(12345)
+    done = 0
+    while done < 30:
+        nt = int(rng.integers(2, 420)); nug = int(rng.integers(1, 140)); ntg = int(rng.integers(1, 140))
+        kind = rng.integers(0, 4)
+        t = np.sort(rng.random(nt)) * rng.uniform(0.5, 20) + rng.uniform(-5, 5)
+        if kind == 1:
+            t = np.linspace(t[0], t[-1] + 1e-3, nt)
+        w = rng.standard_normal(nt).cumsum() * rng.uniform(0.01, 3.0)
+        if kind == 2:
+            w = np.round(w, 1)                                   # plateaus / repeated values
+        if kind == 3:
+            w = np.abs(np.sin(np.linspace(0, 9, nt))) * 2
+        if np.any(np.diff(t) == 0):
+            continue
+        lo, hi = w.min(), w.max()
+        if hi == lo:
+            hi = lo + 1.0
+        grid = (float(t[0]) - rng.uniform(0, 1), float(t[-1]) + rng.uniform(0, 1),
+                float(lo - rng.uniform(0, 1) * (hi - lo)), float(hi + rng.uniform(0, 1) * (hi - lo)), nug, ntg)
+        fpgrid = (grid[0] + 0.1, grid[1] + 0.5, grid[2] - 0.2, grid[3] + 0.1) if rng.random() < 0.25 else None
+        theta = 45.0 if rng.random() < 0.7 else float(rng.uniform(20, 70))
+        _, tant = O.resolve_theta(theta, 1.0)
+        out = B.fingerprint_batch(t, w, grid, nug, ntg, 0.05, tantheta=tant, fpgrids=fpgrid, deriv=False)
+        torch.cuda.synchronize()
+        win = O.make_window(t, w, grid, fpgrid=fpgrid, theta=theta)
+        O.calcpdf(win, lambdav=0.05)
+        np.testing.assert_array_equal(out["iray"][0].cpu().numpy().astype(np.int64), win.irays)
+        np.testing.assert_array_equal(out["dfield"][0].cpu().numpy(), win.dfield)
+        np.testing.assert_array_equal(out["lray"][0].cpu().numpy(), win.lrays)
+        done += 1
