@@ -272,6 +272,16 @@ def secondary_configs(dev):
     dt3 = time.perf_counter() - t0
     out["cfg3_surface_512x512_W1_and_W2"] = {"models": 512 * 512, "seconds": dt3, "models_per_s": 512 * 512 / dt3,
                                             "note": "wall clock incl. on-device forward model, 2 fused passes (W1, W2), D2H"}
+    # cfg1 latency: ONE Ricker evaluation (misfit + gradient w.r.t. the 3 model parameters) through the adapter
+    # a scipy.optimize loop would call, host in / host out, forward model included (ricker_util.optfunc)
+    data = [tgt3, "W2", (-2.0, 2.0), grid3, 0.03, False, 0.5, 45.0]
+    X1 = np.array([[0.7, 1.3, 0.8]])
+    adapters.optfunc_ricker_batch(X1, data)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        adapters.optfunc_ricker_batch(X1, data)
+    out["cfg1_single_eval_latency"] = {"ms": (time.perf_counter() - t0) / 20 * 1e3,
+                                       "note": "adapters.optfunc_ricker_batch, 1 model, wall clock incl. Python, launches, D2H"}
     # cfg2: batched 1-D OT, W2 + dW2/df + d/dx0 on random densities (FP32 in, FP64 out), C ABI called directly
     n, nb = 1024, 100000
     f = torch.rand(nb, n, device=dev) + 1e-3
