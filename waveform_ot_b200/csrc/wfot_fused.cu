@@ -86,6 +86,7 @@ struct FusedArgs {
     // per-CTA scratch slabs
     double* s_pdf; double* s_wa; double* s_wb; int32_t* s_idx;
     int32_t* status;
+    int* next_window;     // global work counter (zeroed by the launcher)
     int Spad, ntg_pad, nug_pad, nmax;
     SmemLayout L;
 };
@@ -140,10 +141,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T, false};
     int zero_dist = 0, slow = 0, common = 0, degen = 0, tiles = 0;
 
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    // windows are drawn from a global counter (the pruned scan makes their cost uneven): the first window of a
+    // CTA is blockIdx.x, the following ones come from the counter, which starts at gridDim.x
+    for (int b = blockIdx.x; b < a.B;) {
         // ---------------- P0: window -> shared memory
         const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
-        if (tid == 0) { s_hdr->degenerate = 0; s_hdr->nonmono = 0; s_qcount[0] = 0; s_qcount[1] = 0; }
+        if (tid == 0) {
+            s_hdr->degenerate = 0; s_hdr->nonmono = 0; s_qcount[0] = 0; s_qcount[1] = 0;
+            s_qcount[2] = (int)gridDim.x + atomicAdd(a.next_window, 1);      // this CTA's next window
+        }
         if (a.grad) {      // P4 accumulates into these rows with L2 reductions
             double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
             for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
@@ -325,6 +331,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
                 }
             }
         }
+        b = s_qcount[2];
         __syncthreads();
     }
     if (a.status) {
@@ -421,7 +428,7 @@ size_t wfot_misfit_grad_workspace_bytes(int B, int nt, int nug, int ntg) {
     if (sms <= 0) sms = 148;
     size_t ctas = (size_t)sms * 8;
     if ((size_t)B < ctas) ctas = (size_t)B;
-    return ctas * (size_t)nug * ntg * 28 + 256;
+    return ctas * (size_t)nug * ntg * 28 + 512;
 }
 
 int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
@@ -466,6 +473,10 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     if (ctas > B) ctas = B;
     const size_t npix = (size_t)nug * ntg;
     uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    if (workspace_bytes < (base - (uintptr_t)workspace) + 256) return WFOT_ERR_WORKSPACE;
+    a.next_window = (int*)base;                       // first 256 bytes: the window counter
+    if (cudaMemsetAsync(a.next_window, 0, 256, stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMemsetAsync");
+    base += 256;
     const size_t avail = workspace_bytes - (base - (uintptr_t)workspace);
     const size_t max_ctas = avail / (npix * 28);
     if (max_ctas < 1) return WFOT_ERR_WORKSPACE;
