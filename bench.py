@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4736, help="windows per GPU per step (32 per SM)")
+    ap.add_argument("--batch", type=int, default=9472, help="windows per GPU per step (64 per SM)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="windows timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--secondary", type=int, default=1,
                     help="also time the other BASELINE.json configs' kernels (N=1, a few ms each)")
