@@ -17,6 +17,7 @@
 //                              accumulated with FP64 reductions in L2
 // Reference chain replaced: ricker_util.py:386-388 (BuildOTobjfromWaveform ->
 // CalcWasserWaveform(deriv=True, returnmarg=True)).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -87,6 +88,7 @@ struct FusedArgs {
     double* s_pdf; double* s_wa; double* s_wb; int32_t* s_idx;
     int32_t* status;
     int* next_window;     // global work counter (zeroed by the launcher)
+    int cluster;          // > 1: launched as thread-block clusters of this many CTAs, one window per CLUSTER
     int Spad, ntg_pad, nug_pad, nmax;
     SmemLayout L;
 };
@@ -137,20 +139,30 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     WFOT_SMEM_POINTERS(a.L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = a.nug * a.ntg, S = a.nt - 1;
-    const size_t slab = (size_t)blockIdx.x * npix;
+    // Small batches (fewer windows than resident CTAs) are launched as thread-block clusters: the CTAs of a
+    // cluster share ONE window - each prepares it in its own shared memory, they split the pixel footprints
+    // of P1, and rank 0 runs the short P2-P4 after a cluster barrier.  That cuts the latency of a single
+    // evaluation (the reference's scipy.optimize loops evaluate one model at a time).
+    namespace cg = cooperative_groups;
+    const int csize = a.cluster > 1 ? a.cluster : 1;
+    const int crank = csize > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    const int cid = (int)blockIdx.x / csize, nclusters = (int)gridDim.x / csize;
+    const size_t slab = (size_t)cid * npix;
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T, false};
     int zero_dist = 0, slow = 0, common = 0, degen = 0, tiles = 0;
 
     // windows are drawn from a global counter (the pruned scan makes their cost uneven): the first window of a
-    // CTA is blockIdx.x, the following ones come from the counter, which starts at gridDim.x
-    for (int b = blockIdx.x; b < a.B;) {
+    // CTA is blockIdx.x, the following ones come from the counter, which starts at gridDim.x.  Clusters take
+    // windows cid, cid + nclusters, ... (every CTA of a cluster must see the same sequence).
+    for (int b = cid; b < a.B;) {
         // ---------------- P0: window -> shared memory
         const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
         if (tid == 0) {
             s_hdr->degenerate = 0; s_hdr->nonmono = 0; s_qcount[0] = 0; s_qcount[1] = 0;
-            s_qcount[2] = (int)gridDim.x + atomicAdd(a.next_window, 1);      // this CTA's next window
+            s_qcount[2] = csize > 1 ? b + nclusters
+                                    : (int)gridDim.x + atomicAdd(a.next_window, 1);      // this CTA's next window
         }
-        if (a.grad) {      // P4 accumulates into these rows with L2 reductions
+        if (a.grad && crank == 0) {      // P4 accumulates into these rows with L2 reductions
             double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
             for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
             __threadfence();
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
         __syncthreads();
         const WinHdr hdr = *s_hdr;
         tb.mono = (hdr.nonmono == 0);
-        degen += (tid == 0) ? hdr.degenerate : 0;
+        degen += (tid == 0 && crank == 0) ? hdr.degenerate : 0;
         for (int i = tid; i < a.ntg; i += NT) s_xt[i] = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, i, a.ntg);
         for (int i = tid; i < a.nug; i += NT) s_xu[i] = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, i, a.nug);
         __syncthreads();
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
                                            fabsf(s_pys[a.nug - 1] - s_pys[0]));
         for (;;) {
             int f = 0;
-            if (lane == 0) f = atomicAdd(s_qcount + 1, 1);
+            if (lane == 0) f = atomicAdd(s_qcount + 1, 1) * csize + crank;     // this CTA's share of the footprints
             f = __shfl_sync(0xffffffffu, f, 0);
             if (f >= fm.nfoot) break;
             const LaneBlock lb = lane_block<R>(fm, f, lane, a.ntg, a.nug, s_pxs, s_pys);
@@ -218,7 +230,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
             }
         }
         __syncthreads();   // scratch slab complete (block-scope visibility of global writes)
-
+        if (csize > 1) {   // ... and cluster-scope: every CTA's share of the slab is visible to rank 0
+            __threadfence();
+            cg::this_cluster().sync();
+        }
+        if (crank == 0) {
         // ---------------- P2: marginals of the normalised density (fixed summation order;
         //                  8 independent loads in flight per thread)
         double part = 0.0;
@@ -331,8 +347,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
                 }
             }
         }
+        }   // crank == 0
         b = s_qcount[2];
         __syncthreads();
+        if (csize > 1) cg::this_cluster().sync();   // rank 0 is done reading the slab: the next window may overwrite it
     }
     if (a.status) {
         if (zero_dist) atomicAdd(a.status + WFOT_STAT_ZERO_DIST, zero_dist);
@@ -470,7 +488,16 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     else ctas = nthreads == 64 ? WFOT_OCC(4, 64, 16) : nthreads == 128 ? WFOT_OCC(4, 128, 16) : WFOT_OCC(4, 256, 16);
 #undef WFOT_OCC
     if (ctas < 1) return cuda_fail(cudaGetLastError(), "k_misfit_grad occupancy");
-    if (ctas > B) ctas = B;
+    // few windows: clusters of 2/4/8 CTAs per window (as many as keep every window resident at once)
+    int csize = 1;
+    {
+        const char* ec = getenv("WFOT_DEV_CLUSTER");
+        const int cmax = ec ? atoi(ec) : 8;
+        while (csize * 2 <= cmax && (long long)B * csize * 2 <= ctas) csize *= 2;
+    }
+    a.cluster = csize;
+    if (csize > 1) ctas = B * csize;
+    else if (ctas > B) ctas = B;
     const size_t npix = (size_t)nug * ntg;
     uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     if (workspace_bytes < (base - (uintptr_t)workspace) + 256) return WFOT_ERR_WORKSPACE;
@@ -480,17 +507,30 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     const size_t avail = workspace_bytes - (base - (uintptr_t)workspace);
     const size_t max_ctas = avail / (npix * 28);
     if (max_ctas < 1) return WFOT_ERR_WORKSPACE;
-    if ((size_t)ctas > max_ctas) ctas = (int)max_ctas;
+    if (csize == 1 && (size_t)ctas > max_ctas) ctas = (int)max_ctas;
+    if (csize > 1 && (size_t)(ctas / csize) > max_ctas) return WFOT_ERR_WORKSPACE;   // one slab per cluster
     unsigned char* p = (unsigned char*)base;
-    a.s_pdf = (double*)p;   p += (size_t)ctas * npix * 8;
-    a.s_wa = (double*)p;    p += (size_t)ctas * npix * 8;
-    a.s_wb = (double*)p;    p += (size_t)ctas * npix * 8;
+    const size_t nslab = csize > 1 ? (size_t)(ctas / csize) : (size_t)ctas;
+    a.s_pdf = (double*)p;   p += nslab * npix * 8;
+    a.s_wa = (double*)p;    p += nslab * npix * 8;
+    a.s_wb = (double*)p;    p += nslab * npix * 8;
     a.s_idx = (int32_t*)p;
-#define WFOT_LAUNCH(RR, NN, TT) k_misfit_grad<RR, NN, TT><<<ctas, NN, smem, stream>>>(a)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3((unsigned)nthreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    if (csize > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    cudaError_t le = cudaSuccess;
+#define WFOT_LAUNCH(RR, NN, TT) le = cudaLaunchKernelEx(&cfg, k_misfit_grad<RR, NN, TT>, a)
     if (R == 8) WFOT_LAUNCH(8, 256, 16);
     else if (T == 8) { if (nthreads == 64) WFOT_LAUNCH(4, 64, 8); else if (nthreads == 128) WFOT_LAUNCH(4, 128, 8); else WFOT_LAUNCH(4, 256, 8); }
     else { if (nthreads == 64) WFOT_LAUNCH(4, 64, 16); else if (nthreads == 128) WFOT_LAUNCH(4, 128, 16); else WFOT_LAUNCH(4, 256, 16); }
 #undef WFOT_LAUNCH
+    if (le != cudaSuccess) return cuda_fail(le, "wfot_misfit_grad_batch launch");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_misfit_grad_batch launch");
     return WFOT_OK;
