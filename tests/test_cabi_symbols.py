@@ -46,5 +46,6 @@ def test_sass_is_blackwell_packed_fp32():
     assert "sm_100a" in out
     for op in ("FFMA2", "FMUL2", "FMNMX3", "FADD.SAT",
                "CREDUX.MAX",            # warp-uniform pruning bound of the scan (one instruction per evaluated tile)
-               "ATOMG.E.ADD.F64"):      # gradient assembly: native FP64 reductions in L2
+               "ATOMG.E.ADD.F64",       # gradient assembly: native FP64 reductions in L2
+               "UCGABAR_ARV"):          # thread-block cluster barrier (one window per cluster for small batches)
         assert op in out, op
