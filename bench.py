@@ -282,6 +282,13 @@ def secondary_configs(dev):
         adapters.optfunc_ricker_batch(X1, data)
     out["cfg1_single_eval_latency"] = {"ms": (time.perf_counter() - t0) / 20 * 1e3,
                                        "note": "adapters.optfunc_ricker_batch, 1 model, wall clock incl. Python, launches, D2H"}
+    ev = adapters.RickerGraphEvaluator(data)
+    ev(X1[0])
+    t0 = time.perf_counter()
+    for _ in range(100):
+        ev(X1[0])
+    out["cfg1_single_eval_latency_cuda_graph"] = {"ms": (time.perf_counter() - t0) / 100 * 1e3,
+                                                  "note": "adapters.RickerGraphEvaluator: one captured CUDA graph replayed per evaluation"}
     # cfg2: batched 1-D OT, W2 + dW2/df + d/dx0 on random densities (FP32 in, FP64 out), C ABI called directly
     n, nb = 1024, 100000
     f = torch.rand(nb, n, device=dev) + 1e-3

@@ -241,3 +241,19 @@ def test_transport_plan_golden(mods, golden):
     assert len(w) == 2 and w[0] == pytest.approx(float(g["plan_W1"]), rel=1e-12)
     np.testing.assert_allclose(w[1], g["plan_H_nod"], atol=1e-15)
     assert w[1].sum() == pytest.approx(1.0, abs=1e-14)
+
+
+def test_ricker_graph_evaluator(mods, golden):
+    """The CUDA-graph evaluator (device-side sequence captured once, replayed per evaluation) returns what
+    ru.optfunc returns, call after call with changing parameters."""
+    _, _, adapters = mods
+    g = golden("ricker_forward")
+    grid = _grid(g)
+    lam, alpha = float(g["lam"]), float(g["alpha"])
+    target = adapters.make_target(g["to"], g["wo"], grid, lam)
+    ev = adapters.RickerGraphEvaluator([target, "W2", (-2.0, 2.0), grid, lam, False, alpha, 45.0])
+    for rep in range(2):
+        for i, x in enumerate(g["X"]):
+            f, d = ev(x)
+            assert f == pytest.approx(float(g["F"][i]), rel=1e-9)
+            np.testing.assert_allclose(d, g["G"][i], rtol=1e-7, atol=1e-10)

@@ -168,3 +168,59 @@ def misfit_surface(tshifts, amps, f, target, grid, lambdav, trange=(-2.0, 2.0), 
     torch.cuda.current_stream().synchronize()
     shp = (len(tshifts), len(amps), 2)
     return torch.cat(out["W1"]).cpu().numpy().reshape(shp), torch.cat(out["W2"]).cpu().numpy().reshape(shp)
+
+
+class RickerGraphEvaluator:
+    """`optfunc(x, data)` of libs/ricker_util.py:373-404 as a callable for `scipy.optimize.minimize(..., jac=True)`,
+    with the device-side sequence (forward model -> fused misfit + gradient -> chain rule) captured ONCE in a
+    CUDA graph and replayed per evaluation: the model parameters go into a static device buffer, the four
+    results come back through pinned memory.  One evaluation takes ~0.2 ms on a B200 (0.73 s in the reference).
+    `data` as for optfunc_ricker (target from make_target)."""
+
+    def __init__(self, data):
+        import torch
+        target, distfunc, trange, grid, lambdav, transform, alpha, theta = data
+        t0, t1, u0, u1, Nu, Nt = grid
+        tant = 1.0 if theta == 45.0 else float(np.tan(np.pi * theta / 180.0))
+        dev = _B._device()
+        self._x = torch.zeros((1, 3), dtype=torch.float64, device=dev)
+        self._xh = torch.zeros((1, 3), dtype=torch.float64).pin_memory()
+        self._out_h = torch.empty(4, dtype=torch.float64).pin_memory()
+        g = _B.pack_grids((t0, t1, u0, u1, Nu, Nt), tant)
+        ws = torch.empty(_B.C.lib.wfot_misfit_grad_workspace_bytes(1, 256, int(Nu), int(Nt)), dtype=torch.uint8,
+                         device=dev)
+        self.status = _B.Status()
+        self._keep = (g, ws, target)
+
+        def device_eval():
+            fw = _B.ricker_batch(self._x, trange, deriv=True)
+            r = _B.misfit_grad_batch(fw["t"], fw["w"], g, int(Nu), int(Nt), lambdav, target, distfunc=distfunc,
+                                     tantheta=tant, transform=transform, workspace=ws, status=self.status)
+            W, gr = r["W"], r["grad"]
+            w2 = alpha * W[:, 0] + (1 - alpha) * W[:, 1]                              # :390
+            dr = (alpha * gr[:, 0] + (1 - alpha) * gr[:, 1]).contiguous()             # :399-401
+            deriv = _B.chain_batch(fw["dw"], dr)
+            deriv[:, 0] = alpha * r["dwg"] / (tant * (t1 - t0))                       # :333,392,402
+            return torch.cat([w2, deriv[0]])
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up outside the capture (lazy module loads, attributes)
+            for _ in range(2):
+                device_eval()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._res = device_eval()
+        torch.cuda.synchronize()
+
+    def __call__(self, x, *unused):
+        import torch
+        self._xh[0] = torch.from_numpy(np.asarray(x, dtype=np.float64))
+        self._x.copy_(self._xh, non_blocking=True)
+        self._graph.replay()
+        self._out_h.copy_(self._res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        o = self._out_h.numpy()
+        return float(o[0]), o[1:].copy()
