@@ -22,7 +22,8 @@
  *    device array (WFOT_STAT_* slots, int32 each, per call, accumulated with
  *    atomics) and mapped back to the reference's exception classes by the shim.
  *  - window b of a batch reads t + b*t_stride and w + b*nt (t_stride = 0
- *    shares one time axis); grids[n_grids==1 ? 0 : b].
+ *    shares one time axis); window b uses grids[b % n_grids] (1 = shared, B = one per
+ *    window, nr*nc = one per station/component of every trial model).
  *  - pixel flat index k = iu*ntg + it (row-major (nug, ntg), the reference's
  *    meshgrid 'xy' order, libs/FingerprintLib.py:254-255).
  */
@@ -169,8 +170,9 @@ int wfot_ricker_batch(const double* params, int M, double t0, double t1,
  * =True, returnmargW=True) -> wf.PDFderivMarg: libs/ricker_util.py:204-268,
  * 321-337; libs/OTlib.py:1055-1154; libs/FingerprintLib.py:205-228.
  * Target (observed) marginals are given as their CDFs + bin positions:
- *   tgt_cdf_t/tgt_x_t (Bt, ntg), tgt_cdf_u/tgt_x_u (Bt, nug), window b uses
- *   row (tgt_stride_windows ? b : 0).
+ *   tgt_cdf_t/tgt_x_t (tgt_rows, ntg), tgt_cdf_u/tgt_x_u (tgt_rows, nug), window b
+ *   uses row b % tgt_rows (1 = one observation for the whole batch, B = one per
+ *   window, nr*nc = one per station/component shared by all trial models).
  * Outputs: W (B, 2) = [W^t, W^u]; grad (B, 2, nt) = [dW^t/dw, dW^u/dw] (NULL =
  * misfit only); dwg (B,) = dW^t/d(translation) in normalised time units
  * (divide by tan(theta)*(t1-t0) as libs/ricker_util.py:333).
@@ -182,7 +184,7 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
                            const wfot_grid* grids, int n_grids, int B, int nug, int ntg,
                            double lambda, int q, int pmask, int transform,
                            const double* tgt_cdf_t, const double* tgt_x_t,
-                           const double* tgt_cdf_u, const double* tgt_x_u, int tgt_per_window,
+                           const double* tgt_cdf_u, const double* tgt_x_u, int tgt_rows,
                            double* W, double* grad, double* dwg,
                            void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 

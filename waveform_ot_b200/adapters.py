@@ -103,12 +103,9 @@ def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfu
     M, nr, nc, nt = seis.shape
     Nu, Nt = int(obs_grids[0][0][4]), int(obs_grids[0][0][5])
     flat = [tuple(obs_grids[i][j][:4]) + (Nu, Nt) for i in range(nr) for j in range(nc)]
-    g1 = _B.pack_grids(flat)                                   # (nr*nc, 80 B)
-    g = g1.repeat(M, 1).contiguous()                           # window b = m*(nr*nc) + i*nc + j
-    tgt = _B.Target(targets.cdf_t.repeat(M, 1).contiguous(), targets.x_t.repeat(M, 1).contiguous(),
-                    targets.cdf_u.repeat(M, 1).contiguous(), targets.x_u.repeat(M, 1).contiguous())
-    tgt.per_window = True
-    r = _B.misfit_grad_batch(t, seis.reshape(M * nr * nc, nt), g, Nu, Nt, lambdav, tgt, distfunc=distfunc,
+    g = _B.pack_grids(flat)                                    # (nr*nc, 80 B): window b = m*(nr*nc) + i*nc + j uses
+    #                                                            grid / observed window b % (nr*nc) (no per-model copies)
+    r = _B.misfit_grad_batch(t, seis.reshape(M * nr * nc, nt), g, Nu, Nt, lambdav, targets, distfunc=distfunc,
                              transform=True)
     W = r["W"].reshape(M, nr * nc, 2)
     gr = r["grad"].reshape(M, nr * nc, 2, nt)

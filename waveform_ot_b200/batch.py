@@ -214,6 +214,12 @@ class Target:
         self.cdf_t, self.x_t, self.cdf_u, self.x_u = cdf_t, x_t, cdf_u, x_u
         self.per_window = cdf_t.dim() == 2 and cdf_t.shape[0] > 1
 
+    @property
+    def rows(self):
+        """Number of observed windows held: window b of a batch is compared with row b % rows (1 = one
+        observation for the whole batch, B = one per window, nr*nc = one per station/component)."""
+        return int(self.cdf_t.shape[0]) if self.cdf_t.dim() == 2 else 1
+
     @staticmethod
     def from_waveform(t, w, grids, nug, ntg, lambdav, q=None, tantheta=1.0, fpgrids=None):
         """Fingerprint the observed window(s) and keep their marginal CDFs."""
@@ -286,7 +292,7 @@ def misfit_grad_batch(t, w, grids, nug, ntg, lambdav, target: Target, distfunc="
         C.ptr(t), C.ptr(w), _dt(w), t_stride, nt, C.ptr(g), g.shape[0], B, nug, ntg,
         float(lambdav), 0 if q is None else int(q), pmask, int(bool(transform)),
         C.ptr(target.cdf_t), C.ptr(target.x_t), C.ptr(target.cdf_u), C.ptr(target.x_u),
-        int(target.per_window), C.ptr(W), C.ptr(grad), C.ptr(dwg), C.ptr(ws), ws.numel(),
+        target.rows, C.ptr(W), C.ptr(grad), C.ptr(dwg), C.ptr(ws), ws.numel(),
         C.ptr(st.t), _stream()), "wfot_misfit_grad_batch")
     return dict(W=W, grad=grad, dwg=dwg, status=st, _keepalive=(t, w, g, ws))
 

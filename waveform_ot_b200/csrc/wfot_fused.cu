@@ -82,7 +82,7 @@ struct FusedArgs {
     const wfot_grid* grids; int n_grids; int B; int nug, ntg;
     double lambda; int q, pmask, transform;
     const double* tgt_cdf_t; const double* tgt_x_t; const double* tgt_cdf_u; const double* tgt_x_u;
-    int tgt_per_window;
+    int tgt_rows;
     double* W; double* grad; double* dwg;
     // per-CTA scratch slabs
     double* s_pdf; double* s_wa; double* s_wb; int32_t* s_idx;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     // windows cid, cid + nclusters, ... (every CTA of a cluster must see the same sequence).
     for (int b = cid; b < a.B;) {
         // ---------------- P0: window -> shared memory
-        const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
+        const wfot_grid g = a.grids[b % a.n_grids];
         if (tid == 0) {
             s_hdr->degenerate = 0; s_hdr->nonmono = 0; s_qcount[0] = 0; s_qcount[1] = 0;
             s_qcount[2] = csize > 1 ? b + nclusters
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
         __syncthreads();
 
         // ---------------- P3: 1-D OT per marginal
-        const size_t trow = a.tgt_per_window ? (size_t)b : 0;
+        const size_t trow = (size_t)(b % a.tgt_rows);
         OtScratch sc{s_cf, s_tk, s_dx, s_E, s_posf, s_red};
         for (int c = tid; c < a.ntg; c += NT) s_cf[c] = s_margt[c];
         __syncthreads();
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256, 2) k_scan_probe(FusedArgs a, float* out) 
     const int tid = threadIdx.x, S = a.nt - 1;
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, 16, false};
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-        const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
+        const wfot_grid g = a.grids[b % a.n_grids];
         if (tid == 0) { s_hdr->degenerate = 0; s_hdr->nonmono = 0; }
         __syncthreads();
         PrepOut po{s_pn, s_A, s_H, s_bbox, tb.tile, s_pxs, s_pys, s_hdr};
@@ -452,12 +452,12 @@ size_t wfot_misfit_grad_workspace_bytes(int B, int nt, int nug, int ntg) {
 int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
                            const wfot_grid* grids, int n_grids, int B, int nug, int ntg, double lambda,
                            int q, int pmask, int transform, const double* tgt_cdf_t, const double* tgt_x_t,
-                           const double* tgt_cdf_u, const double* tgt_x_u, int tgt_per_window, double* W,
+                           const double* tgt_cdf_u, const double* tgt_x_u, int tgt_rows, double* W,
                            double* grad, double* dwg, void* workspace, size_t workspace_bytes,
                            int32_t* status, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!t || !w || !grids || !W || !workspace || !tgt_cdf_t || !tgt_x_t || !tgt_cdf_u || !tgt_x_u ||
-        B <= 0 || nt < 2 || nug < 1 || ntg < 1 || (n_grids != 1 && n_grids != B) ||
+        B <= 0 || nt < 2 || nug < 1 || ntg < 1 || n_grids < 1 || tgt_rows < 1 ||
         (q != 0 && q != 2) || (pmask != WFOT_W1 && pmask != WFOT_W2) || !(lambda > 0.0) ||
         (in_dtype != WFOT_F32 && in_dtype != WFOT_F64))
         return WFOT_ERR_INVALID_ARG;
@@ -465,7 +465,7 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
     a.t = t; a.w = w; a.dtype = in_dtype; a.t_stride = t_stride; a.nt = nt; a.grids = grids;
     a.n_grids = n_grids; a.B = B; a.nug = nug; a.ntg = ntg; a.lambda = lambda; a.q = q; a.pmask = pmask;
     a.transform = transform; a.tgt_cdf_t = tgt_cdf_t; a.tgt_x_t = tgt_x_t; a.tgt_cdf_u = tgt_cdf_u;
-    a.tgt_x_u = tgt_x_u; a.tgt_per_window = tgt_per_window; a.W = W; a.grad = grad; a.dwg = dwg;
+    a.tgt_x_u = tgt_x_u; a.tgt_rows = tgt_rows; a.W = W; a.grad = grad; a.dwg = dwg;
     a.status = status;
     a.Spad = seg_pad(nt); a.ntg_pad = pad4(ntg); a.nug_pad = pad4(nug);
     a.nmax = pad4(ntg > nug ? ntg : nug);

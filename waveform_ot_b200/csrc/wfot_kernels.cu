@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs a) {
     __shared__ double red[64];
     const int wl = blockIdx.x;
     const long long b = a.b0 + wl;
-    const wfot_grid g = a.grids[a.n_grids == 1 ? 0 : b];
+    const wfot_grid g = a.grids[b % a.n_grids];
     PrepOut o;
     o.pn = a.ws.pn + (size_t)wl * a.nt;
     o.A = a.ws.A + (size_t)wl * a.ws.Spad;
@@ -461,7 +461,7 @@ int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long
                            size_t workspace_bytes, int32_t* status, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!t || !w || !grids || !workspace || B <= 0 || nt < 2 || nug < 1 || ntg < 1 ||
-        (n_grids != 1 && n_grids != B) || (q != 0 && q != 2) || !(lambda > 0.0) ||
+        n_grids < 1 || (q != 0 && q != 2) || !(lambda > 0.0) ||
         (in_dtype != WFOT_F32 && in_dtype != WFOT_F64))
         return WFOT_ERR_INVALID_ARG;
     const size_t per = fp_workspace_per_window(nt, nug, ntg);
