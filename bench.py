@@ -289,6 +289,28 @@ def secondary_configs(dev):
         ev(X1[0])
     out["cfg1_single_eval_latency_cuda_graph"] = {"ms": (time.perf_counter() - t0) / 100 * 1e3,
                                                   "note": "adapters.RickerGraphEvaluator: one captured CUDA graph replayed per evaluation"}
+    # cfg4 end to end: 1024 trial models x (10 stations x 3 components) windows of 61 samples, host-precomputed
+    # (synthetic) seismograms and Jacobians in, per-model misfit + gradient w.r.t. 9 source parameters out
+    rng = np.random.default_rng(1)
+    M4, nr4, nc4, nt4 = 1024, 10, 3, 61
+    t4 = np.arange(float(nt4))
+    pulse = lambda sh, wd: np.exp(-0.5 * ((t4 - sh) / wd) ** 2) * np.sin(0.35 * (t4 - sh))
+    obs4 = np.stack([[pulse(22 + 2 * i + j, 4.0) for j in range(nc4)] for i in range(nr4)]) * 1e-3
+    obs4 += 2e-5 * rng.standard_normal(obs4.shape)
+    sh = rng.uniform(-4, 4, size=(M4, 1, 1))
+    pred4 = np.stack([[pulse(22 + 2 * i + j, 4.0) for j in range(nc4)] for i in range(nr4)])[None] * 1e-3
+    pred4 = np.stack([np.roll(pred4[0], int(round(s_)), axis=-1) for s_ in sh[:, 0, 0]]) * rng.uniform(0.7, 1.3, size=(M4, 1, 1, 1))
+    J4 = rng.standard_normal((M4, 9, nr4 * nc4 * nt4))
+    grids4 = adapters.buildFingerprintwindows(t4, obs4)
+    tg4 = adapters.make_targets_models(t4, obs4, grids4, 0.04)
+    adapters.misfit_grad_models(t4, pred4[:8], grids4, tg4, 0.04, J=J4[:8])
+    t0 = time.perf_counter()
+    adapters.misfit_grad_models(t4, pred4, grids4, tg4, 0.04, J=J4)
+    dt4 = time.perf_counter() - t0
+    out["cfg4_models_1024x30_windows_end_to_end"] = {
+        "models": M4, "windows": M4 * nr4 * nc4, "seconds": dt4, "models_per_s": M4 / dt4,
+        "note": "adapters.misfit_grad_models: pageable host arrays in (seismograms 15 MB, Jacobians 135 MB), "
+                "fused kernel with in-kernel arctan transform, Jacobian chain, results back on the host"}
     # cfg2: batched 1-D OT, W2 + dW2/df + d/dx0 on random densities (FP32 in, FP64 out), C ABI called directly
     n, nb = 1024, 100000
     f = torch.rand(nb, n, device=dev) + 1e-3

@@ -89,3 +89,19 @@ def test_shard_bounds_cover_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_build_fingerprint_windows_rule():
+    """adapters.buildFingerprintwindows == libs/loc_cmt_util.py:429-446 (oracle restatement), no GPU needed."""
+    import numpy as np
+    from oracle import wfot_oracle as O
+    from waveform_ot_b200 import adapters
+    rng = np.random.default_rng(4)
+    t = np.arange(61.0)
+    wave = rng.standard_normal((3, 2, 61)) * 1e-3
+    g = adapters.buildFingerprintwindows(t, wave)
+    for i in range(3):
+        for j in range(2):
+            assert list(g[i][j]) == list(O.build_fingerprint_window(t, wave[i, j]))
+    g2 = adapters.buildFingerprintwindows(t, wave, Nu=50, Nt=40, u0=-1.0, u1=2.0)
+    assert g2[1][1][2:] == [-1.0, 2.0, 50, 40]

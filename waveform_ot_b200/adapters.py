@@ -221,3 +221,30 @@ class RickerGraphEvaluator:
         torch.cuda.current_stream().synchronize()
         o = self._out_h.numpy()
         return float(o[0]), o[1:].copy()
+
+
+def buildFingerprintwindows(t, wave, Nu=None, Nt=None, u0=None, u1=None):
+    """libs/loc_cmt_util.py:429-446: per station/component fingerprint window [t0, t1, u0, u1, Nu, Nt] from the
+    observed seismograms wave (nr, nc, nt): amplitude box = data range widened by 30 % each side, Nu = int(1.3 nt),
+    Nt = nt unless given."""
+    nr, nc, nt = np.shape(wave)
+    grid = np.zeros((nr, nc)).tolist()
+    for i in range(nr):
+        for j in range(nc):
+            du = np.max(wave[i, j]) - np.min(wave[i, j])
+            u0out = np.min(wave[i, j]) - 0.3 * du if u0 is None else u0
+            u1out = np.max(wave[i, j]) + 0.3 * du if u1 is None else u1
+            grid[i][j] = [np.min(t), np.max(t), u0out, u1out,
+                          int(1.3 * len(wave[i, j])) if Nu is None else Nu, len(wave[i, j]) if Nt is None else Nt]
+    return grid
+
+
+def make_targets_models(t, seis_obs, obs_grids, lambdav, q=None):
+    """Observed seismograms (nr, nc, nt) -> Target with one row per station/component, arctan-transformed with
+    each window's amplitude box (libs/loc_cmt_util.py:237-249,576-587), as misfit_grad_models() expects."""
+    obs = np.asarray(seis_obs, dtype=np.float64)
+    nr, nc, nt = obs.shape
+    Nu, Nt = int(obs_grids[0][0][4]), int(obs_grids[0][0][5])
+    un = np.stack([arctan_trans(obs[i, j], obs_grids[i][j][2], obs_grids[i][j][3]) for i in range(nr) for j in range(nc)])
+    g01 = [(obs_grids[i][j][0], obs_grids[i][j][1], 0.0, 1.0, Nu, Nt) for i in range(nr) for j in range(nc)]
+    return _B.Target.from_waveform(t, un, g01, Nu, Nt, lambdav, q=q)
