@@ -513,3 +513,20 @@ def test_fingerprint_random_shapes_stress(B):
         np.testing.assert_array_equal(out["dfield"][0].cpu().numpy(), win.dfield)
         np.testing.assert_array_equal(out["lray"][0].cpu().numpy(), win.lrays)
         done += 1
+
+
+def test_sharded_evaluation_single_rank(B):
+    """dist.misfit_grad_sharded at world size 1 (the N > 1 host logic is covered by the gloo test on CPU):
+    packed [sum W, sum dwg, sum grad] equals the sums of the per-window results."""
+    from waveform_ot_b200 import dist as wd
+    rng = np.random.default_rng(8)
+    nt, nug, ntg = 50, 24, 40
+    t = np.linspace(0, 1, nt)
+    w = rng.standard_normal((9, nt)).cumsum(axis=1) * 0.1
+    grid = (0.0, 1.0, float(w.min()) - 0.2, float(w.max()) + 0.2, nug, ntg)
+    tg = B.Target.from_waveform(t, w[0], grid, nug, ntg, 0.05)
+    packed = wd.misfit_grad_sharded(t, w[1:], grid, nug, ntg, 0.05, tg).cpu().numpy()
+    r = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, 0.05, tg)
+    ref = np.concatenate([r["W"].sum(0).cpu().numpy(), [float(r["dwg"].sum())],
+                          r["grad"].sum(0).reshape(-1).cpu().numpy()])
+    np.testing.assert_allclose(packed, ref, rtol=1e-12, atol=1e-15)

@@ -66,3 +66,26 @@ def sharded_misfit_grad(evaluate, n_windows, reducer):
     lo, hi = shard_bounds(n_windows, rank, world)
     W, dwg, grad = evaluate(lo, hi)
     return allreduce_sum_(pack_local_sums(W, dwg, grad, reducer))
+
+
+def misfit_grad_sharded(t, w, grids, nug, ntg, lambdav, target, **kw):
+    """The multi-GPU evaluation of a stacked misfit: this rank runs the fused kernel on its contiguous shard
+    of the windows `w` (B, nt) (a per-window time axis `t` (B, nt) is sharded alike), reduces it to
+    [sum W^t, sum W^u, sum dW^t/dx0, sum dW^t/dw, sum dW^u/dw] with the fixed-order window sum, and the ranks
+    combine with ONE allreduce.  Returns the packed (3 + 2 nt,) device vector, identical on every rank.
+    Grids / observed windows with one row per window are sharded alike; shared or periodic rows are kept
+    (a periodic layout needs shard boundaries that are multiples of the period)."""
+    from . import batch as B
+    rank, world, _ = env_rank_world()
+    n = w.shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    tt = t[lo:hi] if getattr(t, "ndim", 1) == 2 else t
+    g = grids
+    if hasattr(grids, "shape") and grids.shape[0] == n and n > 1:
+        g = grids[lo:hi].contiguous()
+    tg = target
+    if target.rows == n and n > 1:
+        tg = B.Target(target.cdf_t[lo:hi].contiguous(), target.x_t[lo:hi].contiguous(),
+                      target.cdf_u[lo:hi].contiguous(), target.x_u[lo:hi].contiguous())
+    r = B.misfit_grad_batch(tt, w[lo:hi], g, nug, ntg, lambdav, tg, **kw)
+    return allreduce_sum_(pack_local_sums(r["W"], r["dwg"], r["grad"], B.sum_windows))
