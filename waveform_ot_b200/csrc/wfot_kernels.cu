@@ -251,9 +251,7 @@ __global__ void __launch_bounds__(256) k_otpdf1d(const void* f, int dtype, int n
         if (pdfn) pdfn[b * n + j] = p;
     }
     __syncthreads();
-    block_scan(c, n, false, red);
-    const double last = c[n - 1];
-    __syncthreads();
+    const double last = block_cumsum(c, n, red);
     if (cdf) for (int j = tid; j < n; j += 256) cdf[b * n + j] = c[j] / last;
     if (tid == 0 && amp) amp[b] = A;
     const int nneg = __syncthreads_count(neg > 0);

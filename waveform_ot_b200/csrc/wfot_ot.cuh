@@ -56,6 +56,49 @@ __device__ __forceinline__ void block_scan(double* a, int n, bool reverse, doubl
     __syncthreads();
 }
 
+// In-place inclusive running maximum of a[0..n) in shared memory (exact: max is associative).
+__device__ __forceinline__ void block_running_max(double* a, int n, double* red) {
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int chunk = (n + T - 1) / T;
+    const int beg = tid * chunk, end = min(beg + chunk, n);
+    const double ninf = __longlong_as_double(0xfff0000000000000LL);
+    double run = ninf;
+    for (int i = beg; i < end; ++i) { run = fmax(run, a[i]); a[i] = run; }
+    double inc = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc = fmax(inc, o);
+    }
+    double excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) excl = ninf;
+    __syncthreads();
+    if (lane == 31) red[wid] = inc;
+    __syncthreads();
+    for (int i = 0; i < wid; ++i) excl = fmax(excl, red[i]);
+    for (int i = beg; i < end; ++i) a[i] = fmax(a[i], excl);
+    __syncthreads();
+}
+
+// np.cumsum of non-negative terms (libs/OTlib.py:113) for a[0..n) in shared memory; returns cumsum[-1].
+// The reference's sequential sum is non-decreasing by construction.  A parallel scan groups the additions
+// differently, and where a term is smaller than the ulp of the running sum (density tails for small lambda)
+// a later prefix can round BELOW an earlier one.  The CDF merge needs sorted knots, so such entries are raised
+// to the running maximum (a change of at most the scan's own rounding error).  No extra barrier when the scan
+// is already monotone.
+__device__ __forceinline__ double block_cumsum(double* a, int n, double* red) {
+    block_scan(a, n, false, red);
+    int viol = 0;
+    for (int j = threadIdx.x + 1; j < n; j += blockDim.x) viol |= (a[j] < a[j - 1]);
+    double last = a[n - 1];
+    if (__syncthreads_or(viol)) {
+        block_running_max(a, n, red);
+        last = a[n - 1];
+        __syncthreads();
+    }
+    return last;
+}
+
 __device__ __forceinline__ int lower_bound_d(const double* a, int n, double v) {   // bisect_left
     int lo = 0, hi = n;
     while (lo < hi) {
@@ -105,9 +148,7 @@ __device__ __forceinline__ OtResult block_ot1d(const OtScratch& sc, int n, const
     r.amp = block_sum(part, sc.red);
     for (int j = tid; j < n; j += T) sc.cf[j] = sc.cf[j] / r.amp;
     __syncthreads();
-    block_scan(sc.cf, n, false, sc.red);
-    const double last = sc.cf[n - 1];
-    __syncthreads();
+    const double last = block_cumsum(sc.cf, n, sc.red);          // every thread has read cf[n-1] behind a barrier
     for (int j = tid; j < n; j += T) sc.cf[j] = sc.cf[j] / last;
     __syncthreads();
     // -- stable rank-merge of cf[:-1] and cg (:668-672)

@@ -86,6 +86,42 @@ __device__ __forceinline__ void load4(const void* row, int dtype, bool vec, int 
     }
 }
 
+// Running maximum over c[0..npad): a CDF that is not strictly increasing may hold prefix sums that the parallel
+// scan rounded out of order (terms below the ulp of the running sum; see block_cumsum in wfot_ot.cuh).  The
+// reference's sequential np.cumsum is non-decreasing by construction and the merge needs sorted knots, so such
+// entries of the (already rescaled) CDF are raised to the running maximum.  Only reached by non-strict CDFs
+// (rare), a no-op on sorted ones.
+__device__ __forceinline__ void warp_running_max(double* c, int n, int npad, double* cdf_out, int lane) {
+    double carry = -CUDART_INF;
+    for (int base = 0; base < npad; base += 128) {
+        const int idx = base + 4 * lane;
+        const double2 a0 = *reinterpret_cast<const double2*>(c + idx);
+        const double2 a1 = *reinterpret_cast<const double2*>(c + idx + 2);
+        double v0 = a0.x, v1 = fmax(v0, a0.y), v2 = fmax(v1, a1.x), v3 = fmax(v2, a1.y);
+        double inc = v3;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(kFull, inc, off);
+            if (lane >= off) inc = fmax(inc, o);
+        }
+        double excl = __shfl_up_sync(kFull, inc, 1);
+        excl = lane == 0 ? carry : fmax(excl, carry);
+        // the rescaled CDF ends at exactly 1: an earlier prefix that rounded above the last one is capped there
+        v0 = fmin(fmax(v0, excl), 1.0); v1 = fmin(fmax(v1, excl), 1.0);
+        v2 = fmin(fmax(v2, excl), 1.0); v3 = fmin(fmax(v3, excl), 1.0);
+        *reinterpret_cast<double2*>(c + idx) = make_double2(v0, v1);
+        *reinterpret_cast<double2*>(c + idx + 2) = make_double2(v2, v3);
+        if (cdf_out) {
+            if (idx < n) cdf_out[idx] = v0;
+            if (idx + 1 < n) cdf_out[idx + 1] = v1;
+            if (idx + 2 < n) cdf_out[idx + 2] = v2;
+            if (idx + 3 < n) cdf_out[idx + 3] = v3;
+        }
+        carry = fmax(carry, __shfl_sync(kFull, inc, 31));
+    }
+    __syncwarp();
+}
+
 // Register-resident OTpdf.__init__ for FP32 rows of n <= 1024 (16-byte aligned): the samples stay in
 // registers from the global load to the final CDF value, which is written to shared memory once
 // (the generic path below makes three shared-memory round trips).  Same arithmetic, same order.
@@ -174,6 +210,7 @@ __device__ __forceinline__ double warp_cdf_f32_1k(const float* fr, int n, int np
     }
     strict = __all_sync(kFull, ok);
     __syncwarp();
+    if (!strict) warp_running_max(c, n, npad, cdf_out, lane);
     return amp;
 }
 
@@ -278,6 +315,7 @@ __device__ __forceinline__ double warp_cdf(const void* row, int dtype, int n, in
     }
     strict = __all_sync(kFull, ok);
     __syncwarp();
+    if (!strict) warp_running_max(c, n, npad, cdf_out, lane);
     return amp;
 }
 
