@@ -569,6 +569,71 @@ def test_fused_random_shapes_stress(B):
                                            atol=1e-9 * max(np.abs(dr[i]).max(), 1e-300), err_msg=msg)
 
 
+def test_fused_variants_stress(B):
+    """Randomised fused calls over the API's options: FP32 / FP64 samples, theta != 45 deg, the in-kernel arctan
+    transform, per-window time axes / grids / observed windows, misfit-only calls, batches of up to 24 windows."""
+    n_env, seed = _stress_env()
+    rng = np.random.default_rng(seed + 3)
+    for _ in range(n_env or 6):
+        nt = int(rng.integers(3, 400 if n_env else 120))
+        nug = int(rng.integers(2, 150 if n_env else 70)); ntg = int(rng.integers(2, 150 if n_env else 70))
+        nb = int(rng.integers(1, 25 if nt * nug * ntg < 400000 else 4))
+        lam = float(rng.uniform(0.02, 0.15))
+        dtype = np.float32 if rng.random() < 0.4 else np.float64
+        transform = rng.random() < 0.3
+        theta = 45.0 if rng.random() < 0.6 else float(rng.uniform(25, 65))
+        per_window = rng.random() < 0.5
+        want_grad = rng.random() < 0.8
+        _, tant = O.resolve_theta(theta, 1.0)
+        tt = (np.sort(rng.random((nb, nt)), axis=1) * rng.uniform(0.5, 20) + rng.uniform(-5, 5)).astype(dtype)
+        if np.any(np.diff(tt.astype(np.float64), axis=1) <= 0):
+            continue
+        wp = (rng.standard_normal((nb, nt)).cumsum(axis=1) * rng.uniform(0.02, 2.0)).astype(dtype)
+        wo = (rng.standard_normal((nb, nt)).cumsum(axis=1) * rng.uniform(0.02, 2.0)).astype(dtype)
+        if not per_window:
+            tt, wo = np.repeat(tt[:1], nb, axis=0), np.repeat(wo[:1], nb, axis=0)
+        t64, wp64, wo64 = tt.astype(np.float64), wp.astype(np.float64), wo.astype(np.float64)
+        grids = []
+        for b in range(nb if per_window else 1):
+            sel = slice(b, b + 1) if per_window else slice(0, nb)
+            lo = min(wp64[sel].min(), wo64[sel].min()); hi = max(wp64[sel].max(), wo64[sel].max())
+            pad = 0.1 * (hi - lo) + 1e-3
+            grids.append((float(t64[b, 0]) - rng.uniform(0, 1), float(t64[b, -1]) + rng.uniform(0, 1),
+                          float(lo - pad), float(hi + pad), nug, ntg))
+        glist = grids if per_window else grids[0]
+        if transform:       # the observed window is transformed on the host; its amplitude box becomes (0, 1)
+            uo = np.stack([O.arctan_trans(wo64[b], *(grids[b if per_window else 0][2:4])) for b in range(nb)])
+            tgrids = [g[:2] + (0.0, 1.0, nug, ntg) for g in grids]
+        else:
+            uo, tgrids = wo64, grids
+        if per_window:
+            tg = B.Target.from_waveform(t64, uo, tgrids, nug, ntg, lam, tantheta=tant)
+        else:
+            tg = B.Target.from_waveform(t64[0], uo[0], tgrids[0], nug, ntg, lam, tantheta=tant)
+        r = B.misfit_grad_batch(tt if per_window else tt[0], wp, glist, nug, ntg, lam, tg, distfunc="W2",
+                                tantheta=tant, transform=transform, want_grad=want_grad)
+        torch.cuda.synchronize()
+        rt_w, rt_g = (1e-7, 1e-5) if transform else (1e-9, 1e-7)
+        for b in range(nb):
+            gb = grids[b if per_window else 0]
+            msg = (f"nt={nt} grid={nug}x{ntg} nb={nb} lam={lam} {dtype.__name__} transform={transform} "
+                   f"theta={theta} per_window={per_window} b={b}")
+            try:
+                _, tgt = O.build_ot_from_waveform(t64[b], wo64[b], gb, lambdav=lam, transform=transform, theta=theta)
+                W, dr, dg, _, _ = O.misfit_grad_window(t64[b], wp64[b], gb, tgt, lambdav=lam, distfunc="W2",
+                                                       theta=theta, transform=transform)
+            except O.TargetSourceCDFError:
+                assert int(r["status"].read()[1]) > 0, msg
+                continue
+            np.testing.assert_allclose(r["W"][b].cpu().numpy(), W, rtol=rt_w, err_msg=msg)
+            np.testing.assert_allclose(float(r["dwg"][b]) / (tant * (gb[1] - gb[0])), dg[0], rtol=10 * rt_w,
+                                       atol=1e-11 * max(1.0, float(np.abs(W).max())), err_msg=msg)
+            if want_grad:
+                for i in range(2):
+                    np.testing.assert_allclose(r["grad"][b, i].cpu().numpy(), dr[i], rtol=rt_g,
+                                               atol=rt_g * 1e-2 * max(np.abs(dr[i]).max(), 1e-300), err_msg=msg)
+
+
 def test_ot1d_random_stress(B):
     """Randomised 1-D OT against the oracle: random lengths (equal and unequal), FP32 / FP64 amplitudes,
     quantised amplitudes and zeros (repeated CDF values -> non-strict path), shared and per-pair x."""
