@@ -99,6 +99,8 @@ int wfot_device_cc(void);
  *   xray   (B, nug*ntg, 2) nearest point on the waveform         (:267)
  *   pdf    (B, nug, ntg) exp(-|d|/lambda) (q=0) or exp(-d^2/lambda) (q=2)  (:174,176)
  *   dddy   (B, nug*ntg, 2) d(d)/d(raw amplitude of the segment's end samples) (:385)
+ * Size limit: the FP32 segment table of a window stays in one SM's shared memory
+ * (20 B per sample), i.e. nt up to about 10 000; beyond that WFOT_ERR_UNSUPPORTED.
  */
 size_t wfot_fingerprint_workspace_bytes(int B, int nt, int nug, int ntg);
 int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
@@ -178,7 +180,11 @@ int wfot_ricker_batch(const double* params, int M, double t0, double t1,
  * (divide by tan(theta)*(t1-t0) as libs/ricker_util.py:333).
  * pmask is WFOT_W1 or WFOT_W2.  If transform != 0 the arctan amplitude
  * transform of libs/ricker_util.py:270-275 is applied in-kernel with each
- * grid's (u0,u1) and the gradient is multiplied by d(un)/du (:393-397). */
+ * grid's (u0,u1) and the gradient is multiplied by d(un)/du (:393-397).
+ * Size limit: sample coordinates, segment table, marginals and the OT scratch of a
+ * window share one SM's shared memory (about 36 B per sample + 40 B per grid point
+ * of the longer axis), i.e. nt up to about 6 000; beyond that WFOT_ERR_UNSUPPORTED
+ * (use the materialising entry points above). */
 size_t wfot_misfit_grad_workspace_bytes(int B, int nt, int nug, int ntg);
 int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
                            const wfot_grid* grids, int n_grids, int B, int nug, int ntg,
