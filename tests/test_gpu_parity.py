@@ -504,6 +504,9 @@ def test_fingerprint_random_shapes_stress(B):
             w = np.round(w, 1)                                   # plateaus / repeated values
         if kind == 3:
             w = np.abs(np.sin(np.linspace(0, 9, nt))) * 2
+        if rng.random() < 0.3:                                   # physical units: tiny amplitudes, epoch-like times
+            w = w * 10.0 ** rng.uniform(-9, 3)
+            t = t + 10.0 ** rng.uniform(3, 9)
         if np.any(np.diff(t) == 0):
             continue
         lo, hi = w.min(), w.max()
@@ -652,25 +655,31 @@ def test_ot1d_random_stress(B):
             f[:, 0] += 1; g[:, -1] += 1
         elif mode == 2:                                 # dyadic amplitudes: exact CDF collisions between f and g
             f = (np.round(f * 8) / 8 + 0.125).astype(dtype); g = (np.round(g * 8) / 8 + 0.125).astype(dtype)
-        xf = np.sort(rng.random(n)) if rng.random() < 0.5 else np.linspace(0, 1, n)
-        xg = xf if m == n and rng.random() < 0.5 else np.sort(rng.random(m)) + rng.uniform(-0.2, 0.2)
-        if np.any(np.diff(xf) <= 0) or np.any(np.diff(xg) <= 0):
+        per_pair = rng.random() < 0.3
+        shp = (nb,) if per_pair else ()
+        xf = np.sort(rng.random(shp + (n,)), axis=-1) if rng.random() < 0.5 else np.broadcast_to(np.linspace(0, 1, n), shp + (n,)).copy()
+        xg = xf if m == n and rng.random() < 0.5 else np.sort(rng.random(shp + (m,)), axis=-1) + rng.uniform(-0.2, 0.2)
+        if np.any(np.diff(xf, axis=-1) <= 0) or np.any(np.diff(xg, axis=-1) <= 0):
             continue
         deriv = (n == m)
-        r = B.ot1d_batch(f, g, xf, xg, "W12", derivatives=deriv)
+        distfunc = ("W1", "W2", "W12")[int(rng.integers(0, 3))]
+        r = B.ot1d_batch(f, g, xf, xg, distfunc, derivatives=deriv)
         torch.cuda.synchronize()
+        cols = {"W1": [0], "W2": [1], "W12": [0, 1]}[distfunc]
         for b in range(nb):
-            s, tt = O.otpdf(f[b].astype(np.float64), xf), O.otpdf(g[b].astype(np.float64), xg)
-            out = O.wasser(s, tt, "W12", derivatives=deriv, ignoreCommonCDFerror=True)
-            msg = f"n={n} m={m} {dtype.__name__} mode={mode} b={b}"
-            W = [out[0], out[3]] if deriv else [out[0], out[1]]
-            np.testing.assert_allclose(r["W"][b].cpu().numpy(), W, rtol=1e-9, atol=1e-15, err_msg=msg)
+            s = O.otpdf(f[b].astype(np.float64), xf[b] if per_pair else xf)
+            tt = O.otpdf(g[b].astype(np.float64), xg[b] if per_pair else xg)
+            out = O.wasser(s, tt, distfunc, derivatives=deriv, ignoreCommonCDFerror=True)
+            msg = f"n={n} m={m} {dtype.__name__} mode={mode} {distfunc} per_pair={per_pair} b={b}"
+            W = out[0::3] if deriv else out
+            np.testing.assert_allclose(r["W"][b].cpu().numpy()[cols], W, rtol=1e-9, atol=1e-15, err_msg=msg)
             if deriv:
-                np.testing.assert_allclose(r["dpos"][b].cpu().numpy(), [out[2], out[5]], rtol=1e-8, atol=1e-11,
+                np.testing.assert_allclose(r["dpos"][b].cpu().numpy()[cols], out[2::3], rtol=1e-8, atol=1e-11,
                                            err_msg=msg)
                 if mode == 0:       # with ties the amplitude derivative depends on np.argsort's unstable order
-                    np.testing.assert_allclose(r["dW1"][b].cpu().numpy(), out[1], rtol=1e-7, atol=1e-10, err_msg=msg)
-                    np.testing.assert_allclose(r["dW2"][b].cpu().numpy(), out[4], rtol=1e-7, atol=1e-10, err_msg=msg)
+                    for c, dw in zip(cols, out[1::3]):
+                        np.testing.assert_allclose(r["dW1" if c == 0 else "dW2"][b].cpu().numpy(), dw, rtol=1e-7,
+                                                   atol=1e-10, err_msg=msg)
 
 
 def test_fused_tail_cdf_monotone_regression(B):
