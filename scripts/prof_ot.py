@@ -1,5 +1,5 @@
 """Timing / ncu driver for the batched 1-D OT kernel (cfg2 shape), outputs preallocated, C ABI called directly.
-usage: prof_ot.py <pairs> [reps]"""
+usage: prof_ot.py <pairs> [reps] [bins]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -8,7 +8,7 @@ from waveform_ot_b200 import batch as B
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-n = 1024
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 dev = "cuda"
 f = torch.rand(nb, n, device=dev) + 1e-3
 g = torch.rand(nb, n, device=dev) + 1e-3
@@ -28,13 +28,13 @@ def run(pmask, deriv):
 
 
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for name, pm, dv, bytes_alg, bytes_moved in (("W12+dW1+dW2", 3, 1, 12288, 24576), ("W2+dW2", 2, 1, 12288, 16384),
-                                             ("W12 only", 3, 0, 8192, 8192)):
+for name, pm, dv, bytes_alg, bytes_moved in (("W12+dW1+dW2", 3, 1, 12 * n, 24 * n), ("W2+dW2", 2, 1, 12 * n, 16 * n),
+                                             ("W12 only", 3, 0, 8 * n, 8 * n)):
     run(pm, dv); torch.cuda.synchronize()
     best = 1e30
     for _ in range(reps):
         s.record(); run(pm, dv); e.record(); torch.cuda.synchronize()
         best = min(best, s.elapsed_time(e))
-    print("ot1d %-12s B=%d %.3f ms  %.2f Mpairs/s  %.0f GB/s algorithmic (SURVEY 8d: 12 KiB/pair)  %.0f GB/s moved" % (
-        name, nb, best, nb / best / 1e3, nb * 12288 / best / 1e6, nb * bytes_moved / best / 1e6))
+    print("ot1d %-12s B=%d n=%d %.3f ms  %.2f Mpairs/s  %.1f Gknots/s  %.0f GB/s algorithmic (SURVEY 8d: 12 B/bin/pair)  %.0f GB/s moved" % (
+        name, nb, n, best, nb / best / 1e3, nb * (2 * n - 1) / best / 1e6, nb * bytes_alg / best / 1e6, nb * bytes_moved / best / 1e6))
 print("ok")
