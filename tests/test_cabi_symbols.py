@@ -45,7 +45,7 @@ def test_sass_is_blackwell_packed_fp32():
     out = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     for op in ("FFMA2", "FMUL2", "FMNMX3", "FADD.SAT",
-               "CREDUX.MAX",            # warp-uniform pruning bound of the scan (one instruction per evaluated tile)
+               "VOTE.ANY",              # per-lane tile pruning of the scan: one vote per tile
                "ATOMG.E.ADD.F64",       # gradient assembly: native FP64 reductions in L2
                "UCGABAR_ARV"):          # thread-block cluster barrier (one window per cluster for small batches)
         assert op in out, op

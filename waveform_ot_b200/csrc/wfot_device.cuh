@@ -334,12 +334,16 @@ __device__ __forceinline__ LaneBlock lane_block(const FootMap& m, int f, int lan
 // among the tiles that were evaluated.
 //
 // Exact pruning (must be called by all 32 lanes of a converged warp; `fp` is the bounding box of
-// the warp's pixels).  Tiles are visited outwards from the one nearest in time to the footprint
-// centre.  A tile is skipped when the distance `lb` between its bounding box and the footprint
-// satisfies lb (1 - 2e-6) - 4e-6 > sqrt(max over the warp's pixels of the running minimum b1):
-// every FP32 distance of such a tile exceeds b1 + tau32(b1) of every pixel of the warp (the FP32
-// rounding tolerance is 1.25e-6 absolute + 1.5e-7 relative in distance units, see tau32), so the
-// tile can neither hold the FP64 nearest segment nor a near-tie the resolve step has to look at.
+// the warp's pixels and only picks the start tile).  Tiles are visited outwards from the one nearest
+// in time to the footprint centre.  Every lane tests a tile against ITS OWN pixel block: the tile is
+// of no interest to the lane when the distance `lb` between the tile's bounding box and the block's
+// satisfies lb (1 - 2e-6) - 4e-6 > sqrt(max over the lane's pixels of the running minimum b1): every
+// FP32 distance of such a tile exceeds b1 + tau32(b1) of every pixel of the lane (the FP32 rounding
+// tolerance is 1.25e-6 absolute + 1.5e-7 relative in distance units, see tau32), so the tile can
+// neither hold the FP64 nearest segment nor a near-tie the resolve step has to look at.  The warp
+// skips a tile that no lane is interested in (one vote).  Testing per lane instead of against the
+// warp-wide maximum of b1 roughly halves the evaluated tiles: the far corner of a 16 x 16 pixel
+// footprint no longer keeps tiles alive that are only close to the opposite corner.
 template <int R, int T>
 __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& fp, float px0, float px1,
                                            const float (&py)[R],
@@ -364,8 +368,11 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
         for (int i = 0; i < ntiles && ct < ntiles - 1 && tb.bbox[ct].y < xc; ++i) ++ct;
         for (int i = 0; i < ntiles && ct > 0 && tb.bbox[ct].x > xc; ++i) --ct;
     }
-    // thr2 = ((sqrt(wmax) + 4e-6) / (1 - 2e-6))^2: a tile whose squared box distance exceeds it cannot matter
-    float thr2 = kBig;   // from wmax = max over the warp's pixels of b1 (warp-uniform), updated per evaluated tile
+    // the lane's pixel block in the scaled frame
+    const float qx0 = fminf(px0, px1), qx1 = fmaxf(px0, px1);
+    const float qy0 = fminf(py[0], py[R - 1]), qy1 = fmaxf(py[0], py[R - 1]);
+    // thr2 = ((sqrt(lmax) + 4e-6) / (1 - 2e-6))^2: a tile whose squared box distance exceeds it cannot matter
+    float thr2 = kBig;   // from lmax = max over the lane's pixels of b1, updated per evaluated tile
     // walk outwards from ct, alternating sides: r = next tile on the right (starts AT ct), l = next on the left;
     // on a time-ordered table a side is closed (r = ntiles / l = -1) once the time gap alone exceeds the bound
     int l = ct - 1, r = ct;
@@ -378,11 +385,13 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
         go_right = !right;
         {
             const float4 bb = tb.bbox[tile];
-            const float dx = fmaxf(0.f, fmaxf(bb.x - fp.x1, fp.x0 - bb.y));
-            const float dy = fmaxf(0.f, fmaxf(bb.z - fp.y1, fp.y0 - bb.w));
+            const float dx = fmaxf(0.f, fmaxf(bb.x - qx1, qx0 - bb.y));
+            const float dy = fmaxf(0.f, fmaxf(bb.z - qy1, qy0 - bb.w));
             const float dx2 = dx * dx;
-            if (__fmaf_rn(dy, dy, dx2) > thr2) {
-                if (tb.mono && dx2 > thr2) { if (right) r = ntiles; else l = -1; }
+            if (!__any_sync(0xffffffffu, !(__fmaf_rn(dy, dy, dx2) > thr2))) {
+                // time-ordered table: once the time gap alone rules the tile out for every lane, so does
+                // every tile further out on this side
+                if (tb.mono && __all_sync(0xffffffffu, dx2 > thr2)) { if (right) r = ntiles; else l = -1; }
                 continue;
             }
         }
@@ -439,9 +448,7 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
             b1[k] = fminf(b1[k], tm[k]);
             mx = fmaxf(mx, b1[k]);
         }
-        // non-negative floats order like their bit patterns: one REDUX gives the warp maximum
-        const float wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
-        const float tq = (sqrtf(wmax) + 4.0e-6f) * 1.000002f;
+        const float tq = (sqrtf(mx) + 4.0e-6f) * 1.000002f;
         thr2 = tq * tq;
     }
 }
