@@ -334,21 +334,24 @@ __device__ __forceinline__ LaneBlock lane_block(const FootMap& m, int f, int lan
 // among the tiles that were evaluated.
 //
 // Exact pruning (must be called by all 32 lanes of a converged warp; `fp` is the bounding box of
-// the warp's pixels and only picks the start tile).  Tiles are visited outwards from the one nearest
-// in time to the footprint centre.  Every lane tests a tile against ITS OWN pixel block: the tile is
-// of no interest to the lane when the distance `lb` between the tile's bounding box and the block's
-// satisfies lb (1 - 2e-6) - 4e-6 > sqrt(max over the lane's pixels of the running minimum b1): every
-// FP32 distance of such a tile exceeds b1 + tau32(b1) of every pixel of the lane (the FP32 rounding
+// the warp's pixels).  Tiles are visited BEST FIRST: in the order of the distance between their
+// bounding box and the footprint box, so the running minima tighten as early as possible.  Every lane
+// keeps the keys (distance bits | tile index) of the tiles it owns (tile % 32 == lane) in `keys`
+// (shared memory, >= Spad / T entries per warp); one warp minimum (REDUX) pops the next tile.
+// Every lane tests a popped tile against ITS OWN pixel block: the tile is of no interest to the lane
+// when the distance `lb` between the tile's bounding box and the block's satisfies
+// lb (1 - 2e-6) - 4e-6 > sqrt(max over the lane's pixels of the running minimum b1): every FP32
+// distance of such a tile exceeds b1 + tau32(b1) of every pixel of the lane (the FP32 rounding
 // tolerance is 1.25e-6 absolute + 1.5e-7 relative in distance units, see tau32), so the tile can
 // neither hold the FP64 nearest segment nor a near-tie the resolve step has to look at.  The warp
-// skips a tile that no lane is interested in (one vote).  Testing per lane instead of against the
-// warp-wide maximum of b1 roughly halves the evaluated tiles: the far corner of a 16 x 16 pixel
-// footprint no longer keeps tiles alive that are only close to the opposite corner.
+// skips a tile that no lane is interested in (one vote), and stops as soon as the popped key - a
+// lower bound of the box distance of every remaining tile to every lane's block, which lies inside
+// the footprint - fails that test for all lanes.
 template <int R, int T>
 __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& fp, float px0, float px1,
                                            const float (&py)[R],
                                            float (&b1)[2 * R], int (&t1)[2 * R], float (&b2)[2 * R],
-                                           float (&b3)[2 * R], int& tiles_done) {
+                                           float (&b3)[2 * R], int& tiles_done, unsigned* __restrict__ keys) {
     static_assert(R % 2 == 0, "rows are processed in pairs");
     const uint64_t px2 = pack2(px0, px1);
     uint64_t y2[R / 2];
@@ -357,43 +360,39 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
 #pragma unroll
     for (int k = 0; k < 2 * R; ++k) { b1[k] = kBig; b2[k] = kBig; b3[k] = kBig; t1[k] = 0; }
     const int ntiles = tb.Spad / T;
-    // start tile: the one whose time span holds the footprint centre (segments are normally time ordered;
-    // any start is correct, a poor one only prunes less)
-    int ct;
-    {
-        const float xc = 0.5f * (fp.x0 + fp.x1);
-        const float xa = tb.bbox[0].x, xb = tb.bbox[ntiles - 1].y;
-        const float fr = (xb != xa) ? (xc - xa) / (xb - xa) : 0.f;
-        ct = min(max((int)(fr * (float)ntiles), 0), ntiles - 1);
-        for (int i = 0; i < ntiles && ct < ntiles - 1 && tb.bbox[ct].y < xc; ++i) ++ct;
-        for (int i = 0; i < ntiles && ct > 0 && tb.bbox[ct].x > xc; ++i) --ct;
+    const int lane = threadIdx.x & 31;
+    // keys: squared box distance to the footprint (low bits dropped: still a lower bound) | tile index
+    const unsigned idxmask = ntiles > 1 ? (0xffffffffu >> __clz(ntiles - 1)) : 0u;
+    unsigned mykey = 0xffffffffu;
+    for (int tile = lane; tile < ntiles; tile += 32) {
+        const float4 bb = tb.bbox[tile];
+        const float dx = fmaxf(0.f, fmaxf(bb.x - fp.x1, fp.x0 - bb.y));
+        const float dy = fmaxf(0.f, fmaxf(bb.z - fp.y1, fp.y0 - bb.w));
+        const unsigned key = (__float_as_uint(__fmaf_rn(dy, dy, dx * dx)) & ~idxmask) | (unsigned)tile;
+        keys[tile] = key;
+        mykey = min(mykey, key);
     }
     // the lane's pixel block in the scaled frame
     const float qx0 = fminf(px0, px1), qx1 = fmaxf(px0, px1);
     const float qy0 = fminf(py[0], py[R - 1]), qy1 = fmaxf(py[0], py[R - 1]);
     // thr2 = ((sqrt(lmax) + 4e-6) / (1 - 2e-6))^2: a tile whose squared box distance exceeds it cannot matter
     float thr2 = kBig;   // from lmax = max over the lane's pixels of b1, updated per evaluated tile
-    // walk outwards from ct, alternating sides: r = next tile on the right (starts AT ct), l = next on the left;
-    // on a time-ordered table a side is closed (r = ntiles / l = -1) once the time gap alone exceeds the bound
-    int l = ct - 1, r = ct;
-    bool go_right = true;
-    while (l >= 0 || r < ntiles) {
-        const bool right = (r < ntiles) && (go_right || l < 0);
-        const int tile = right ? r : l;
-        r += right ? 1 : 0;
-        l -= right ? 0 : 1;
-        go_right = !right;
+    while (true) {
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, mykey);
+        if (kmin == 0xffffffffu) break;                                  // every tile visited
+        if (__all_sync(0xffffffffu, __uint_as_float(kmin & ~idxmask) > thr2)) break;
+        const int tile = (int)(kmin & idxmask);
+        if (mykey == kmin) {                                             // the owner pops it and finds its next key
+            keys[tile] = 0xffffffffu;
+            unsigned m = 0xffffffffu;
+            for (int t2 = lane; t2 < ntiles; t2 += 32) m = min(m, keys[t2]);
+            mykey = m;
+        }
         {
             const float4 bb = tb.bbox[tile];
             const float dx = fmaxf(0.f, fmaxf(bb.x - qx1, qx0 - bb.y));
             const float dy = fmaxf(0.f, fmaxf(bb.z - qy1, qy0 - bb.w));
-            const float dx2 = dx * dx;
-            if (!__any_sync(0xffffffffu, !(__fmaf_rn(dy, dy, dx2) > thr2))) {
-                // time-ordered table: once the time gap alone rules the tile out for every lane, so does
-                // every tile further out on this side
-                if (tb.mono && __all_sync(0xffffffffu, dx2 > thr2)) { if (right) r = ntiles; else l = -1; }
-                continue;
-            }
+            if (!__any_sync(0xffffffffu, !(__fmaf_rn(dy, dy, dx * dx) > thr2))) continue;
         }
         ++tiles_done;
         float tm[2 * R];

@@ -37,7 +37,7 @@ struct FQEntry { int pix; float b1; };
 // from the `extern __shared__` symbol inside each kernel so the compiler keeps them in the
 // shared address space (LDS/STS instead of generic loads).
 struct SmemLayout {
-    int pn, A, H, bbox, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
+    int pn, A, H, bbox, keys, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
     int total;
 };
 
@@ -51,7 +51,9 @@ __host__ __device__ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad,
     const int ubase = o;
     L.A = take(Spad * 16);
     L.H = take(Spad * 4);
-    L.bbox = take((Spad / kTileMin) * 16);
+    const int ntiles = Spad / tile_for(nt);
+    L.bbox = take(ntiles * 16);
+    L.keys = take(8 * ntiles * 4);                // best-first tile keys, one array per warp (<= 8 warps)
     const int uend_scan = o;
     o = ubase;
     L.cf = take(nmax * 8);
@@ -98,6 +100,7 @@ struct FusedArgs {
     float4* const s_A = reinterpret_cast<float4*>(smem_raw + (L).A);                     \
     float* const s_H = reinterpret_cast<float*>(smem_raw + (L).H);                       \
     float4* const s_bbox = reinterpret_cast<float4*>(smem_raw + (L).bbox);               \
+    unsigned* const s_keys = reinterpret_cast<unsigned*>(smem_raw + (L).keys);           \
     float* const s_pxs = reinterpret_cast<float*>(smem_raw + (L).pxs);                   \
     float* const s_pys = reinterpret_cast<float*>(smem_raw + (L).pys);                   \
     double* const s_margt = reinterpret_cast<double*>(smem_raw + (L).margt);             \
@@ -196,7 +199,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
             for (int r = 0; r < R; ++r) py[r] = s_pys[min(rg * R + r, a.nug - 1)];
             float b1[2 * R], b2[2 * R], b3[2 * R];
             int t1[2 * R];
-            scan_block<R, T>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles);
+            scan_block<R, T>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles,
+                             s_keys + (threadIdx.x >> 5) * (a.Spad / T));
             if (!lb.owns) continue;
             float lb1[2 * R], lb2[2 * R], lb3[2 * R];
             int lt1[2 * R];
@@ -394,7 +398,8 @@ __global__ void __launch_bounds__(256, 2) k_scan_probe(FusedArgs a, float* out) 
             for (int r = 0; r < R; ++r) py[r] = s_pys[min(rg * R + r, a.nug - 1)];
             float b1[2 * R], b2[2 * R], b3[2 * R];
             int t1[2 * R];
-            scan_block<R, 16>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles);
+            scan_block<R, 16>(tb, lb.fp, s_pxs[it0], s_pxs[it1], py, b1, t1, b2, b3, tiles,
+                              s_keys + (threadIdx.x >> 5) * (a.Spad / 16));
             if (!lb.owns) continue;
 #pragma unroll
             for (int k = 0; k < 2 * R; ++k) {

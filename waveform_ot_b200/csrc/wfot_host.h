@@ -24,7 +24,7 @@ struct FpWorkspace {
 
 inline int seg_pad(int nt) { return ((nt - 1 + kTilePad - 1) / kTilePad) * kTilePad; }
 // argmin tile size: short waveforms use 8-segment tiles (fewer FP32 re-evaluations per pixel, finer pruning)
-inline int tile_for(int nt) { return (nt - 1 <= 256) ? 8 : 16; }
+__host__ __device__ inline int tile_for(int nt) { return (nt - 1 <= 256) ? 8 : 16; }
 inline int pad4(int n) { return (n + 3) & ~3; }
 
 inline size_t fp_workspace_per_window(int nt, int nug, int ntg) {

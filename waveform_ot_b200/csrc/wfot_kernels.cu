@@ -91,10 +91,11 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     const int Spad = a.ws.Spad, S = a.nt - 1;
     float4* sA = reinterpret_cast<float4*>(smem_raw);
     float4* sBB = sA + Spad;
-    float* sH = reinterpret_cast<float*>(sBB + Spad / kTileMin);
+    float* sH = reinterpret_cast<float*>(sBB + Spad / T);
     float* sPx = sH + Spad;
     float* sPy = sPx + a.ws.ntg_pad;
     QEntry* queue = reinterpret_cast<QEntry*>(sPy + a.ws.nug_pad);
+    unsigned* sKeys = reinterpret_cast<unsigned*>(queue + kQCap) + (threadIdx.x >> 5) * (Spad / T);   // this warp's tile keys
     __shared__ int qcount;
     __shared__ WinHdr hdr;
     const int tid = threadIdx.x;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
         for (int r = 0; r < R; ++r) py[r] = sPy[min(rg * R + r, a.nug - 1)];
         float b1[2 * R], b2[2 * R], b3[2 * R];
         int t1[2 * R];
-        scan_block<R, T>(tb, lb.fp, sPx[it0], sPx[it1], py, b1, t1, b2, b3, tiles);
+        scan_block<R, T>(tb, lb.fp, sPx[it0], sPx[it1], py, b1, t1, b2, b3, tiles, sKeys);
         if (lb.owns) {
         // The epilogue is deliberately NOT unrolled (FP64 division/exp per pixel would
         // multiply the code size by 2R); the scan results move to local arrays first.
@@ -471,9 +472,12 @@ int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long
     if (chunk > kFpChunk) chunk = kFpChunk;
     FpWorkspace ws = fp_workspace_carve((void*)base, chunk, nt, nug, ntg);
     constexpr int R = 4;
-    const size_t smem = (size_t)ws.Spad * 20 + (size_t)(ws.Spad / kTileMin) * 16 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry);
-    if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
     const int T = tile_for(nt);
+    const size_t ntiles = (size_t)(ws.Spad / T);
+    // segment table (20 B / segment) + tile boxes + pixel axes + slow-pixel queue + best-first tile keys (8 warps)
+    const size_t smem = (size_t)ws.Spad * 20 + ntiles * 16 + (size_t)(ws.ntg_pad + ws.nug_pad) * 4 + kQCap * sizeof(QEntry) +
+                        8 * ntiles * 4;
+    if (smem > 220 * 1024) return WFOT_ERR_UNSUPPORTED;
     cudaError_t e = T == 8 ? cudaFuncSetAttribute(k_fingerprint<R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                            : cudaFuncSetAttribute(k_fingerprint<R, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_fingerprint)");
