@@ -41,7 +41,7 @@ struct SmemLayout {
     int total;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nmax) {
+inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nmax) {
     SmemLayout L;
     int o = 0;
     auto take = [&](int bytes) { const int at = o; o += (bytes + 15) & ~15; return at; };

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "wfot_device.cuh"
 
@@ -23,8 +24,12 @@ struct FpWorkspace {
 };
 
 inline int seg_pad(int nt) { return ((nt - 1 + kTilePad - 1) / kTilePad) * kTilePad; }
-// argmin tile size: short waveforms use 8-segment tiles (fewer FP32 re-evaluations per pixel, finer pruning)
-__host__ __device__ inline int tile_for(int nt) { return (nt - 1 <= 256) ? 8 : 16; }
+// argmin tile size: 8-segment tiles (fewer FP32 re-evaluations per pixel, finer pruning) unless the window is so long
+// that the per-tile bookkeeping of the best-first walk would dominate
+inline int tile_for(int nt) {
+    if (const char* e = getenv("WFOT_DEV_TILE")) return atoi(e) == 8 ? 8 : 16;   // development override
+    return (nt - 1 <= 2048) ? 8 : 16;
+}
 inline int pad4(int n) { return (n + 3) & ~3; }
 
 inline size_t fp_workspace_per_window(int nt, int nug, int ntg) {
