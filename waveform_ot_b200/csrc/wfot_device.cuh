@@ -363,15 +363,27 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
     const int lane = threadIdx.x & 31;
     // keys: squared box distance to the footprint (low bits dropped: still a lower bound) | tile index
     const unsigned idxmask = ntiles > 1 ? (0xffffffffu >> __clz(ntiles - 1)) : 0u;
-    unsigned mykey = 0xffffffffu;
-    for (int tile = lane; tile < ntiles; tile += 32) {
+    // a lane owns the tiles lane, lane + 32, ...: the first kRegKeys of them live in registers, the rest in `keys`
+    constexpr int kRegKeys = 4;
+    constexpr unsigned kNoKey = 0xffffffffu;
+    unsigned kr[kRegKeys];
+    unsigned kmem = kNoKey;                      // minimum of the lane's keys kept in shared memory
+#pragma unroll
+    for (int i = 0; i < kRegKeys; ++i) kr[i] = kNoKey;
+    for (int i = 0, tile = lane; tile < ntiles; ++i, tile += 32) {
         const float4 bb = tb.bbox[tile];
         const float dx = fmaxf(0.f, fmaxf(bb.x - fp.x1, fp.x0 - bb.y));
         const float dy = fmaxf(0.f, fmaxf(bb.z - fp.y1, fp.y0 - bb.w));
         const unsigned key = (__float_as_uint(__fmaf_rn(dy, dy, dx * dx)) & ~idxmask) | (unsigned)tile;
-        keys[tile] = key;
-        mykey = min(mykey, key);
+        if (i < kRegKeys) {
+#pragma unroll
+            for (int q = 0; q < kRegKeys; ++q) kr[q] = (q == i) ? key : kr[q];
+        } else {
+            keys[tile] = key;
+            kmem = min(kmem, key);
+        }
     }
+    unsigned mykey = min(min(min(kr[0], kr[1]), min(kr[2], kr[3])), kmem);
     // the lane's pixel block in the scaled frame
     const float qx0 = fminf(px0, px1), qx1 = fmaxf(px0, px1);
     const float qy0 = fminf(py[0], py[R - 1]), qy1 = fmaxf(py[0], py[R - 1]);
@@ -379,15 +391,18 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
     float thr2 = kBig;   // from lmax = max over the lane's pixels of b1, updated per evaluated tile
     while (true) {
         const unsigned kmin = __reduce_min_sync(0xffffffffu, mykey);
-        if (kmin == 0xffffffffu) break;                                  // every tile visited
+        if (kmin == kNoKey) break;                                       // every tile visited
         if (__all_sync(0xffffffffu, __uint_as_float(kmin & ~idxmask) > thr2)) break;
         const int tile = (int)(kmin & idxmask);
-        if (mykey == kmin) {                                             // the owner pops it and finds its next key
-            keys[tile] = 0xffffffffu;
-            unsigned m = 0xffffffffu;
-            for (int t2 = lane; t2 < ntiles; t2 += 32) m = min(m, keys[t2]);
-            mykey = m;
+        // the owner drops the key (branch-free for the register keys) and every lane re-derives its minimum
+#pragma unroll
+        for (int q = 0; q < kRegKeys; ++q) kr[q] = (kr[q] == kmin) ? kNoKey : kr[q];
+        if (kmem == kmin) {                                              // long windows only: rescan the lane's keys in memory
+            keys[tile] = kNoKey;
+            kmem = kNoKey;
+            for (int t2 = lane + 32 * kRegKeys; t2 < ntiles; t2 += 32) kmem = min(kmem, keys[t2]);
         }
+        mykey = min(min(min(kr[0], kr[1]), min(kr[2], kr[3])), kmem);
         {
             const float4 bb = tb.bbox[tile];
             const float dx = fmaxf(0.f, fmaxf(bb.x - qx1, qx0 - bb.y));
