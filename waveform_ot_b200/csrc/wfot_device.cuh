@@ -395,14 +395,18 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
         if (__all_sync(0xffffffffu, __uint_as_float(kmin & ~idxmask) > thr2)) break;
         const int tile = (int)(kmin & idxmask);
         // the owner drops the key (branch-free for the register keys) and every lane re-derives its minimum
+        if (ntiles <= 32) {                                              // short windows: one key per lane
+            mykey = (mykey == kmin) ? kNoKey : mykey;
+        } else {
 #pragma unroll
-        for (int q = 0; q < kRegKeys; ++q) kr[q] = (kr[q] == kmin) ? kNoKey : kr[q];
-        if (kmem == kmin) {                                              // long windows only: rescan the lane's keys in memory
-            keys[tile] = kNoKey;
-            kmem = kNoKey;
-            for (int t2 = lane + 32 * kRegKeys; t2 < ntiles; t2 += 32) kmem = min(kmem, keys[t2]);
+            for (int q = 0; q < kRegKeys; ++q) kr[q] = (kr[q] == kmin) ? kNoKey : kr[q];
+            if (kmem == kmin) {                                          // long windows only: rescan the lane's keys in memory
+                keys[tile] = kNoKey;
+                kmem = kNoKey;
+                for (int t2 = lane + 32 * kRegKeys; t2 < ntiles; t2 += 32) kmem = min(kmem, keys[t2]);
+            }
+            mykey = min(min(min(kr[0], kr[1]), min(kr[2], kr[3])), kmem);
         }
-        mykey = min(min(min(kr[0], kr[1]), min(kr[2], kr[3])), kmem);
         {
             const float4 bb = tb.bbox[tile];
             const float dx = fmaxf(0.f, fmaxf(bb.x - qx1, qx0 - bb.y));
