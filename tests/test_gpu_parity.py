@@ -734,21 +734,25 @@ def test_long_windows(B):
     tables exceed what the fused kernel can keep in one SM's shared memory (about 6 000 samples) must make the
     fused call fail loudly, while the materialising path (segment table only, about 10 000 samples) still works."""
     rng = np.random.default_rng(31)
-    nt, nug, ntg, lam = 3000, 40, 50, 0.05
-    t = np.linspace(0.0, 5.0, nt)
-    w = rng.standard_normal((2, nt)).cumsum(axis=1) * 0.02
-    grid = (0.0, 5.0, float(w.min()) - 0.2, float(w.max()) + 0.2, nug, ntg)
-    out = B.fingerprint_batch(t, w[1:], grid, nug, ntg, lam, deriv=True)
-    torch.cuda.synchronize()
-    _check_fields(out, _oracle_window(t, w[1], grid, lam))
-    tg = B.Target.from_waveform(t, w[0], grid, nug, ntg, lam)
-    r = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg)
-    torch.cuda.synchronize()
-    _, tgt = O.build_ot_from_waveform(t, w[0], grid, lambdav=lam)
-    W, dr, dg, _, _ = O.misfit_grad_window(t, w[1], grid, tgt, lambdav=lam)
-    np.testing.assert_allclose(r["W"][0].cpu().numpy(), W, rtol=1e-9)
-    for i in range(2):
-        np.testing.assert_allclose(r["grad"][0, i].cpu().numpy(), dr[i], rtol=1e-7, atol=1e-9 * np.abs(dr[i]).max())
+    nug, ntg, lam = 40, 50, 0.05
+    # 1500 / 2049 samples: 8-segment tiles with more tile keys per lane than fit in registers;
+    # 2050 / 3000 samples: 16-segment tiles
+    for nt in (1500, 2049, 2050, 3000):
+        t = np.linspace(0.0, 5.0, nt)
+        w = rng.standard_normal((2, nt)).cumsum(axis=1) * 0.02
+        grid = (0.0, 5.0, float(w.min()) - 0.2, float(w.max()) + 0.2, nug, ntg)
+        out = B.fingerprint_batch(t, w[1:], grid, nug, ntg, lam, deriv=True)
+        torch.cuda.synchronize()
+        _check_fields(out, _oracle_window(t, w[1], grid, lam))
+        tg = B.Target.from_waveform(t, w[0], grid, nug, ntg, lam)
+        r = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg)
+        torch.cuda.synchronize()
+        _, tgt = O.build_ot_from_waveform(t, w[0], grid, lambdav=lam)
+        W, dr, dg, _, _ = O.misfit_grad_window(t, w[1], grid, tgt, lambdav=lam)
+        np.testing.assert_allclose(r["W"][0].cpu().numpy(), W, rtol=1e-9)
+        for i in range(2):
+            np.testing.assert_allclose(r["grad"][0, i].cpu().numpy(), dr[i], rtol=1e-7,
+                                       atol=1e-9 * np.abs(dr[i]).max())
     nt = 9000
     t = np.linspace(0.0, 5.0, nt)
     w = rng.standard_normal((2, nt)).cumsum(axis=1) * 0.01
