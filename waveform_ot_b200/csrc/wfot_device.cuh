@@ -125,8 +125,13 @@ __device__ __forceinline__ void eval64(const double2* __restrict__ pn, int s, do
     const double L = __dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy));   // lsq_n (:113)
     const double bx = __dsub_rn(px, a.x);                      // b = p - x0 (:256)
     const double by = __dsub_rn(py, a.y);
-    double l = __ddiv_rn(__dadd_rn(__dmul_rn(bx, cx), __dmul_rn(by, cy)), L);   // (:257)
-    l = fmin(fmax(l, 0.0), 1.0);                               // np.clip
+    const double num = __dadd_rn(__dmul_rn(bx, cx), __dmul_rn(by, cy));
+    // (:257) lam = clip(num / L, 0, 1).  The quotient is only needed when the projection falls inside the segment:
+    // num <= 0 clips to 0 and num >= L clips to 1 whatever the rounding of the division (L > 0), so pixels whose
+    // nearest point is a vertex - most pixels away from the waveform - skip the FP64 division (warp-uniformly for
+    // whole warps of such pixels).  A zero-length segment has num = 0 -> 0, as before.
+    double l = (num <= 0.0) ? 0.0 : 1.0;
+    if (num > 0.0 && num < L) l = fmin(fmax(__ddiv_rn(num, L), 0.0), 1.0);   // np.clip
     const double dx = __dsub_rn(bx, __dmul_rn(cx, l));         // ds = b - c*lam (:258)
     const double dy = __dsub_rn(by, __dmul_rn(cy, l));
     D = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));       // (:259)
