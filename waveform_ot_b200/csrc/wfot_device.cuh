@@ -67,8 +67,7 @@ struct WinHdr {
     double sigma;              // power-of-two scale of the FP32 frame
     double du;                 // u1 - u0 (raw amplitude box)
     double u0raw, u1raw;       // raw amplitude box before an arctan transform
-    int degenerate;            // number of zero-length segments          } both zeroed by the caller
-    int nonmono;               // number of time-reversed segments        } before prep_window()
+    int degenerate;            // number of zero-length segments (zeroed by the caller before prep_window())
 };
 
 // FP32 segment table in the rotated frame (shared or global memory)
@@ -79,7 +78,6 @@ struct SegTable {
     int S;             // real segments
     int Spad;          // padded to a multiple of kTilePad
     int tile;          // segments per tile (8 or 16)
-    bool mono;         // sample times are non-decreasing: tiles are ordered along the time axis
 };
 
 // Pixel footprint of one warp in the scaled frame (warp-uniform): the scan skips every segment
@@ -568,14 +566,13 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
     const double sigma = ldexp(1.0, -ex);
     const int S = nt - 1;
     const int Spad = ((S + kTilePad - 1) / kTilePad) * kTilePad;
-    int degen = 0, nonmono = 0;
+    int degen = 0;
     for (int s = tid; s < Spad; s += nth) {
         float4 A;
         float h;
         if (s < S) {
             const double2 a = o.pn[s], b = o.pn[s + 1];
             const double cx = b.x - a.x, cy = b.y - a.y;
-            nonmono += !(cx >= 0.0);
             const double len = sqrt(cx * cx + cy * cy);
             double exd = 1.0, eyd = 0.0;
             if (len > 0.0) { exd = cx / len; eyd = cy / len; } else { degen++; }
@@ -606,7 +603,6 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
     for (int i = tid; i < nug; i += nth)
         o.pys[i] = (float)((lin_axis(U0, Us, Ul, i, nug) - ccy) * sigma);
     if (degen) atomicAdd(&o.hdr->degenerate, degen);   // zeroed by the caller before prep_window
-    if (nonmono) atomicAdd(&o.hdr->nonmono, nonmono);
     if (tid == 0) {
         WinHdr* h = o.hdr;
         h->T0 = T0; h->Tstep = Ts; h->Tlast = Tl; h->U0 = U0; h->Ustep = Us; h->Ulast = Ul;

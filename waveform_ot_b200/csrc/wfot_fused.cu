@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     const int crank = csize > 1 ? (int)cg::this_cluster().block_rank() : 0;
     const int cid = (int)blockIdx.x / csize, nclusters = (int)gridDim.x / csize;
     const size_t slab = (size_t)cid * npix;
-    SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T, false};
+    SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T};
     int zero_dist = 0, slow = 0, common = 0, degen = 0, tiles = 0;
 
     // windows are drawn from a global counter (the pruned scan makes their cost uneven): the first window of a
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
         // ---------------- P0: window -> shared memory
         const wfot_grid g = a.grids[b % a.n_grids];
         if (tid == 0) {
-            s_hdr->degenerate = 0; s_hdr->nonmono = 0; s_qcount[0] = 0; s_qcount[1] = 0;
+            s_hdr->degenerate = 0; s_qcount[0] = 0; s_qcount[1] = 0;
             s_qcount[2] = csize > 1 ? b + nclusters
                                     : (int)gridDim.x + atomicAdd(a.next_window, 1);      // this CTA's next window
         }
@@ -176,7 +176,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
         __syncthreads();
         const WinHdr hdr = *s_hdr;
-        tb.mono = (hdr.nonmono == 0);
         degen += (tid == 0 && crank == 0) ? hdr.degenerate : 0;
         for (int i = tid; i < a.ntg; i += NT) s_xt[i] = lin_axis(hdr.T0, hdr.Tstep, hdr.Tlast, i, a.ntg);
         for (int i = tid; i < a.nug; i += NT) s_xu[i] = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, i, a.nug);
@@ -375,17 +374,16 @@ __global__ void __launch_bounds__(256, 2) k_scan_probe(FusedArgs a, float* out) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     const int tid = threadIdx.x, S = a.nt - 1;
-    SegTable tb{s_A, s_H, s_bbox, S, a.Spad, 16, false};
+    SegTable tb{s_A, s_H, s_bbox, S, a.Spad, 16};
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         const wfot_grid g = a.grids[b % a.n_grids];
-        if (tid == 0) { s_hdr->degenerate = 0; s_hdr->nonmono = 0; }
+        if (tid == 0) s_hdr->degenerate = 0;
         __syncthreads();
         PrepOut po{s_pn, s_A, s_H, s_bbox, tb.tile, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, 0, po, s_red, nullptr);
         __syncthreads();
         const float inv_sigma = (float)(1.0 / s_hdr->sigma);
-        tb.mono = (s_hdr->nonmono == 0);
         const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(s_pxs[a.ntg - 1] - s_pxs[0]),
                                            fabsf(s_pys[a.nug - 1] - s_pys[0]));
         int tiles = 0;

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) k_prep(PrepArgs a) {
     o.pxs = a.ws.pxs + (size_t)wl * a.ws.ntg_pad;
     o.pys = a.ws.pys + (size_t)wl * a.ws.nug_pad;
     o.hdr = a.ws.hdr + wl;
-    if (threadIdx.x == 0) { o.hdr->degenerate = 0; o.hdr->nonmono = 0; }
+    if (threadIdx.x == 0) o.hdr->degenerate = 0;
     __syncthreads();
     prep_window(a.t, a.w, a.dtype, b * a.t_stride, b * (long long)a.nt, a.nt, g, a.nug, a.ntg,
                 a.transform, o, red, a.pn_out ? a.pn_out + (size_t)b * a.nt * 2 : nullptr);
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_fingerprint(FpArgs a) {
     }
     __syncthreads();
     const double2* pn = a.ws.pn + (size_t)wl * a.nt;
-    SegTable tb{sA, sH, sBB, S, Spad, T, hdr.nonmono == 0};
+    SegTable tb{sA, sH, sBB, S, Spad, T};
     const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(sPx[a.ntg - 1] - sPx[0]), fabsf(sPy[a.nug - 1] - sPy[0]));
     const int foot = blockIdx.x * 8 + (tid >> 5);     // one warp per footprint (warp-uniform)
     int zero_dist = 0, slow = 0, tiles = 0;
