@@ -194,6 +194,25 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
                            double* W, double* grad, double* dwg,
                            void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 
+/* ---- observed window: CDFs of the two marginals --------------------------------
+ * What the fused entry point above consumes as its target.  Replaces, for the OBSERVED
+ * window(s), the chain ru.BuildOTobjfromWaveform (fingerprint, libs/ricker_util.py:204-268)
+ * -> OTpdf (2-D, libs/OTlib.py:90-93) -> setMarginals (:146-160) -> OTpdf of each marginal
+ * (:91-93,112-114): cdf_t (B, ntg), cdf_u (B, nug), amp (B,) = sum of the 2-D density
+ * (nullable).  It runs the SAME kernels and the same summation orders as
+ * wfot_misfit_grad_batch (which derives the predicted window's CDFs on the fly), and every
+ * sum that feeds a CDF bit is independent of the launch shape, so a predicted window that
+ * equals the observed one produces bit-identical CDFs and is reported through
+ * WFOT_STAT_COMMON_CDF exactly as the reference raises TargetSourceCDFError (:663-666).
+ * The bin positions the target also needs are the pixel axes (np.linspace of the window's
+ * normalised limits, libs/FingerprintLib.py:254), host arithmetic.
+ * Workspace: wfot_misfit_grad_workspace_bytes(B, nt, nug, ntg). */
+int wfot_marginal_cdfs_batch(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
+                             const wfot_grid* grids, int n_grids, int B, int nug, int ntg,
+                             double lambda, int q, int transform,
+                             double* cdf_t, double* cdf_u, double* amp,
+                             void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
 /* ---- chain to model parameters ----------------------------------------------
  * Replaces `dw.dot(dr)` / `d.dot(dr.flatten())`: libs/ricker_util.py:399-400,
  * libs/loc_cmt_util.py:283-296.  out (M, P) = J (M, P, L) . dr (M, L);
@@ -209,18 +228,6 @@ int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M,
 size_t wfot_sum_windows_workspace_bytes(int C);
 int wfot_sum_windows(const double* in, long long B, int C, double* out,
                      void* workspace, size_t workspace_bytes, void* stream);
-
-/* ---- microbenchmark used by bench.py to measure the FP32-pipe peak -----------
- * Runs `iters` dependent-free FFMA2 (packed) or FFMA (scalar) bundles on every
- * SM; returns executed FMA lane-operations through *fma_ops (host pointer). */
-int wfot_fp32_peak_probe(int packed, int iters, float* sink, double* fma_ops, void* stream);
-
-/* ---- diagnostic: the brute-force scan alone -------------------------------------
- * prep + FP32 scan of every (pixel, segment) pair, no FP64 resolve: dist32 (B, nug, ntg)
- * = FP32 nearest distance.  bench.py uses it to attribute time to the scan. */
-int wfot_scan_probe(const void* t, const void* w, int in_dtype, long long t_stride, int nt,
-                    const wfot_grid* grids, int n_grids, int B, int nug, int ntg, float* dist32,
-                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,25 @@
+/*
+ * wfot_dev.h -- development / measurement entry points of libwfot.so.  NOT part of the drop-in
+ * boundary (include/wfot.h): nothing here is needed to run the hot path, and the Python shim
+ * never calls it.  bench.py uses the FP32 probe as the roofline denominator of the CUDA-core
+ * bound scan; scripts/ use the option switch for A/B timing of kernel variants.
+ */
+#ifndef WFOT_DEV_H
+#define WFOT_DEV_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Runs `iters` dependent-free FFMA2 (packed) or FFMA (scalar) bundles on every SM; returns the
+ * executed FMA lane-operations through *fma_ops (host pointer).  FP32-pipe peak measurement. */
+int wfot_fp32_peak_probe(int packed, int iters, float* sink, double* fma_ops, void* stream);
+
+/* Process-wide tuning switch (see csrc/wfot_dev_options.h for the ids); value 0 restores the
+ * library's own choice.  Returns the previous value, or -1 for an unknown id. */
+int wfot_dev_set_option(int id, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFOT_DEV_H */

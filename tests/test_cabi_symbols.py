@@ -7,8 +7,8 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    src = open(os.path.join(ROOT, "include", "wfot.h")).read()
+def _declared(header="wfot.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(wfot_[a-z0-9_]+)\s*\(", src)))
 
@@ -17,7 +17,7 @@ def test_library_builds_and_exports_header():
     from waveform_ot_b200 import build
     lib_path = build.build()
     lib = ctypes.CDLL(lib_path)
-    names = _declared()
+    names = _declared() + _declared("wfot_dev.h")
     assert len(names) >= 15
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
@@ -30,6 +30,9 @@ def test_library_builds_and_exports_header():
 def test_binding_table_matches_header():
     from waveform_ot_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == _declared()
+    assert sorted(_cabi.DEV_SIGNATURES) == _declared("wfot_dev.h")
+    # the drop-in boundary holds no probes or tuning switches
+    assert not [n for n in _declared() if "probe" in n or "dev_" in n]
     assert ctypes.sizeof(_cabi.wfot_grid) == 80
 
 

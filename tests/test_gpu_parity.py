@@ -765,3 +765,27 @@ def test_long_windows(B):
     tg = B.Target.from_waveform(t, w[0], grid, 16, 20, lam)
     with pytest.raises(Exception, match="(?i)unsupported|wfot"):
         B.misfit_grad_batch(t, w[1:], grid, 16, 20, lam, tg)
+
+
+def test_sharded_periodic_rows_equal_unsharded(B, monkeypatch):
+    """dist.misfit_grad_sharded with periodic grids / observed windows (one row per station/component, repeated
+    per trial model) and shard boundaries that are NOT multiples of the period: the sum over simulated ranks
+    must equal the unsharded totals (shard-local b % rows picked the wrong rows)."""
+    from waveform_ot_b200 import dist as wd
+    nt, nug, ntg, lam, rows, models = 48, 20, 24, 0.05, 3, 3
+    n = rows * models
+    w = torch.from_numpy(O.random_walk_windows(n + rows, nt, seed=21).astype(np.float64)).cuda()
+    t = torch.linspace(0, 1, nt, dtype=torch.float64, device="cuda")
+    grids = [(0.0, 1.0, -1.2 - 0.1 * i, 1.2 + 0.2 * i, nug, ntg) for i in range(rows)]
+    g = B.pack_grids(grids)
+    tg = B.Target.from_waveform(t, w[:rows], grids, nug, ntg, lam)
+    assert tg.rows == rows
+    full = B.misfit_grad_batch(t, w[rows:], g, nug, ntg, lam, tg)
+    ref = wd.pack_local_sums(full["W"], full["dwg"], full["grad"], B.sum_windows)
+    for world in (2, 4):
+        tot = torch.zeros_like(ref)
+        for rank in range(world):
+            monkeypatch.setenv("RANK", str(rank))
+            monkeypatch.setenv("WORLD_SIZE", str(world))
+            tot += wd.misfit_grad_sharded(t, w[rows:], g, nug, ntg, lam, tg)
+        np.testing.assert_allclose(tot.cpu().numpy(), ref.cpu().numpy(), rtol=1e-11, atol=1e-14)

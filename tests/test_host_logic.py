@@ -105,3 +105,36 @@ def test_build_fingerprint_windows_rule():
             assert list(g[i][j]) == list(O.build_fingerprint_window(t, wave[i, j]))
     g2 = adapters.buildFingerprintwindows(t, wave, Nu=50, Nt=40, u0=-1.0, u1=2.0)
     assert g2[1][1][2:] == [-1.0, 2.0, 50, 40]
+
+
+def test_shard_rows_periodic_rotation():
+    """dist._shard_rows: shard-local window b must find the row of global window lo + b
+    (the kernels index periodic rows with b % rows)."""
+    import torch
+    from waveform_ot_b200.dist import _shard_rows, shard_bounds
+    n, rows = 900, 9
+    x = torch.arange(rows * 2, dtype=torch.float64).reshape(rows, 2)
+    per_window = torch.arange(n * 2, dtype=torch.float64).reshape(n, 2)
+    for world in (1, 2, 7, 8):
+        for rank in range(world):
+            lo, hi = shard_bounds(n, rank, world)
+            y = _shard_rows(x, n, lo, hi, "grids")
+            for b in (0, 1, rows - 1, rows, hi - lo - 1):
+                assert torch.equal(y[b % rows], x[(lo + b) % rows])
+            z = _shard_rows(per_window, n, lo, hi, "grids")
+            assert z.shape[0] == hi - lo and torch.equal(z[0], per_window[lo])
+            assert _shard_rows(x[:1], n, lo, hi, "grids") is not None
+    with pytest.raises(ValueError):
+        _shard_rows(torch.zeros(7, 2), n, 5, 10, "grids")      # 7 rows do not tile 900 windows
+
+
+def test_sharded_empty_shard_contributes_zeros(monkeypatch):
+    """fewer windows than ranks: the empty rank must not call the kernel (it would raise INVALID_ARG while the
+    other ranks wait in the allreduce) but add a zero vector."""
+    import torch
+    from waveform_ot_b200 import dist as wd
+    monkeypatch.setenv("RANK", "3")
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    w = torch.zeros((2, 16))
+    out = wd.misfit_grad_sharded(torch.linspace(0, 1, 16), w, None, 4, 4, 0.04, None)
+    assert out.shape == (3 + 2 * 16,) and float(out.abs().sum()) == 0.0

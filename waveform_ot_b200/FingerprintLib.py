@@ -145,7 +145,7 @@ class waveformFP(object):
         self._dev = {k: v for k, v in out.items() if k in ("pn", "dfield", "iray", "lray", "xray", "pdf", "dddy")}
         self._host = {}
         self._geom = None
-        self._status = out["status"].read()
+        self._status = out["status"].raise_for_reference(derivatives=deriv, what="waveformFP.wdist")
         self.dcalc = True
         if deriv:
             self.drcalc = True

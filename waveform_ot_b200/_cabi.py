@@ -11,6 +11,7 @@ STAT_NEG_PDF, STAT_COMMON_CDF, STAT_ZERO_DIST, STAT_DEGENERATE_SEG, STAT_SLOW_PI
 STAT_SCAN_TILES = 6          # slots 6-7: one 64-bit counter
 STAT_SLOTS = 8
 F32, F64 = 0, 1
+ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = -1, -2, -3, -4
 W1, W2, W12 = 1, 2, 3
 
 
@@ -52,15 +53,22 @@ SIGNATURES = {
     "wfot_misfit_grad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "wfot_misfit_grad_batch": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _d, _i, _i, _i,
                                          _p, _p, _p, _p, _i, _p, _p, _p, _p, _sz, _p, _p]),
+    "wfot_marginal_cdfs_batch": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _d, _i, _i,
+                                           _p, _p, _p, _p, _sz, _p, _p]),
     "wfot_ricker_batch": (C.c_int, [_p, _i, _d, _d, _p, _p, _p, _p]),
     "wfot_chain_batch": (C.c_int, [_p, _p, _i, _i, _i, _ll, _p, _p]),
     "wfot_sum_windows_workspace_bytes": (_sz, [_i]),
     "wfot_sum_windows": (C.c_int, [_p, _ll, _i, _p, _p, _sz, _p]),
-    "wfot_fp32_peak_probe": (C.c_int, [_i, _i, _p, _p, _p]),
-    "wfot_scan_probe": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _p, _p]),
 }
 
-for _name, (_res, _args) in SIGNATURES.items():
+# include/wfot_dev.h: measurement / tuning entry points, not part of the drop-in boundary
+DEV_SIGNATURES = {
+    "wfot_fp32_peak_probe": (C.c_int, [_i, _i, _p, _p, _p]),
+    "wfot_dev_set_option": (C.c_int, [_i, _i]),
+}
+OPT_PIPELINE, OPT_RESOLVE_SHAPE, OPT_FUSED_THREADS, OPT_CLUSTER_MAX, OPT_TILE, OPT_SPLIT_CHUNK = range(6)
+
+for _name, (_res, _args) in list(SIGNATURES.items()) + list(DEV_SIGNATURES.items()):
     _f = getattr(lib, _name)       # AttributeError here = header/library mismatch
     _f.restype = _res
     _f.argtypes = _args

@@ -57,7 +57,9 @@ def misfit_grad(t, waves, grid, target, lambdav, distfunc="W2", transform=False,
     """CalcWasserWaveform(..., deriv=True, returnmarg=True) for a batch of predicted windows
     (libs/ricker_util.py:289-339): returns W (B,2), dr (B,2,nt), dg (B,2) with dg[:,0] =
     dwg/(tan(theta)*(t1-t0)) (:333), dg[:,1] = 0.  With `alpha` the weighted sums
-    alpha*Wt + (1-alpha)*Wu (:390-392) are returned instead."""
+    alpha*Wt + (1-alpha)*Wu (:390-392) are returned instead.
+    Raises the reference's exceptions on the conditions it raises them (batch.Status.raise_for_reference);
+    with to_host=False nothing is synchronised and the caller checks the status itself."""
     import torch
     t0, t1, u0, u1, Nu, Nt = grid
     tant = 1.0 if theta == 45.0 else float(np.tan(np.pi * theta / 180.0))
@@ -72,6 +74,7 @@ def misfit_grad(t, waves, grid, target, lambdav, distfunc="W2", transform=False,
         dg = alpha * dg[:, 0] + (1 - alpha) * dg[:, 1]
     if to_host:
         torch.cuda.current_stream().synchronize()
+        r["status"].raise_for_reference(what="misfit_grad")      # TargetSourceCDFError etc. as the reference
         return W.cpu().numpy(), dr.cpu().numpy(), dg.cpu().numpy()
     return W, dr, dg
 
@@ -120,6 +123,7 @@ def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfu
     if J is not None:
         dmis = _B.chain_batch(J, dr.reshape(M, nr * nc * nt).contiguous())        # :296
     torch.cuda.current_stream().synchronize()
+    r["status"].raise_for_reference(what="misfit_grad_models")
     return mis.cpu().numpy(), None if dmis is None else dmis.cpu().numpy(), dr.reshape(M, nr, nc, nt).cpu().numpy()
 
 
@@ -142,6 +146,7 @@ def optfunc_ricker_batch(X, data):
     deriv = _B.chain_batch(fw["dw"], dr.contiguous())                              # dw.dot(dr)
     deriv[:, 0] = alpha * r["dwg"] / (tant * (t1 - t0))                            # :333,392,402 (dgM[1] = 0)
     torch.cuda.current_stream().synchronize()
+    r["status"].raise_for_reference(what="optfunc_ricker_batch")
     return w2.cpu().numpy(), deriv.cpu().numpy()
 
 
@@ -156,13 +161,15 @@ def misfit_surface(tshifts, amps, f, target, grid, lambdav, trange=(-2.0, 2.0), 
     P = np.stack([ts.ravel(), am.ravel(), np.full(ts.size, float(f))], axis=1)
     out = {"W1": [], "W2": []}
     g = _B.pack_grids((t0, t1, u0, u1, Nu, Nt), tant)
+    status = _B.Status()
     for a in range(0, P.shape[0], chunk):
         fw = _B.ricker_batch(P[a:a + chunk], trange)
         for d in ("W1", "W2"):
             r = _B.misfit_grad_batch(fw["t"], fw["w"], g, int(Nu), int(Nt), lambdav, target, distfunc=d,
-                                     want_grad=False)
+                                     want_grad=False, status=status)
             out[d].append(r["W"])
     torch.cuda.current_stream().synchronize()
+    status.raise_for_reference(derivatives=False, what="misfit_surface")
     shp = (len(tshifts), len(amps), 2)
     return torch.cat(out["W1"]).cpu().numpy().reshape(shp), torch.cat(out["W2"]).cpu().numpy().reshape(shp)
 
@@ -174,8 +181,15 @@ class RickerGraphEvaluator:
     results come back through pinned memory.  One evaluation takes ~0.2 ms on a B200 (0.73 s in the reference).
     `data` as for optfunc_ricker (target from make_target)."""
 
-    def __init__(self, data):
+    def __init__(self, data, on_common_cdf="raise"):
+        """on_common_cdf: what to do when a source and a target marginal CDF share a value - "raise" (the
+        reference: TargetSourceCDFError from wasser(checkCommonCDF=True), libs/OTlib.py:663-666, 1111-1113),
+        "warn" or "ignore".  Near a noise-free optimum the two CDFs agree to the last bits and chance
+        coincidences become likely; an optimiser loop that should run through them passes "warn"."""
         import torch
+        if on_common_cdf not in ("raise", "warn", "ignore"):
+            raise ValueError("on_common_cdf must be 'raise', 'warn' or 'ignore'")
+        self.on_common_cdf = on_common_cdf
         target, distfunc, trange, grid, lambdav, transform, alpha, theta = data
         t0, t1, u0, u1, Nu, Nt = grid
         tant = 1.0 if theta == 45.0 else float(np.tan(np.pi * theta / 180.0))
@@ -183,6 +197,8 @@ class RickerGraphEvaluator:
         self._x = torch.zeros((1, 3), dtype=torch.float64, device=dev)
         self._xh = torch.zeros((1, 3), dtype=torch.float64).pin_memory()
         self._out_h = torch.empty(4, dtype=torch.float64).pin_memory()
+        self._st_h = torch.zeros(_B.C.STAT_SLOTS, dtype=torch.int32).pin_memory()
+        self._st_seen = np.zeros(_B.C.STAT_SLOTS, dtype=np.int64)
         g = _B.pack_grids((t0, t1, u0, u1, Nu, Nt), tant)
         ws = torch.empty(_B.C.lib.wfot_misfit_grad_workspace_bytes(1, 256, int(Nu), int(Nt)), dtype=torch.uint8,
                          device=dev)
@@ -207,6 +223,8 @@ class RickerGraphEvaluator:
                 device_eval()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self.status.t.zero_()                          # the warm-up evaluations (x = 0) do not count
+        torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._res = device_eval()
@@ -218,7 +236,21 @@ class RickerGraphEvaluator:
         self._x.copy_(self._xh, non_blocking=True)
         self._graph.replay()
         self._out_h.copy_(self._res, non_blocking=True)
+        self._st_h.copy_(self.status.t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        st = self._st_h.numpy().astype(np.int64)
+        new, self._st_seen = st - self._st_seen, st          # the counters accumulate over the replays
+        if new[_B.C.STAT_COMMON_CDF] and self.on_common_cdf != "ignore":   # libs/OTlib.py:663-666 via MargWasserstein
+            from . import OTlib
+            err = OTlib.TargetSourceCDFError(["%d common value(s)" % int(new[_B.C.STAT_COMMON_CDF])])
+            if self.on_common_cdf == "raise":
+                raise err
+            import warnings
+            warnings.warn(str(err), RuntimeWarning, stacklevel=2)
+        if new[_B.C.STAT_ZERO_DIST]:
+            import warnings
+            warnings.warn("RickerGraphEvaluator: pixel(s) at zero distance, NaN derivative (libs/FingerprintLib.py:355)",
+                          RuntimeWarning, stacklevel=2)
         o = self._out_h.numpy()
         return float(o[0]), o[1:].copy()
 

@@ -78,6 +78,36 @@ class Status:
     def read(self):
         return self.t.cpu().numpy()
 
+    def raise_for_reference(self, derivatives=True, what="waveform_ot_b200"):
+        """Map the counters onto what the reference does on the same data (call after the stream has been
+        synchronised; costs one 32-byte device -> host copy):
+          * common_cdf > 0  -> OTlib.TargetSourceCDFError: MargWasserstein always calls
+            wasser(checkCommonCDF=True) (libs/OTlib.py:1111-1113, 663-666) and the derivatives are
+            invalid when source and target CDFs share values;
+          * neg_pdf > 0     -> OTlib.PDFSignError (libs/OTlib.py:91);
+          * zero_dist > 0 with derivatives -> RuntimeWarning: a pixel lies exactly on the waveform, d = 0,
+            and d(d)/dw = 0/0 = NaN there exactly as in libs/FingerprintLib.py:355 (NumPy prints the same
+            kind of warning); the NaN is in the returned gradient of the two samples of that segment;
+          * degenerate > 0  -> RuntimeWarning: zero-length segments (repeated samples).  The reference
+            divides 0/0 at libs/FingerprintLib.py:257 and returns NaN fields; here such a segment acts as
+            a point.
+        Returns the counters as a NumPy array."""
+        import warnings
+        st = self.read()
+        if st[C.STAT_NEG_PDF] or st[C.STAT_COMMON_CDF]:
+            from . import OTlib
+            if st[C.STAT_NEG_PDF]:
+                raise OTlib.PDFSignError()
+            raise OTlib.TargetSourceCDFError(["%d common value(s) in %s" % (int(st[C.STAT_COMMON_CDF]), what)])
+        if derivatives and st[C.STAT_ZERO_DIST]:
+            warnings.warn("%s: %d pixel(s) at zero distance from the waveform: d(d)/dw is NaN there "
+                          "(libs/FingerprintLib.py:355)" % (what, int(st[C.STAT_ZERO_DIST])), RuntimeWarning, stacklevel=3)
+        if st[C.STAT_DEGENERATE_SEG]:
+            warnings.warn("%s: %d zero-length waveform segment(s) (repeated samples); the reference returns NaN "
+                          "fields for such input (libs/FingerprintLib.py:257)" % (what, int(st[C.STAT_DEGENERATE_SEG])),
+                          RuntimeWarning, stacklevel=3)
+        return st
+
     def scan_pairs(self):
         """Executed (pixel, segment) pairs of the pruned scan (64-bit counter in slots 6-7,
         kept by the kernels in units of 2048 pairs)."""
@@ -221,20 +251,63 @@ class Target:
         return int(self.cdf_t.shape[0]) if self.cdf_t.dim() == 2 else 1
 
     @staticmethod
-    def from_waveform(t, w, grids, nug, ntg, lambdav, q=None, tantheta=1.0, fpgrids=None):
-        """Fingerprint the observed window(s) and keep their marginal CDFs."""
-        fp = fingerprint_batch(t, w, grids, nug, ntg, lambdav, q=q, tantheta=tantheta, fpgrids=fpgrids,
-                               fields=("pdf", "pn"))
-        mg = marginals_batch(fp["pdf"])
-        Bt = mg["marg_t"].shape[0]
-        # bin positions = pixel axes (libs/OTlib.py:157-158 on wf.pos)
-        pn = fp["pn"]
+    def from_waveform(t, w, grids, nug, ntg, lambdav, q=None, tantheta=1.0, fpgrids=None, transform=False,
+                      status=None):
+        """Observed window(s) -> marginal CDFs + bin positions (wfot_marginal_cdfs_batch: the fused path's own
+        kernels and summation orders, so a predicted window equal to the observed one yields bit-identical
+        CDFs and the common-CDF condition of libs/OTlib.py:663-666 is detected exactly).
+        transform=True applies the arctan amplitude transform in-kernel with each grid's (u0, u1), as
+        misfit_grad_batch(transform=True) does for the predicted windows."""
+        dev = _device()
+        w = _as_device(w)
+        if w.dim() == 1:
+            w = w[None, :]
+        B, nt = w.shape
+        t = _as_device(t, w.dtype)
+        t_stride = 0 if t.dim() == 1 else nt
         g = grids if isinstance(grids, torch.Tensor) else pack_grids(grids, tantheta, fpgrids)
-        x_t, x_u = pixel_axes(pn, g, nug, ntg)
-        ct = otpdf1d_batch(mg["marg_t"])["cdf"]
-        cu = otpdf1d_batch(mg["marg_u"])["cdf"]
-        tg = Target(ct, x_t, cu, x_u)
-        tg.per_window = Bt > 1
+        f64 = dict(dtype=torch.float64, device=dev)
+        ct, cu = torch.empty((B, ntg), **f64), torch.empty((B, nug), **f64)
+        amp = torch.empty(B, **f64)
+        wsb = C.lib.wfot_misfit_grad_workspace_bytes(B, nt, nug, ntg)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        st = status or Status()
+        rc = C.lib.wfot_marginal_cdfs_batch(
+            C.ptr(t), C.ptr(w), _dt(w), t_stride, nt, C.ptr(g), g.shape[0], B, nug, ntg, float(lambdav),
+            0 if q is None else int(q), int(bool(transform)), C.ptr(ct), C.ptr(cu), C.ptr(amp),
+            C.ptr(ws), wsb, C.ptr(st.t), _stream())
+        if rc == C.ERR_UNSUPPORTED and not transform:
+            # window too long for the fused kernels' shared memory (they cannot evaluate a predicted window
+            # against this target either): the materialising kernels still give the CDFs
+            fp = fingerprint_batch(t, w, g, nug, ntg, lambdav, q=q, fields=("pdf",), status=st)
+            mg = marginals_batch(fp["pdf"], status=st)
+            ct = otpdf1d_batch(mg["marg_t"], status=st)["cdf"]
+            cu = otpdf1d_batch(mg["marg_u"], status=st)["cdf"]
+            amp = mg["amp"]
+        else:
+            C.check(rc, "wfot_marginal_cdfs_batch")
+        # bin positions = pixel axes (libs/OTlib.py:157-158 on wf.pos): host arithmetic, IEEE-identical to the
+        # kernel's (t - t0) / (tan(theta) (t1 - t0)) and np.linspace
+        ends = t[..., [0, -1]].to(torch.float64).cpu().numpy().reshape(-1, 2)
+        gr = g.cpu().numpy().view(GRID_DTYPE).reshape(-1)
+        xt, xu = np.empty((B, ntg)), np.empty((B, nug))
+        for b in range(B):
+            gb = gr[b % len(gr)]
+            e = ends[b if t_stride else 0]
+            delt = gb["tantheta"] * (gb["t1"] - gb["t0"])
+            u0, du = (0.0, 1.0) if transform else (gb["u0"], gb["u1"] - gb["u0"])
+            if gb["has_fpgrid"]:
+                a0, a1 = (gb["fp_t0"] - gb["t0"]) / delt, (gb["fp_t1"] - gb["t0"]) / delt
+                c0, c1 = (gb["fp_u0"] - u0) / du, (gb["fp_u1"] - u0) / du
+            else:
+                a0, a1, c0, c1 = (e[0] - gb["t0"]) / delt, (e[1] - gb["t0"]) / delt, 0.0, 1.0
+            xt[b] = np.linspace(a0, a1, ntg)
+            xu[b] = np.linspace(c0, c1, nug)
+        tg = Target(ct, torch.from_numpy(xt).to(dev), cu, torch.from_numpy(xu).to(dev))
+        tg.per_window = B > 1
+        tg.amp = amp
+        tg.status = st
+        tg._keepalive = (t, w, g, ws)
         return tg
 
 

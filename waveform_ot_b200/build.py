@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwfot.so")
-SOURCES = ["wfot_kernels.cu", "wfot_fused.cu", "wfot_ot1d.cu"]
+SOURCES = ["wfot_kernels.cu", "wfot_fused.cu", "wfot_split.cu", "wfot_ot1d.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -21,7 +21,8 @@ def needs_build():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + \
-           [os.path.join(HERE, "..", "include", "wfot.h"), os.path.abspath(__file__)]
+           [os.path.join(HERE, "..", "include", "wfot.h"), os.path.join(HERE, "..", "include", "wfot_dev.h"),
+            os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

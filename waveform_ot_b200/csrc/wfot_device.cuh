@@ -59,6 +59,11 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
     return r;
 }
 
+// The segment table, tile boxes and tile keys always live in shared memory; the pointers reach the
+// scan / resolve functions through structs, where the compiler loses the address space and falls back
+// to generic loads (LD.E instead of LDS: longer latency, long-scoreboard tracking).  Telling it restores LDS.
+#define WFOT_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+
 // ------------------------------------------------------------------ per-window header
 struct WinHdr {
     double T0, Tstep, Tlast;   // pixel time axis:      np.linspace(tlimnfp[0], tlimnfp[1], ntg)
@@ -70,10 +75,14 @@ struct WinHdr {
     int degenerate;            // number of zero-length segments (zeroed by the caller before prep_window())
 };
 
-// FP32 segment table in the rotated frame (shared or global memory)
+// FP32 segment table in the rotated frame (shared memory), stored per PAIR of segments (2p, 2p + 1) so that
+// the per-pixel re-evaluation of a tile runs as packed FFMA2 over two segments and the scan reads a pair with
+// two 16-byte loads:
+//   A[p]            = {ex0, ex1, ey0, ey1}        e = unit direction
+//   A[Spad / 2 + p] = {-am0, -am1, -bm0, -bm1}    am = mid.e, bm = mid x e (scaled)
 struct SegTable {
-    const float4* A;   // {ex, ey, -am, -bm}   e = unit direction, am = mid.e, bm = mid x e (scaled)
-    const float* H;    // half length (scaled)
+    const float4* A;   // [Spad] = [Spad / 2 direction pairs | Spad / 2 offset pairs]
+    const float* H;    // [Spad] half length (scaled)
     const float4* bbox;   // per tile of `tile` segments: {xlo, xhi, ylo, yhi} of its vertices (scaled frame)
     int S;             // real segments
     int Spad;          // padded to a multiple of kTilePad
@@ -95,20 +104,30 @@ __device__ __forceinline__ double lin_axis(double a0, double step, double alast,
 
 // ------------------------------------------------------------------ FP32 pair kernel (scalar form)
 __device__ __forceinline__ float eval32(const SegTable& tb, int s, float px, float py) {
-    const float4 a = tb.A[s];
+    WFOT_ASSUME_SHARED(tb.A); WFOT_ASSUME_SHARED(tb.H);
+    const float* e = reinterpret_cast<const float*>(tb.A + (s >> 1)) + (s & 1);
+    const float* m = reinterpret_cast<const float*>(tb.A + (tb.Spad >> 1) + (s >> 1)) + (s & 1);
+    const float ex = e[0], ey = e[2], nam = m[0], nbm = m[2];
     const float h = tb.H[s];
-    const float P = __fmaf_rn(px, a.x, a.z);     // px*ex - am
-    const float Q = __fmaf_rn(px, a.y, a.w);     // px*ey - bm
-    const float al = __fmaf_rn(py, a.y, P);      // along  = (p - mid).e
-    const float pe = __fmaf_rn(py, -a.x, Q);     // perp   = (p - mid) x e
+    const float P = __fmaf_rn(px, ex, nam);      // px*ex - am
+    const float Q = __fmaf_rn(px, ey, nbm);      // px*ey - bm
+    const float al = __fmaf_rn(py, ey, P);       // along  = (p - mid).e
+    const float pe = __fmaf_rn(py, -ex, Q);      // perp   = (p - mid) x e
     const float tm = __saturatef(__fadd_rn(fabsf(al), -h));
     return __fmaf_rn(tm, tm, __fmul_rn(pe, pe));
 }
 
 // rounding tolerance of the FP32 squared distance (scaled frame, |coords| <= 0.5, D < 1);
 // derivation in DESIGN.md section 3.3
+// one MUFU.SQRT (relative error <= 2^-23) instead of the 8-instruction IEEE sequence: every use below is an
+// upper bound with margins that dwarf it
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float tau32(float d2) {
-    return 2.5e-6f * sqrtf(d2) + 3.0e-7f * d2 + 1.0e-12f;
+    return 2.5000006e-6f * sqrt_approx(d2) + 3.0e-7f * d2 + 1.0e-12f;
 }
 
 // ------------------------------------------------------------------ FP64 reference-order evaluation
@@ -159,24 +178,26 @@ struct PixelHit {
 // Padding segments evaluate to kPadD > thr, so no bounds check is needed.
 template <int T>
 __device__ __forceinline__ unsigned tile_mask(const SegTable& tb, int tile, float px, float py, float thr) {
-    const float4* __restrict__ A = tb.A + tile * T;
-    const float4* __restrict__ H4 = reinterpret_cast<const float4*>(tb.H + tile * T);
+    WFOT_ASSUME_SHARED(tb.A); WFOT_ASSUME_SHARED(tb.H);
+    const float4* __restrict__ E = tb.A + tile * (T / 2);
+    const float4* __restrict__ M = E + (tb.Spad >> 1);
+    const float2* __restrict__ H2 = reinterpret_cast<const float2*>(tb.H + tile * T);
+    const uint64_t px2 = pack2(px, px), py2 = pack2(py, py);
     unsigned mask = 0u;
 #pragma unroll
-    for (int q4 = 0; q4 < T / 4; ++q4) {
-        const float4 h = H4[q4];
-        const float hh[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 a = A[4 * q4 + i];
-            const float P = __fmaf_rn(px, a.x, a.z);
-            const float Q = __fmaf_rn(px, a.y, a.w);
-            const float al = __fmaf_rn(py, a.y, P);
-            const float pe = __fmaf_rn(py, -a.x, Q);
-            const float tm = __saturatef(__fadd_rn(fabsf(al), -hh[i]));
-            const float d32 = __fmaf_rn(tm, tm, __fmul_rn(pe, pe));
-            mask |= (d32 <= thr) ? (1u << (4 * q4 + i)) : 0u;
-        }
+    for (int p = 0; p < T / 2; ++p) {            // two segments per step, the same FP32 operations as the scan
+        const float4 e = E[p], m = M[p];
+        const float2 h = H2[p];
+        const uint64_t ex2 = pack2(e.x, e.y), ey2 = pack2(e.z, e.w), nex2 = pack2(-e.x, -e.y);
+        const uint64_t P = ffma2(px2, ex2, pack2(m.x, m.y));
+        const uint64_t Q = ffma2(px2, ey2, pack2(m.z, m.w));
+        float al0, al1, d0, d1;
+        unpack2(ffma2(py2, ey2, P), al0, al1);
+        const uint64_t pe = ffma2(py2, nex2, Q);
+        const uint64_t tm = pack2(__saturatef(__fadd_rn(fabsf(al0), -h.x)), __saturatef(__fadd_rn(fabsf(al1), -h.y)));
+        unpack2(ffma2(tm, tm, fmul2(pe, pe)), d0, d1);
+        mask |= (d0 <= thr) ? (1u << (2 * p)) : 0u;
+        mask |= (d1 <= thr) ? (2u << (2 * p)) : 0u;
     }
     return mask;
 }
@@ -195,17 +216,17 @@ __device__ __forceinline__ void eval_candidates(const double2* __restrict__ pn, 
     }
 }
 
+// `other` = another tile holds a segment within the tolerance (b2 <= thr), `many` = two or more do (b3 <= thr).
 template <int T>
-__device__ __forceinline__ bool resolve_pixel(const SegTable& tb, const double2* __restrict__ pn,
-                                              float pxl, float pyl, double px, double py,
-                                              float b1, int t1, float b2, float b3, PixelHit& hit) {
-    const float thr = b1 + tau32(b1);
+__device__ __forceinline__ bool resolve_pixel_flagged(const SegTable& tb, const double2* __restrict__ pn,
+                                                      float pxl, float pyl, double px, double py,
+                                                      float thr, int t1, bool other, bool many, PixelHit& hit) {
     hit.D = CUDART_INF; hit.lam = 0.0; hit.s = t1 * T;
-    if (b2 > thr) {                                   // the common case: one tile
+    if (!other) {                                     // the common case: one tile
         eval_candidates<T>(pn, t1, tile_mask<T>(tb, t1, pxl, pyl, thr), px, py, hit);
         return true;
     }
-    if (b3 <= thr) return false;
+    if (many) return false;
     // exactly one other tile holds a candidate: resolved here only if it is a neighbour of t1
     const int ntiles = tb.Spad / T;
     const unsigned m0 = (t1 > 0) ? tile_mask<T>(tb, t1 - 1, pxl, pyl, thr) : 0u;
@@ -216,6 +237,14 @@ __device__ __forceinline__ bool resolve_pixel(const SegTable& tb, const double2*
     eval_candidates<T>(pn, t1, m1, px, py, hit);
     if (m2) eval_candidates<T>(pn, t1 + 1, m2, px, py, hit);
     return true;
+}
+
+template <int T>
+__device__ __forceinline__ bool resolve_pixel(const SegTable& tb, const double2* __restrict__ pn,
+                                              float pxl, float pyl, double px, double py,
+                                              float b1, int t1, float b2, float b3, PixelHit& hit) {
+    const float thr = b1 + tau32(b1);
+    return resolve_pixel_flagged<T>(tb, pn, pxl, pyl, px, py, thr, t1, !(b2 > thr), b3 <= thr, hit);
 }
 
 // Full rescan of every segment by one thread (queue-overflow fallback).
@@ -356,6 +385,7 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
                                            float (&b1)[2 * R], int (&t1)[2 * R], float (&b2)[2 * R],
                                            float (&b3)[2 * R], int& tiles_done, unsigned* __restrict__ keys) {
     static_assert(R % 2 == 0, "rows are processed in pairs");
+    WFOT_ASSUME_SHARED(tb.A); WFOT_ASSUME_SHARED(tb.H); WFOT_ASSUME_SHARED(tb.bbox); WFOT_ASSUME_SHARED(keys);
     const uint64_t px2 = pack2(px0, px1);
     uint64_t y2[R / 2];
 #pragma unroll
@@ -390,7 +420,7 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
     // the lane's pixel block in the scaled frame
     const float qx0 = fminf(px0, px1), qx1 = fmaxf(px0, px1);
     const float qy0 = fminf(py[0], py[R - 1]), qy1 = fmaxf(py[0], py[R - 1]);
-    // thr2 = ((sqrt(lmax) + 4e-6) / (1 - 2e-6))^2: a tile whose squared box distance exceeds it cannot matter
+    // thr2 = ((sqrt(lmax) + 4e-6) / (1 - 2e-6))^2 (+ 3e-7 relative for the approximate square root): a tile whose squared box distance exceeds it cannot matter
     float thr2 = kBig;   // from lmax = max over the lane's pixels of b1, updated per evaluated tile
     while (true) {
         const unsigned kmin = __reduce_min_sync(0xffffffffu, mykey);
@@ -420,11 +450,13 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
         float tm[2 * R];
 #pragma unroll
         for (int k = 0; k < 2 * R; ++k) tm[k] = kBig;
-        const float4* __restrict__ A = tb.A + tile * T;
+        const float4* __restrict__ E = tb.A + tile * (T / 2);
+        const float4* __restrict__ M = E + (tb.Spad >> 1);
         const float* __restrict__ H = tb.H + tile * T;
 #pragma unroll 2
         for (int j = 0; j < T; j += 2) {
-            const float4 a0 = A[j], a1 = A[j + 1];
+            const float4 e = E[j >> 1], m = M[j >> 1];
+            const float4 a0 = make_float4(e.x, e.z, m.x, m.z), a1 = make_float4(e.y, e.w, m.y, m.w);
             const float2 hh = *reinterpret_cast<const float2*>(H + j);
             // per column: P = px*ex - am, Q = px*ey - bm (both columns in one packed op)
             float P0[2], Q0[2], P1[2], Q1[2];
@@ -469,7 +501,7 @@ __device__ __forceinline__ void scan_block(const SegTable& tb, const Footprint& 
             b1[k] = fminf(b1[k], tm[k]);
             mx = fmaxf(mx, b1[k]);
         }
-        const float tq = (sqrtf(mx) + 4.0e-6f) * 1.000002f;
+        const float tq = (sqrt_approx(mx) + 4.0e-6f) * 1.0000023f;
         thr2 = tq * tq;
     }
 }
@@ -500,7 +532,7 @@ __device__ __forceinline__ double block_reduce_minmax(double v, bool is_max, dou
 // Destination buffers may live in shared or global memory.
 struct PrepOut {
     double2* pn;    // [nt]
-    float4* A;      // [Spad]  {ex, ey, -am, -bm}
+    float4* A;      // [Spad]  pair layout, see SegTable
     float* H;       // [Spad]
     float4* bbox;   // [Spad / tile]  per-tile vertex bounding boxes (scaled frame)
     int tile;       // segments per tile (8 or 16)
@@ -567,6 +599,8 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
     const int S = nt - 1;
     const int Spad = ((S + kTilePad - 1) / kTilePad) * kTilePad;
     int degen = 0;
+    float* const tabE = reinterpret_cast<float*>(o.A);
+    float* const tabM = reinterpret_cast<float*>(o.A + (Spad >> 1));
     for (int s = tid; s < Spad; s += nth) {
         float4 A;
         float h;
@@ -586,7 +620,9 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
             A = make_float4(0.f, 0.f, -4.f, 2.f);
             h = 0.f;
         }
-        o.A[s] = A; o.H[s] = h;
+        const int at = (s >> 1) * 4 + (s & 1);
+        tabE[at] = A.x; tabE[at + 2] = A.y; tabM[at] = A.z; tabM[at + 2] = A.w;
+        o.H[s] = h;
     }
     for (int tile = tid; tile < Spad / o.tile; tile += nth) {
         const int s0 = min(tile * o.tile, S), s1 = min(s0 + o.tile, S);      // vertices s0 .. s1 inclusive

@@ -1,0 +1,318 @@
+// wfot_fused.cuh -- pieces shared by the two forms of the throughput path:
+//   wfot_fused.cu   k_misfit_grad   one persistent kernel per call (small batches: thread-block
+//                                   clusters share a window; short windows)
+//   wfot_split.cu   k_scan + k_resolve   the same work as two kernels for large batches of large
+//                                   windows: the FP32 scan keeps its 120+ registers, the FP64
+//                                   resolve / density / OT / gradient half runs at twice the occupancy
+// Shared: argument block, shared-memory layout, the per-pixel scratch-slab store and the window
+// tail (marginals -> 1-D OT -> gradient assembly, phases P2-P4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "wfot_device.cuh"
+#include "wfot_host.h"
+#include "wfot_ot.cuh"
+
+namespace wfot {
+
+constexpr int kFQCap = 512;
+struct FQEntry { int pix; float b1; };
+
+// Shared-memory layout (byte offsets from the dynamic shared base).  Pointers are formed
+// from the `extern __shared__` symbol inside each kernel so the compiler keeps them in the
+// shared address space (LDS/STS instead of generic loads).
+struct SmemLayout {
+    int pn, A, H, bbox, keys, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
+    int total;
+};
+
+inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nmax) {
+    SmemLayout L;
+    int o = 0;
+    auto take = [&](int bytes) { const int at = o; o += (bytes + 15) & ~15; return at; };
+    L.pn = take(nt * 16);
+    // union region: the FP32 segment table is only needed by the scan / resolve phase (P0-P1);
+    // the OT scratch (P3) and the per-sample chain factors (P4) re-use its bytes.
+    const int ubase = o;
+    L.A = take(Spad * 16);
+    L.H = take(Spad * 4);
+    const int ntiles = Spad / tile_for(nt);
+    L.bbox = take(ntiles * 16);
+    L.keys = take(8 * ntiles * 4);                // best-first tile keys, one array per warp (<= 8 warps)
+    const int uend_scan = o;
+    o = ubase;
+    L.cf = take(nmax * 8);
+    L.E = take(nmax * 8);
+    L.tk = take(nmax * 16);
+    L.dx = take(nmax * 16);
+    L.posf = take(nmax * 4);
+    L.gbins = take(nt * 8);
+    o = o > uend_scan ? o : uend_scan;
+    L.margt = take(ntg_pad * 8);
+    L.margu = take(nug_pad * 8);
+    L.Rt = take(ntg_pad * 8);
+    L.Ru = take(nug_pad * 8);
+    L.xt = take(ntg_pad * 8);
+    L.xu = take(nug_pad * 8);
+    L.red = take(64 * 8);
+    L.hdr = take(128);
+    L.queue = take(kFQCap * (int)sizeof(FQEntry));
+    L.pxs = take(ntg_pad * 4);
+    L.pys = take(nug_pad * 4);
+    L.qcount = take(16);
+    L.total = o;
+    return L;
+}
+
+struct FusedArgs {
+    const void* t; const void* w; int dtype; long long t_stride; int nt;
+    const wfot_grid* grids; int n_grids; int B; int nug, ntg;
+    double lambda, rlambda; int q, pmask, transform;      // rlambda = RN(1 / lambda)
+    const double* tgt_cdf_t; const double* tgt_x_t; const double* tgt_cdf_u; const double* tgt_x_u;
+    int tgt_rows;
+    double* W; double* grad; double* dwg;
+    // observed-window mode (wfot_marginal_cdfs_batch): stop after the CDFs of the two marginals and write them
+    // (B, ntg) / (B, nug) and the 2-D amplitude (B,) instead of running the OT against a target
+    double* out_cdf_t; double* out_cdf_u; double* out_amp;
+    // per-CTA scratch slabs
+    double* s_pdf; double* s_wa; double* s_wb; int32_t* s_idx;
+    int32_t* status;
+    int* next_window;     // global work counters (zeroed by the launcher): [0] fused / scan, [16] resolve
+    int cluster;          // > 1: launched as thread-block clusters of this many CTAs, one window per CLUSTER
+    // split form: windows b0 .. b0 + B - 1 of the call; per-pixel scan results {b1 bits, tile | flags} of window
+    // b0 + i at scan_out[i * npix ...]
+    int b0;
+    uint2* scan_out;
+    int Spad, ntg_pad, nug_pad, nmax;
+    SmemLayout L;
+};
+
+// flags in the second word of a scan result: another tile / two other tiles hold a segment within the FP32
+// rounding tolerance of the pixel's minimum (see resolve_pixel)
+constexpr unsigned kScanFlag2 = 1u << 30, kScanFlag3 = 1u << 31, kScanTileMask = kScanFlag2 - 1u;
+
+#define WFOT_SMEM_POINTERS(L)                                                            \
+    double2* const s_pn = reinterpret_cast<double2*>(smem_raw + (L).pn);                 \
+    float4* const s_A = reinterpret_cast<float4*>(smem_raw + (L).A);                     \
+    float* const s_H = reinterpret_cast<float*>(smem_raw + (L).H);                       \
+    float4* const s_bbox = reinterpret_cast<float4*>(smem_raw + (L).bbox);               \
+    unsigned* const s_keys = reinterpret_cast<unsigned*>(smem_raw + (L).keys);           \
+    float* const s_pxs = reinterpret_cast<float*>(smem_raw + (L).pxs);                   \
+    float* const s_pys = reinterpret_cast<float*>(smem_raw + (L).pys);                   \
+    double* const s_margt = reinterpret_cast<double*>(smem_raw + (L).margt);             \
+    double* const s_margu = reinterpret_cast<double*>(smem_raw + (L).margu);             \
+    double* const s_Rt = reinterpret_cast<double*>(smem_raw + (L).Rt);                   \
+    double* const s_Ru = reinterpret_cast<double*>(smem_raw + (L).Ru);                   \
+    double* const s_xt = reinterpret_cast<double*>(smem_raw + (L).xt);                   \
+    double* const s_xu = reinterpret_cast<double*>(smem_raw + (L).xu);                   \
+    double* const s_cf = reinterpret_cast<double*>(smem_raw + (L).cf);                   \
+    double* const s_E = reinterpret_cast<double*>(smem_raw + (L).E);                     \
+    double* const s_tk = reinterpret_cast<double*>(smem_raw + (L).tk);                   \
+    double* const s_dx = reinterpret_cast<double*>(smem_raw + (L).dx);                   \
+    double* const s_red = reinterpret_cast<double*>(smem_raw + (L).red);                 \
+    double* const s_gbins = reinterpret_cast<double*>(smem_raw + (L).gbins);             \
+    int* const s_posf = reinterpret_cast<int*>(smem_raw + (L).posf);                     \
+    FQEntry* const s_queue = reinterpret_cast<FQEntry*>(smem_raw + (L).queue);           \
+    WinHdr* const s_hdr = reinterpret_cast<WinHdr*>(smem_raw + (L).hdr);                 \
+    int* const s_qcount = reinterpret_cast<int*>(smem_raw + (L).qcount)
+
+// pixel -> scratch: density and the two gradient weights of its nearest segment.
+// The throughput path needs d = sqrt(D) only to form exp(-d / lambda) and (xclose_y - p_y) / d, so the three
+// slow FP64 library sequences (IEEE sqrt, two IEEE divisions: ~70 instructions) are replaced by one rsqrt and
+// fused-multiply-add corrections: d = D r + (D - (D r)^2) r / 2, the quotients by Markstein's q0 = a y,
+// q = q0 + (a - b q0) y with y = RN(1 / b) (correctly rounded but for rare half-ulp cases; the density then
+// differs from the materialising kernel's by <= 1 ulp of the exponent, i.e. ~1e-15 relative).
+__device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* pn, size_t slab,
+                                            int it, int iu, const PixelHit& hit, double py, int& zero_dist) {
+    const double* const pny = reinterpret_cast<const double*>(pn) + 1;
+    const double ay = pny[2 * hit.s], by = pny[2 * hit.s + 2];
+    const double cy = __dsub_rn(by, ay);
+    const double xcy = __dadd_rn(ay, __dmul_rn(hit.lam, cy));  // xclose_y (FingerprintLib.py:262)
+    const double num = xcy - py;
+    double d, g;
+    if (hit.D > 0.0) {
+        const double rs = rsqrt(hit.D);
+        const double d0 = hit.D * rs;
+        d = fma(fma(-d0, d0, hit.D), 0.5 * rs, d0);            // (:263)
+        const double g0 = num * rs;
+        g = fma(fma(-g0, d, num), rs, g0);                     // dddx_y = (xclose_y - p_y) / d (:355)
+    } else {                                                   // pixel on the waveform: 0/0 as in the reference
+        d = 0.0;
+        g = num / d;
+        ++zero_dist;
+    }
+    const double e = (a.q == 2) ? d * d : d;                   // exp(-d^2/lambda) (:174) or exp(-|d|/lambda) (:176)
+    const double q0 = e * a.rlambda;
+    const double x = fma(fma(-q0, a.lambda, e), a.rlambda, q0);
+    const double pdf = exp(-x);
+    double wgt = pdf * g;                                      // pdf * dddx_y
+    if (a.q == 2) wgt *= 2.0 * d;                              // :214-217
+    const size_t k = slab + (size_t)iu * a.ntg + it;
+    a.s_pdf[k] = pdf;
+    a.s_wa[k] = (1.0 - hit.lam) * wgt;                         // -> sample iray    (:223)
+    a.s_wb[k] = hit.lam * wgt;                                 // -> sample iray+1  (:224)
+    a.s_idx[k] = hit.s;
+}
+
+// ------------------------------------------------------------------ window tail: P2-P4
+// Called by every thread of the CTA that owns window b once its scratch slab is complete and visible.
+//   P2  marginals of the normalised density (OTlib.py:92-93,155-156), fixed summation order
+//   P3  1-D OT per marginal (OTlib.py:596-706) and <dW, pbar> (OTlib.py:1141,1144-1145)
+//   P4  gradient assembly (FingerprintLib.py:205-228): a thread walks a pixel column, combines runs of
+//       equal nearest segment and adds each run to the window's gradient rows with fire-and-forget FP64
+//       reductions in L2 (RED.ADD.F64; shared-memory FP64 atomics are CAS loops).  The rows were zeroed in P0.
+// Returns the number of exact source/target CDF coincidences (libs/OTlib.py:663-666) in thread 0.
+template <int NT>
+__device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* smem_raw, int b, size_t slab,
+                                           const WinHdr& hdr) {
+    WFOT_SMEM_POINTERS(a.L);
+    (void)s_pn; (void)s_A; (void)s_H; (void)s_bbox; (void)s_keys; (void)s_pxs; (void)s_pys; (void)s_queue;
+    (void)s_hdr; (void)s_qcount;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---------------- P2 (8 independent loads in flight per thread)
+    for (int c = tid; c < a.ntg; c += NT) {
+        const double* col = a.s_pdf + slab + c;
+        double s0 = 0.0;
+        int iu = 0;
+        for (; iu + 8 <= a.nug; iu += 8) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcg(col + (size_t)(iu + j) * a.ntg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s0 += v[j];
+        }
+        for (; iu < a.nug; ++iu) s0 += __ldcg(col + (size_t)iu * a.ntg);
+        s_margt[c] = s0;
+    }
+    __syncthreads();
+    const double A = canon_sum(s_margt, a.ntg, s_red);               // OTpdf.amp (OTlib.py:92), launch-shape independent
+    for (int iu = warp; iu < a.nug; iu += NT / 32) {
+        const double* row = a.s_pdf + slab + (size_t)iu * a.ntg;
+        double s0 = 0.0;
+        for (int c = lane; c < a.ntg; c += 32) s0 += __ldcg(row + c);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+        if (lane == 0) s_margu[iu] = s0 / A;                        // OTlib.py:93,156
+    }
+    for (int c = tid; c < a.ntg; c += NT) s_margt[c] = s_margt[c] / A;     // OTlib.py:93,155
+    __syncthreads();
+
+    if (a.out_cdf_t) {   // observed-window mode: OTpdf of the two marginals (OTlib.py:157-160 -> :91-93,112-114)
+        for (int c = tid; c < a.ntg; c += NT) s_cf[c] = s_margt[c];
+        __syncthreads();
+        int neg = 0;
+        canon_cdf(s_cf, a.ntg, s_red, &neg);
+        for (int c = tid; c < a.ntg; c += NT) a.out_cdf_t[(size_t)b * a.ntg + c] = s_cf[c];
+        __syncthreads();
+        for (int c = tid; c < a.nug; c += NT) s_cf[c] = s_margu[c];
+        __syncthreads();
+        canon_cdf(s_cf, a.nug, s_red, &neg);
+        for (int c = tid; c < a.nug; c += NT) a.out_cdf_u[(size_t)b * a.nug + c] = s_cf[c];
+        if (tid == 0 && a.out_amp) a.out_amp[b] = A;
+        __syncthreads();
+        return 0;
+    }
+
+    // ---------------- P3
+    const size_t trow = (size_t)(b % a.tgt_rows);
+    OtScratch sc{s_cf, s_tk, s_dx, s_E, s_posf, s_red};
+    for (int c = tid; c < a.ntg; c += NT) s_cf[c] = s_margt[c];
+    __syncthreads();
+    const OtResult rt = block_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, a.ntg, s_xt,
+                                   a.tgt_x_t + trow * a.ntg, a.pmask,
+                                   (a.pmask & 1) ? s_Rt : nullptr, (a.pmask & 2) ? s_Rt : nullptr, nullptr);
+    double gp = 0.0;
+    for (int c = tid; c < a.ntg; c += NT) gp += s_margt[c] * s_Rt[c];
+    const double Gt = block_sum(gp, s_red);                         // <dwpmargX, pbar> (OTlib.py:1144)
+    for (int c = tid; c < a.nug; c += NT) s_cf[c] = s_margu[c];
+    __syncthreads();
+    const OtResult ru = block_ot1d(sc, a.nug, a.tgt_cdf_u + trow * a.nug, a.nug, s_xu,
+                                   a.tgt_x_u + trow * a.nug, a.pmask,
+                                   (a.pmask & 1) ? s_Ru : nullptr, (a.pmask & 2) ? s_Ru : nullptr, nullptr);
+    gp = 0.0;
+    for (int c = tid; c < a.nug; c += NT) gp += s_margu[c] * s_Ru[c];
+    const double Gu = block_sum(gp, s_red);                         // OTlib.py:1145
+    if (tid == 0) {
+        a.W[2 * (size_t)b] = (a.pmask & 1) ? rt.W1 : rt.W2;
+        a.W[2 * (size_t)b + 1] = (a.pmask & 1) ? ru.W1 : ru.W2;
+        if (a.dwg) a.dwg[b] = (a.pmask & 1) ? rt.dpos1 : rt.dpos2;  // OTlib.py:1121
+    }
+
+    // ---------------- P4
+    if (a.grad) {
+        // chain vectors: (R - <R, pbar>)/A  (OTlib.py:1144-1147)
+        for (int c = tid; c < a.ntg; c += NT) s_Rt[c] = (s_Rt[c] - Gt) / A;
+        for (int c = tid; c < a.nug; c += NT) s_Ru[c] = (s_Ru[c] - Gu) / A;
+        const double scale = -1.0 / (a.lambda * hdr.du);             // FingerprintLib.py:228,376-378
+        for (int j = tid; j < a.nt; j += NT) {
+            double chain = scale;
+            if (a.transform) {   // d(un)/du, ricker_util.py:273,393-397
+                const double wj = load_sample(a.w, a.dtype, (long long)b * a.nt + j);
+                const double up = ((wj - hdr.u0raw) + (wj - hdr.u1raw)) / (hdr.u1raw - hdr.u0raw);
+                chain *= 2.0 / ((hdr.u1raw - hdr.u0raw) * CUDART_PI * (1.0 + up * up));
+            }
+            s_gbins[j] = chain;
+        }
+        __syncthreads();
+        double* const gt = a.grad + ((size_t)b * 2) * a.nt;
+        double* const gu = gt + a.nt;
+        for (int c = tid; c < a.ntg; c += NT) {
+            const double ct = s_Rt[c];
+            int cur = -1;
+            double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
+            for (int iu0 = 0; iu0 < a.nug; iu0 += 4) {
+                int idx[4];
+                double wa[4], wb[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const size_t k = slab + (size_t)min(iu0 + j, a.nug - 1) * a.ntg + c;
+                    idx[j] = __ldcg(a.s_idx + k); wa[j] = __ldcg(a.s_wa + k); wb[j] = __ldcg(a.s_wb + k);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (iu0 + j >= a.nug) break;
+                    if (idx[j] != cur) {
+                        if (cur >= 0) {
+                            const double c0 = s_gbins[cur], c1 = s_gbins[cur + 1];
+                            atomicAdd(gt + cur, t0 * c0); atomicAdd(gt + cur + 1, t1 * c1);
+                            atomicAdd(gu + cur, u0 * c0); atomicAdd(gu + cur + 1, u1 * c1);
+                        }
+                        cur = idx[j]; t0 = t1 = u0 = u1 = 0.0;
+                    }
+                    const double cu = s_Ru[iu0 + j];
+                    t0 += wa[j] * ct; t1 += wb[j] * ct; u0 += wa[j] * cu; u1 += wb[j] * cu;
+                }
+            }
+            if (cur >= 0) {
+                const double c0 = s_gbins[cur], c1 = s_gbins[cur + 1];
+                atomicAdd(gt + cur, t0 * c0); atomicAdd(gt + cur + 1, t1 * c1);
+                atomicAdd(gu + cur, u0 * c0); atomicAdd(gu + cur + 1, u1 * c1);
+            }
+        }
+    }
+    return (tid == 0) ? (rt.common + ru.common) : 0;
+}
+
+// resident CTAs of a kernel at a given dynamic shared-memory size (sets the opt-in limit on the way)
+template <typename K>
+static int resident_ctas(K kernel, size_t smem, int* per_sm_out, int threads = 256) {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) return -1;
+    if (per_sm < 1) return -1;
+    if (per_sm_out) *per_sm_out = per_sm;
+    return sms * per_sm;
+}
+
+// wfot_split.cu: the two-kernel form.  `a` comes fully populated except scan_out / b0 / the slab pointers;
+// `ws` / `ws_bytes` = what is left of the caller's workspace after the 256-byte counter block at a.next_window.
+int launch_split(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaStream_t stream);
+size_t split_workspace_bytes(int B, int nt, int nug, int ntg, int sms);
+// true when the two-kernel form is used for this problem size (large batches of large windows)
+bool split_wanted(int B, int nt, int nug, int ntg, int sms);
+
+}  // namespace wfot

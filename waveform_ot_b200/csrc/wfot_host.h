@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "wfot_device.cuh"
+#include "wfot_dev_options.h"
 
 namespace wfot {
 
@@ -27,7 +28,7 @@ inline int seg_pad(int nt) { return ((nt - 1 + kTilePad - 1) / kTilePad) * kTile
 // argmin tile size: 8-segment tiles (fewer FP32 re-evaluations per pixel, finer pruning) unless the window is so long
 // that the per-tile bookkeeping of the best-first walk would dominate
 inline int tile_for(int nt) {
-    if (const char* e = getenv("WFOT_DEV_TILE")) return atoi(e) == 8 ? 8 : 16;   // development override
+    if (const int o = dev_option(kOptTile)) return o == 8 ? 8 : 16;   // development override (wfot_dev.h)
     return (nt - 1 <= 2048) ? 8 : 16;
 }
 inline int pad4(int n) { return (n + 3) & ~3; }

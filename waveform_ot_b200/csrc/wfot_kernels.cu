@@ -12,6 +12,7 @@
 
 #include "wfot_device.cuh"
 #include "wfot_host.h"
+#include "../../include/wfot_dev.h"
 #include "wfot_ot.cuh"
 
 namespace wfot {
@@ -298,7 +299,9 @@ __global__ void __launch_bounds__(256) k_pdfderiv(const double* __restrict__ pdf
 }
 
 // ============================================================ k_chain
-// out[m][p] = sum_l J[m][p][l] * dr[m][l]; one warp per (m,p), 16-byte loads.
+// out[m][p] = sum_l J[m][p][l] * dr[m][l]; one warp per (m,p) row.  HBM bound (J is read once: 8 P L bytes per
+// model): fully coalesced 8-byte loads (a row start is only 8-byte aligned for odd L), four independent
+// 256-byte requests in flight per warp, J streamed past L1 (ld.global.cs), fixed summation order.
 __global__ void __launch_bounds__(256) k_chain(const double* __restrict__ J, const double* __restrict__ dr,
                                                int P, int L, int M, long long Jstride, double* out) {
     const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -306,8 +309,14 @@ __global__ void __launch_bounds__(256) k_chain(const double* __restrict__ J, con
     const int mI = warp / P, p = warp % P;
     const double* row = J + (size_t)mI * Jstride + (size_t)p * L;
     const double* d = dr + (size_t)mI * L;
-    double s = 0.0;
-    for (int l = lane; l < L; l += 32) s += row[l] * d[l];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int l = lane;
+    for (; l + 96 < L; l += 128) {
+        const double a0 = __ldcs(row + l), a1 = __ldcs(row + l + 32), a2 = __ldcs(row + l + 64), a3 = __ldcs(row + l + 96);
+        s0 += a0 * d[l]; s1 += a1 * d[l + 32]; s2 += a2 * d[l + 64]; s3 += a3 * d[l + 96];
+    }
+    for (; l < L; l += 32) s0 += __ldcs(row + l) * d[l];
+    double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) out[(size_t)mI * P + p] = s;

@@ -99,6 +99,85 @@ __device__ __forceinline__ double block_cumsum(double* a, int n, double* red) {
     return last;
 }
 
+// ---- canonical (CTA-shape independent) reductions -------------------------------------------------------
+// The fused path compares the CDFs of a predicted window with those of the observed window for EXACT equality
+// (libs/OTlib.py:663-666 raises TargetSourceCDFError on common values; identical windows are the practical
+// trigger).  Observed and predicted CDFs are produced by different launches - different CTA sizes, one kernel
+// or two - so every sum that feeds a CDF bit uses an order that does not depend on the launch shape: warp 0
+// alone, lane k adding elements k, k + 32, ... in ascending order, then a xor-shuffle tree; the prefix sum
+// gives lane k the contiguous chunk [k c, (k + 1) c), c = ceil(n / 32), and scans the 32 chunk totals with
+// shuffles.  n is a grid axis (tens to ~1000 entries): a few hundred cycles per window.
+// Every thread of the block calls; `red` = 2 doubles of shared scratch.
+__device__ __forceinline__ double canon_sum(const double* a, int n, double* red) {
+    if (threadIdx.x < 32) {
+        double v = 0.0;
+        for (int j = threadIdx.x; j < n; j += 32) v += a[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (threadIdx.x == 0) red[0] = v;
+    }
+    __syncthreads();
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
+
+// OTpdf of a 1-D density in shared memory (libs/OTlib.py:91-93,112-114), canonical order:
+// a[0..n) un-normalised amplitudes -> CDF = cumsum(a / amp) / cumsum(a / amp)[-1].  Returns amp; *neg (nullable,
+// valid in every thread) = number of negative amplitudes.  Entries a parallel prefix sum rounds below their
+// predecessor (terms under the ulp of the running sum) are raised to the running maximum, see block_cumsum().
+__device__ __forceinline__ double canon_cdf(double* a, int n, double* red, int* neg) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double v = 0.0;
+        int ng = 0;
+        for (int j = lane; j < n; j += 32) { const double x = a[j]; v += x; ng += (x < 0.0); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, off);
+            ng += __shfl_xor_sync(0xffffffffu, ng, off);
+        }
+        const double amp = v;
+        const int c = (n + 31) >> 5, beg = min(lane * c, n), end = min(beg + c, n);
+        double run = 0.0;
+        for (int j = beg; j < end; ++j) { run += a[j] / amp; a[j] = run; }
+        double inc = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += o;
+        }
+        const double excl = inc - run;
+        for (int j = beg; j < end; ++j) a[j] += excl;
+        __syncwarp();
+        int viol = 0;
+        for (int j = max(beg, 1); j < end; ++j) viol |= (a[j] < a[j - 1]);
+        if (__any_sync(0xffffffffu, viol)) {                   // rare: restore the order with an exact running maximum
+            double m = 0.0;
+            for (int j = beg; j < end; ++j) { m = fmax(m, a[j]); a[j] = m; }
+            double mi = m;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double o = __shfl_up_sync(0xffffffffu, mi, off);
+                if (lane >= off) mi = fmax(mi, o);
+            }
+            double me = __shfl_up_sync(0xffffffffu, mi, 1);
+            if (lane == 0) me = 0.0;
+            for (int j = beg; j < end; ++j) a[j] = fmax(a[j], me);
+        }
+        __syncwarp();
+        const double last = a[n - 1];
+        __syncwarp();
+        for (int j = beg; j < end; ++j) a[j] = a[j] / last;
+        if (lane == 0) { red[0] = amp; red[1] = __longlong_as_double((long long)ng); }
+    }
+    __syncthreads();
+    const double amp = red[0];
+    if (neg) *neg = (int)__double_as_longlong(red[1]);
+    __syncthreads();
+    return amp;
+}
+
 __device__ __forceinline__ int lower_bound_d(const double* a, int n, double v) {   // bisect_left
     int lo = 0, hi = n;
     while (lo < hi) {
@@ -141,16 +220,9 @@ __device__ __forceinline__ OtResult block_ot1d(const OtScratch& sc, int n, const
                                                double* dW1, double* dW2, int32_t* merge_order) {
     const int tid = threadIdx.x, T = blockDim.x;
     OtResult r;
-    // -- OTpdf: sign check, normalise, CDF (libs/OTlib.py:91-93,112-114)
-    double part = 0.0;
+    // -- OTpdf: sign check, normalise, CDF (libs/OTlib.py:91-93,112-114), canonical summation order
     int neg = 0;
-    for (int j = tid; j < n; j += T) { const double v = sc.cf[j]; part += v; neg += (v < 0.0); }
-    r.amp = block_sum(part, sc.red);
-    for (int j = tid; j < n; j += T) sc.cf[j] = sc.cf[j] / r.amp;
-    __syncthreads();
-    const double last = block_cumsum(sc.cf, n, sc.red);          // every thread has read cf[n-1] behind a barrier
-    for (int j = tid; j < n; j += T) sc.cf[j] = sc.cf[j] / last;
-    __syncthreads();
+    r.amp = canon_cdf(sc.cf, n, sc.red, &neg);
     // -- stable rank-merge of cf[:-1] and cg (:668-672)
     const int K = n + m - 1;
     int common = 0;
@@ -190,7 +262,7 @@ __device__ __forceinline__ OtResult block_ot1d(const OtScratch& sc, int n, const
     r.W2 = block_sum(w2, sc.red);
     r.dpos1 = block_sum(p1, sc.red);
     r.dpos2 = block_sum(p2, sc.red);
-    r.neg = __syncthreads_count(neg > 0);
+    r.neg = neg;
     r.common = (int)block_sum((double)common, sc.red);
     // -- d/d(un-normalised source amplitude) (:682-686,694,704), O(n) form
     for (int p = 1; p <= 2; ++p) {

@@ -349,7 +349,7 @@ struct Chain {
 
     // cf and cg (and x_f, x_g) are contiguous: cg = cf + npad, xg = xf + npad.
     __device__ __forceinline__ void init(const double* cf, const double* xf, int npad, int k0,
-                                         int ia_, int ia1_, int ib_, int ib1_) {
+                                         int ia_, int ia1_, int ib_, int ib1_, int n, int m) {
         const double* cg = cf + npad;
         ia = ia_; ia1 = ia1_; ib = ib_; ib1 = ib1_; k = k0; pj = -1;
         tprev = 0.0; runf_val = CUDART_NAN; rung_val = CUDART_NAN; runf_len = 0; rung_len = 0;
@@ -367,8 +367,8 @@ struct Chain {
         va = ia < ia1 ? cf[ia] : CUDART_INF;      // heads, bounded by the chain's own ranges
         vb = ib < ib1 ? cg[ib] : CUDART_INF;
         xa = 0.0; xb = 0.0;
-        if (STRICT) {                             // ia <= n-1 and ib <= m-1 always hold here
-            xa = xf[ia]; xb = xf[npad + ib];
+        if (STRICT) {                             // an empty trailing chain starts at ia = n-1, ib = m: clamp as step() does
+            xa = xf[min(ia, n - 1)]; xb = xf[npad + min(ib, m - 1)];
             if ((E1 || E2) && (ia < ia1 || ib < ib1)) {      // |dx|^p of the chain's first knot (for the previous chain)
                 const bool src = (va <= vb);
                 const bool tie = !src && ia > 0 && (vb == tprev);
@@ -486,8 +486,8 @@ __device__ __forceinline__ void warp_merge(const double* cf, const double* xf, i
     if (lane == 31) iaE = n - 1;
     constexpr bool E1 = (EM & 1) != 0, E2 = (EM & 2) != 0;
     Chain<STRICT, PM, EM, MO> A, B;
-    A.init(cf, xf, npad, dA, iaA, iaB, dA - iaA, dB - iaB);
-    B.init(cf, xf, npad, dB, iaB, iaE, dB - iaB, dE - iaE);
+    A.init(cf, xf, npad, dA, iaA, iaB, dA - iaA, dB - iaB, n, m);
+    B.init(cf, xf, npad, dB, iaB, iaE, dB - iaB, dE - iaE, n, m);
     __syncwarp();                                 // all look-back / split reads done before any lane parks an E_j
     const int lenA = dB - dA, lenB = dE - dB;     // lenB <= lenA
     const uint32_t cfa = (uint32_t)__cvta_generic_to_shared(cf), xfa = (uint32_t)__cvta_generic_to_shared(xf);

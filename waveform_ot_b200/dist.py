@@ -68,24 +68,48 @@ def sharded_misfit_grad(evaluate, n_windows, reducer):
     return allreduce_sum_(pack_local_sums(W, dwg, grad, reducer))
 
 
+def _shard_rows(x, n, lo, hi, what):
+    """Rows of a per-window / shared / periodic array (leading axis) for the shard [lo, hi) of n windows.
+    The kernels index such rows with the SHARD-LOCAL window number (b % rows), so a periodic layout (one row
+    per station/component, repeated for every trial model) is rotated by lo % rows: local window 0 then finds
+    the row of global window lo."""
+    rows = int(x.shape[0])
+    if rows == 1:
+        return x
+    if rows == n:
+        return x[lo:hi].contiguous()
+    if n % rows != 0:
+        raise ValueError("%s: %d rows for %d windows (neither one per window nor a period of the batch)" % (what, rows, n))
+    k = lo % rows
+    if k == 0:
+        return x
+    import torch
+    return torch.roll(x, shifts=-k, dims=0).contiguous()
+
+
 def misfit_grad_sharded(t, w, grids, nug, ntg, lambdav, target, **kw):
     """The multi-GPU evaluation of a stacked misfit: this rank runs the fused kernel on its contiguous shard
     of the windows `w` (B, nt) (a per-window time axis `t` (B, nt) is sharded alike), reduces it to
     [sum W^t, sum W^u, sum dW^t/dx0, sum dW^t/dw, sum dW^u/dw] with the fixed-order window sum, and the ranks
     combine with ONE allreduce.  Returns the packed (3 + 2 nt,) device vector, identical on every rank.
-    Grids / observed windows with one row per window are sharded alike; shared or periodic rows are kept
-    (a periodic layout needs shard boundaries that are multiples of the period)."""
+    Grids / observed windows with one row per window are sharded alike; periodic rows (one per
+    station/component, window b uses row b % rows) are rotated so that every shard starts on its own phase;
+    a rank whose shard is empty (fewer windows than ranks) contributes zeros."""
+    import torch
     from . import batch as B
     rank, world, _ = env_rank_world()
     n = w.shape[0]
+    nt = w.shape[1]
     lo, hi = shard_bounds(n, rank, world)
+    if hi == lo:
+        dev = w.device if isinstance(w, torch.Tensor) else B._device()
+        return allreduce_sum_(torch.zeros(3 + 2 * nt, dtype=torch.float64, device=dev))
     tt = t[lo:hi] if getattr(t, "ndim", 1) == 2 else t
     g = grids
-    if hasattr(grids, "shape") and grids.shape[0] == n and n > 1:
-        g = grids[lo:hi].contiguous()
+    if hasattr(grids, "shape"):
+        g = _shard_rows(grids, n, lo, hi, "grids")
     tg = target
-    if target.rows == n and n > 1:
-        tg = B.Target(target.cdf_t[lo:hi].contiguous(), target.x_t[lo:hi].contiguous(),
-                      target.cdf_u[lo:hi].contiguous(), target.x_u[lo:hi].contiguous())
+    if target.rows > 1:
+        tg = B.Target(*[_shard_rows(x, n, lo, hi, "target") for x in (target.cdf_t, target.x_t, target.cdf_u, target.x_u)])
     r = B.misfit_grad_batch(tt, w[lo:hi], g, nug, ntg, lambdav, tg, **kw)
     return allreduce_sum_(pack_local_sums(r["W"], r["dwg"], r["grad"], B.sum_windows))
