@@ -42,9 +42,14 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=9472, help="windows per GPU per step (64 per SM)")
-    ap.add_argument("--cpu-sample", type=int, default=12, help="windows timed for cpu_baseline (N=1, rank 0)")
+    ap.add_argument("--cpu-sample", type=int, default=3, help="windows timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--secondary", type=int, default=1,
-                    help="also time the other BASELINE.json configs' kernels (N=1, a few ms each)")
+                    help="also time the other BASELINE.json configs at their named sizes (N=1)")
+    ap.add_argument("--parity-windows", type=int, default=8,
+                    help="windows of the TIMED pool checked against the CPU oracle after the timed region (rank 0)")
+    ap.add_argument("--sweep-windows", type=int, default=4 * 1024 * 1024,
+                    help="cfg5 sweep: total windows over all GPUs, generated on the device shard by shard "
+                         "(fixed total = strong scaling); 0 = skip")
     return ap.parse_args()
 
 
@@ -148,62 +153,120 @@ def make_windows_device(nb, nt, seed, device):
     return y.contiguous()
 
 
-# ----------------------------------------------------------------------------- CPU legs (oracle port)
+# ----------------------------------------------------------------------------- CPU legs
+# kind "reference": the UNMODIFIED reference modules (oracle/_ref, made by oracle/build_ref.py in the build
+# container and shipped with the snapshot) through the reference's own call chain
+# ru.BuildOTobjfromWaveform -> ru.CalcWasserWaveform(deriv=True, returnmarg=True) (libs/ricker_util.py:204-339);
+# kind "port": the NumPy restatement oracle/wfot_oracle.py (same arithmetic in bounded-memory chunks), used when
+# oracle/_ref is absent.  The reference materialises (pixels x segments x 2) FP64 temporaries: ~5 GB per
+# process at the cfg5 shape, so the process count is also bounded by the host's free memory.
+REF_BYTES_PER_PROC = 6 << 30
+
+
+def _ref_modules():
+    from oracle import build_ref
+    return build_ref.import_reference() if build_ref.available() else None
+
+
 def _cpu_one(args):
-    from oracle import wfot_oracle as O
-    t, w, tgt = args
+    kind, t, w, tgt = args
     t0 = time.perf_counter()
-    O.misfit_grad_window(t, w, GRID, tgt, lambdav=LAM, distfunc="W2", chunk=2048)
+    if kind == "reference":
+        fp, OT, ru = _ref_modules()
+        wf, src = ru.BuildOTobjfromWaveform(t, w, GRID, lambdav=LAM, deriv=True)
+        ru.CalcWasserWaveform(src, tgt, wf, distfunc="W2", deriv=True, returnmarg=True)
+    else:
+        from oracle import wfot_oracle as O
+        O.misfit_grad_window(t, w, GRID, tgt, lambdav=LAM, distfunc="W2", chunk=2048)
     return time.perf_counter() - t0
 
 
-def cpu_eval_rate(n_windows, procs):
-    """evals/s of the oracle port (NumPy FP64 restatement of the reference path) on host cores."""
+_CPU_TARGET = {}
+
+
+def _cpu_target(kind, t, obs):
+    """Observed-window OT object, built once per process tree and NOT timed (the reference's loops build it once
+    per inversion as well)."""
+    if kind not in _CPU_TARGET:
+        if kind == "reference":
+            fp, OT, ru = _ref_modules()
+            _, tgt = ru.BuildOTobjfromWaveform(t, obs, GRID, lambdav=LAM)
+            tgt.setMarginals()
+        else:
+            from oracle import wfot_oracle as O
+            _, tgt = O.build_ot_from_waveform(t, obs, GRID, lambdav=LAM, chunk=2048)
+            O.set_marginals(tgt)
+        _CPU_TARGET[kind] = tgt
+    return _CPU_TARGET[kind]
+
+
+def cpu_kind():
+    try:
+        return "reference" if _ref_modules() is not None else "port"
+    except Exception:
+        return "port"
+
+
+def cpu_procs(kind, want):
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, want))
+    if kind == "reference":
+        try:
+            import psutil
+            procs = max(1, min(procs, int(0.5 * psutil.virtual_memory().available // REF_BYTES_PER_PROC)))
+        except Exception:
+            procs = min(procs, 8)
+    return procs
+
+
+def cpu_eval_rate(n_windows, procs, kind):
+    """evals/s of the CPU path on host cores: per evaluation the predicted-window chain (fingerprint + density +
+    derivatives, marginals, W2 per marginal, gradient), against an observed-window object built beforehand."""
     from oracle import wfot_oracle as O
     w = O.random_walk_windows(n_windows + 1, NT, seed=5).astype(np.float64)
     t = np.linspace(0, 1, NT)
-    _, tgt = O.build_ot_from_waveform(t, w[0], GRID, lambdav=LAM, chunk=2048)
-    O.set_marginals(tgt)
-    jobs = [(t, w[1 + i], tgt) for i in range(n_windows)]
+    tgt = _cpu_target(kind, t, w[0])
+    jobs = [(kind, t, w[1 + i], tgt) for i in range(n_windows)]
     t0 = time.perf_counter()
     if procs <= 1:
-        for j in jobs:
-            _cpu_one(j)
+        per = [_cpu_one(j) for j in jobs]
     else:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(procs) as pool:
-            pool.map(_cpu_one, jobs, chunksize=1)
+            per = pool.map(_cpu_one, jobs, chunksize=1)
     dt = time.perf_counter() - t0
-    return n_windows / dt, dt
+    return n_windows / dt, dt, per
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU algorithm (oracle port; the reference is pure Python +
-    NumPy and cannot travel to the GPU box) on all host cores, same workload/metric."""
+    """Reference arm: the reference's own CPU implementation of the path (oracle/_ref when present, else the
+    oracle port) on the host cores, same workload and metric; each step = one window per process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 32))
-    per_window_s = 9.0
+    kind = cpu_kind()
+    procs = cpu_procs(kind, 32)
+    per_window_s = 9.0 if kind == "reference" else 9.0
     nsteps = args.steps + args.warmup
-    per_step = int(max(1, min(procs, 150.0 / (nsteps * per_window_s) * procs)))
+    per_step = int(max(1, min(procs, 240.0 / (nsteps * per_window_s) * procs)))
     procs = min(procs, per_step)
     for _ in range(args.warmup):
-        cpu_eval_rate(per_step, procs)
+        cpu_eval_rate(per_step, procs, kind)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_eval_rate(per_step, procs)
+        cpu_eval_rate(per_step, procs, kind)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
+    what = ("unmodified reference modules (oracle/_ref: libs.ricker_util.BuildOTobjfromWaveform + CalcWasserWaveform)"
+            if kind == "reference" else "oracle/wfot_oracle.py, NumPy FP64 restatement")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg5: 1024-sample windows -> 256x256 fingerprint, W2 misfit + gradient",
                    "nt": NT, "nug": NUG, "ntg": NTG, "lambda": LAM, "windows_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "port",
-                         "sample": "%d windows per step on %d processes (oracle/wfot_oracle.py, NumPy FP64)" % (per_step, procs)},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": kind,
+                         "sample": "%d windows per step on %d processes (%s)" % (per_step, procs, what)},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -236,11 +299,16 @@ def secondary_configs(dev):
             b = min(b, s.elapsed_time(e))
         return b
 
+    peak_hbm = None
+    try:
+        peak_hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
     out = {}
     for name, nt, nug, ntg, nb, lam, grad, transform in (
             ("cfg1_shape_misfit_grad", 256, 80, 512, 8192, 0.03, True, False),
             ("cfg3_shape_misfit_only", 256, 80, 512, 8192, 0.03, False, False),
-            ("cfg4_shape_misfit_grad_arctan", 61, 79, 61, 30 * 2048, 0.04, True, True)):
+            ("cfg4_shape_misfit_grad_arctan", 61, 79, 61, 30 * 4096, 0.04, True, True)):
         w = make_windows_device(nb, nt, 77, dev)
         obs = make_windows_device(1, nt, 5, dev)
         t = torch.linspace(0, 1, nt, device=dev, dtype=torch.float32)
@@ -289,30 +357,45 @@ def secondary_configs(dev):
         ev(X1[0])
     out["cfg1_single_eval_latency_cuda_graph"] = {"ms": (time.perf_counter() - t0) / 100 * 1e3,
                                                   "note": "adapters.RickerGraphEvaluator: one captured CUDA graph replayed per evaluation"}
-    # cfg4 end to end: 1024 trial models x (10 stations x 3 components) windows of 61 samples, host-precomputed
-    # (synthetic) seismograms and Jacobians in, per-model misfit + gradient w.r.t. 9 source parameters out
+    # cfg4 end to end at its named size: 4096 trial models x (10 stations x 3 components) windows of 61 samples,
+    # host-precomputed (synthetic) seismograms and Jacobians in PINNED host memory in, per-model misfit + gradient
+    # w.r.t. 9 source parameters out (host NumPy)
     rng = np.random.default_rng(1)
-    M4, nr4, nc4, nt4 = 1024, 10, 3, 61
+    M4, nr4, nc4, nt4 = 4096, 10, 3, 61
     t4 = np.arange(float(nt4))
     pulse = lambda sh, wd: np.exp(-0.5 * ((t4 - sh) / wd) ** 2) * np.sin(0.35 * (t4 - sh))
     obs4 = np.stack([[pulse(22 + 2 * i + j, 4.0) for j in range(nc4)] for i in range(nr4)]) * 1e-3
     obs4 += 2e-5 * rng.standard_normal(obs4.shape)
-    sh = rng.uniform(-4, 4, size=(M4, 1, 1))
-    pred4 = np.stack([[pulse(22 + 2 * i + j, 4.0) for j in range(nc4)] for i in range(nr4)])[None] * 1e-3
-    pred4 = np.stack([np.roll(pred4[0], int(round(s_)), axis=-1) for s_ in sh[:, 0, 0]]) * rng.uniform(0.7, 1.3, size=(M4, 1, 1, 1))
-    J4 = rng.standard_normal((M4, 9, nr4 * nc4 * nt4))
+    sh = rng.integers(-4, 5, size=M4)
+    base4 = np.stack([[pulse(22 + 2 * i + j, 4.0) for j in range(nc4)] for i in range(nr4)]) * 1e-3
+    pred4 = np.stack([np.roll(base4, int(s_), axis=-1) for s_ in sh]) * rng.uniform(0.7, 1.3, size=(M4, 1, 1, 1))
+    pred4_pin = torch.from_numpy(pred4).pin_memory()
+    J4_pin = torch.randn((M4, 9, nr4 * nc4 * nt4), dtype=torch.float64).pin_memory()
     grids4 = adapters.buildFingerprintwindows(t4, obs4)
     tg4 = adapters.make_targets_models(t4, obs4, grids4, 0.04)
-    adapters.misfit_grad_models(t4, pred4[:8], grids4, tg4, 0.04, J=J4[:8])
+    adapters.misfit_grad_models(t4, pred4_pin[:64], grids4, tg4, 0.04, J=J4_pin[:64])
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    adapters.misfit_grad_models(t4, pred4, grids4, tg4, 0.04, J=J4)
+    adapters.misfit_grad_models(t4, pred4_pin, grids4, tg4, 0.04, J=J4_pin)
     dt4 = time.perf_counter() - t0
-    out["cfg4_models_1024x30_windows_end_to_end"] = {
+    out["cfg4_models_4096x30_windows_end_to_end"] = {
         "models": M4, "windows": M4 * nr4 * nc4, "seconds": dt4, "models_per_s": M4 / dt4,
-        "note": "adapters.misfit_grad_models: pageable host arrays in (seismograms 15 MB, Jacobians 135 MB), "
-                "fused kernel with in-kernel arctan transform, Jacobian chain, results back on the host"}
+        "h2d_bytes": int(pred4_pin.numel() * 8 + J4_pin.numel() * 8),
+        "note": "adapters.misfit_grad_models: pinned host tensors in (seismograms 60 MB, Jacobians 540 MB) streamed in "
+                "chunks of 512 models under the kernels, fused kernel with in-kernel arctan transform, Jacobian chain, "
+                "results (misfit, 9 derivatives, d/d(seismogram) 60 MB) back on the host as NumPy"}
+    # the Jacobian chain alone (k_chain, HBM bound: J is read once, 8 P L bytes per model)
+    Jd = J4_pin[:2048].to(dev)
+    drd = torch.randn((2048, nr4 * nc4 * nt4), dtype=torch.float64, device=dev)
+    ms_c = best(lambda: B.chain_batch(Jd, drd))
+    chain_bytes = float(Jd.numel() * 8 + drd.numel() * 8 + 2048 * 9 * 8)
+    out["cfg4_chain_gemv"] = {"models": 2048, "ms": ms_c,
+                              "roofline": {"bound": "hbm", "achieved": chain_bytes / ms_c / 1e6, "unit": "GB/s",
+                                           "peak": peak_hbm, "frac": (chain_bytes / ms_c / 1e6 / peak_hbm) if peak_hbm else None,
+                                           "bytes_per_model": chain_bytes / 2048}}
+    del Jd, drd, J4_pin, pred4_pin
     # cfg2: batched 1-D OT, W2 + dW2/df + d/dx0 on random densities (FP32 in, FP64 out), C ABI called directly
-    n, nb = 1024, 100000
+    n, nb = 1024, 1000000
     f = torch.rand(nb, n, device=dev) + 1e-3
     gq = torch.rand(nb, n, device=dev) + 1e-3
     x = torch.linspace(0, 1, n, dtype=torch.float64, device=dev)
@@ -338,6 +421,90 @@ def secondary_configs(dev):
                                   "moved_gbs": nb * moved / ms / 1e6,
                                   "note": "FP64 outputs: the kernel is instruction-issue bound, not HBM bound (DESIGN.md 3.4)"}}
     return out
+
+
+# ----------------------------------------------------------------------------- checks on the timed data
+def parity_check(B, C, t, w_dev, obs_dev, run_batch, k):
+    """K windows of a TIMED input batch against the CPU oracle (oracle/wfot_oracle.py, pinned to the reference by
+    tests/golden): the batch goes once more through exactly the call that was timed, with the development hook
+    that also captures the kernels' nearest-segment indices; W, gradient and indices of K windows spread over the
+    batch are then compared.  Runs outside the timed region."""
+    import torch
+    from oracle import wfot_oracle as O
+    nb = w_dev.shape[0]
+    iray = torch.empty((nb, NUG * NTG), dtype=torch.int32, device=w_dev.device)
+    C.lib.wfot_dev_capture_iray(C.ptr(iray))
+    try:
+        r = run_batch(w_dev)
+        torch.cuda.synchronize()
+    finally:
+        C.lib.wfot_dev_capture_iray(None)
+    pick = sorted(set(int(x) for x in np.linspace(0, nb - 1, k)))
+    th = t.double().cpu().numpy()
+    _, tgt = O.build_ot_from_waveform(th, obs_dev.double().cpu().numpy(), GRID, lambdav=LAM, chunk=2048)
+    O.set_marginals(tgt)
+    out = {"windows": len(pick), "indices_checked": 0, "index_mismatches": 0, "max_rel_err_W": 0.0,
+           "max_rel_err_grad": 0.0, "max_rel_err_dwg": 0.0}
+    for b in pick:
+        wb = w_dev[b].double().cpu().numpy()
+        W, dr, dg, win, _ = O.misfit_grad_window(th, wb, GRID, tgt, lambdav=LAM, distfunc="W2", chunk=2048)
+        ir = iray[b].cpu().numpy().astype(np.int64)
+        out["indices_checked"] += ir.size
+        out["index_mismatches"] += int((ir != win.irays).sum())
+        Wg = r["W"][b].cpu().numpy()
+        gg = r["grad"][b].cpu().numpy()
+        out["max_rel_err_W"] = max(out["max_rel_err_W"], float(np.max(np.abs(Wg - np.asarray(W)) / np.abs(np.asarray(W)))))
+        for i in range(2):
+            out["max_rel_err_grad"] = max(out["max_rel_err_grad"],
+                                          float(np.max(np.abs(gg[i] - dr[i])) / np.max(np.abs(dr[i]))))
+        # dg[0] = dwg / (tan(theta) (t1 - t0)) with tan = 1, t1 - t0 = 1 here
+        out["max_rel_err_dwg"] = max(out["max_rel_err_dwg"], float(abs(r["dwg"][b].item() - dg[0]) / max(abs(dg[0]), 1e-300)))
+    out["oracle"] = "oracle/wfot_oracle.py (NumPy FP64), windows %s of the first timed batch" % pick
+    out["ok"] = bool(out["index_mismatches"] == 0 and out["max_rel_err_W"] < 1e-9 and out["max_rel_err_grad"] < 1e-7)
+    return out
+
+
+SWEEP_BATCH = 8192
+
+
+def sweep_fixed_total(B, C, dist, world, rank, dev, total, t, grids, target, status):
+    """cfg5 as BASELINE.json names it: `total` windows over all GPUs (fixed total = strong scaling), generated on
+    the device batch by batch (batch g of SWEEP_BATCH windows has seed 7e6 + g whatever the number of GPUs, so every
+    N evaluates the SAME windows), fused misfit + gradient, fixed-order local sums, ONE allreduce of
+    [sum misfit, sum gradient] at the end.  Returns (seconds = max over ranks, windows, checksum)."""
+    import torch
+    from waveform_ot_b200 import dist as wd
+    nb = SWEEP_BATCH
+    nbatches = max(1, total // nb)
+    lo, hi = wd.shard_bounds(nbatches, rank, world)
+    C_out = 2 + 2 * NT + 1
+    ws = torch.empty(C.lib.wfot_misfit_grad_workspace_bytes(nb, NT, NUG, NTG), dtype=torch.uint8, device=dev)
+    packed = torch.empty((nb, C_out), dtype=torch.float64, device=dev)
+    acc = torch.zeros(C_out, dtype=torch.float64, device=dev)
+    tot_buf = torch.empty(C_out, dtype=torch.float64, device=dev)
+    sum_ws = torch.empty(C.lib.wfot_sum_windows_workspace_bytes(C_out), dtype=torch.uint8, device=dev)
+    res = None
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for gb in range(lo, hi):
+        w = make_windows_device(nb, NT, 7_000_000 + gb, dev)
+        res = B.misfit_grad_batch(t, w, grids, NUG, NTG, LAM, target, distfunc="W2", status=status, workspace=ws, out=res)
+        packed[:, 0:2] = res["W"]
+        packed[:, 2] = res["dwg"]
+        packed[:, 3:] = res["grad"].reshape(nb, 2 * NT)
+        acc += B.sum_windows(packed, out=tot_buf, workspace=sum_ws)
+    if world > 1:
+        dist.all_reduce(acc)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / 1e3, nbatches * nb, [float(acc[0].item()), float(acc[1].item()),
+                                                  float(acc[2].item()), float(acc[3:].sum().item())]
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -418,6 +585,7 @@ def run_ours(args):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
+    launches0 = C.lib.wfot_dev_kernel_launches()
     s_ev.record()
     for i in range(args.steps):
         w = pools[(args.warmup + i) % n_pool]
@@ -432,6 +600,8 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tot)
     e_ev.record()
+    launches_per_step = (C.lib.wfot_dev_kernel_launches() - launches0) // max(1, args.steps)
+    launches_call = launches_per_step - 2          # minus the two kernels of the window sum
     torch.cuda.synchronize()
     wall1 = time.time()
     if world > 1:
@@ -504,6 +674,34 @@ def run_ours(args):
     h2d = nb * NT * 4 + NT * 4
     d2h = nb * (2 + 1 + 2 * NT) * 8
 
+    # ---- checks outside the timed regions
+    allreduce_check = None
+    if world > 1:      # the allreduced vector against the rank-ordered sum of the all-gathered local sums
+        r = res = B.misfit_grad_batch(t, pools[0], grids, NUG, NTG, LAM, target, distfunc="W2", status=status,
+                                      workspace=ws, out=res)
+        packed[:, 0:2] = r["W"]; packed[:, 2] = r["dwg"]; packed[:, 3:] = r["grad"].reshape(nb, 2 * NT)
+        local_sum = B.sum_windows(packed, out=tot_buf, workspace=sum_ws).clone()
+        gathered = [torch.empty_like(local_sum) for _ in range(world)]
+        dist.all_gather(gathered, local_sum)
+        reduced = local_sum.clone()
+        dist.all_reduce(reduced)
+        ordered = torch.stack(gathered).sum(dim=0)
+        rel = ((reduced - ordered).abs() / ordered.abs().clamp_min(1e-300)).max()
+        allreduce_check = {"max_rel_diff": float(rel.item()), "ranks": world, "vector_len": int(C_out),
+                           "ok": bool(rel.item() <= 1e-12)}
+    parity = None
+    if rank == 0 and args.parity_windows > 0:
+        parity = parity_check(B, C, t, pools[args.warmup % n_pool], obs[0],
+                              lambda w: B.misfit_grad_batch(t, w, grids, NUG, NTG, LAM, target, distfunc="W2",
+                                                            status=B.Status(), workspace=ws), args.parity_windows)
+    sweep = None
+    if args.sweep_windows > 0:
+        sw_s, sw_n, sw_sum = sweep_fixed_total(B, C, dist, world, rank, dev, args.sweep_windows, t, grids, target, status)
+        sweep = {"windows": sw_n, "seconds": sw_s, "evals_per_s": sw_n / sw_s, "scaling": "strong (fixed total)",
+                 "checksum": {"sum_Wt": sw_sum[0], "sum_Wu": sw_sum[1], "sum_dwg": sw_sum[2], "sum_grad": sw_sum[3]},
+                 "note": "windows generated on the device inside the timed region, batches of %d, one allreduce at the "
+                         "end; identical windows for every GPU count (checksums comparable across N)" % SWEEP_BATCH}
+
     st = status.read()
     if rank == 0:
         total_windows = world * nb * args.steps
@@ -525,29 +723,39 @@ def run_ours(args):
             "config": {"workload": "cfg5: 1024-sample windows -> 256x256 fingerprint, W2 misfit + gradient",
                        "nt": NT, "nug": NUG, "ntg": NTG, "lambda": LAM, "windows_per_gpu_per_step": nb,
                        "global_windows_per_step": world * nb,
-                       "l2": "3 input batches cycled; per-step scratch (28 B/pixel x resident CTAs) + inputs exceed the 126 MB L2",
+                       "l2": "3 input batches cycled; per-step scratch (8 B/pixel scan results per window + 20 B/pixel x resident CTAs) + inputs exceed the 126 MB L2",
                        "parallelism": "windows sharded over %d GPU(s), one allreduce of [sum misfit, sum grad]" % world},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak_tflops, "traffic": traffic,
-                         "kernel": "k_misfit_grad", "kernel_ms": k_ms, "kernel_ms_steps": k_steps,
+                         "kernel": "k_scan + k_resolve (the two-kernel form of the fused path; one call = %d launches)" % launches_call,
+                         "kernel_ms": k_ms, "kernel_ms_steps": k_steps,
                          # exact pruning: the scan evaluates only this fraction of the brute-force
                          # (pixel, segment) pairs the algorithmic count is made of (SURVEY 8d asks for both)
                          "executed_pair_fraction": exec_frac,
                          "achieved_executed": achieved * exec_frac, "frac_executed": achieved * exec_frac / fp32_peak_tflops,
                          "peak_source": "FFMA2 probe measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core entry)",
-                         "algorithmic_flop_per_window": ALG_FLOP_PER_WINDOW},
+                         "algorithmic_flop_per_window": ALG_FLOP_PER_WINDOW,
+                         "note": "achieved = 15 FLOP x pixels x segments (brute-force Enumerate count, SURVEY 8d) / device time "
+                                 "of the call; the per-kernel split (scan ~38 %, resolve ~62 %) and their counters are in "
+                                 "profiles/r02_*"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": nrep, "pipeline": "2 streams, copies of one step overlap the next step's kernel"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
+            "parity_check": parity,
+            "allreduce_check": allreduce_check,
+            "sweep_4M": sweep,
             "status_counters": {"slow_pixels": int(st[4]), "common_cdf": int(st[1]), "zero_dist": int(st[2])},
         }
         if world == 1 and args.secondary:
             line["secondary"] = secondary_configs(dev)
         if world == 1 and args.cpu_sample > 0:
-            v, dt = cpu_eval_rate(args.cpu_sample, 1)
-            line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
-                                    "sample": "%d windows of the same workload, oracle/wfot_oracle.py (NumPy FP64), %.1f s" % (args.cpu_sample, dt)}
+            kind = cpu_kind()
+            v, dt, per = cpu_eval_rate(args.cpu_sample, 1, kind)
+            line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": kind,
+                                    "sample": "%d windows of the same workload on one core, %s, %.1f s" % (
+                                        args.cpu_sample, "unmodified reference modules (oracle/_ref)" if kind == "reference"
+                                        else "oracle/wfot_oracle.py (NumPy FP64)", dt)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -7,6 +7,8 @@
 #ifndef WFOT_DEV_H
 #define WFOT_DEV_H
 
+#include <stdint.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -18,6 +20,15 @@ int wfot_fp32_peak_probe(int packed, int iters, float* sink, double* fma_ops, vo
 /* Process-wide tuning switch (see csrc/wfot_dev_options.h for the ids); value 0 restores the
  * library's own choice.  Returns the previous value, or -1 for an unknown id. */
 int wfot_dev_set_option(int id, int value);
+
+/* Number of kernels the library has launched in this process so far (bench.py's gpu_launches). */
+long long wfot_dev_kernel_launches(void);
+
+/* While `iray` is non-NULL, every wfot_misfit_grad_batch / wfot_marginal_cdfs_batch call also writes the
+ * nearest-segment index of every pixel of every window to iray (B, nug * ntg) int32 (device memory owned by the
+ * caller, large enough for the largest call made).  bench.py uses it to check the TIMED kernels' indices
+ * against the CPU oracle after the timed region.  NULL switches the capture off. */
+void wfot_dev_capture_iray(int32_t* iray);
 
 #ifdef __cplusplus
 }

@@ -54,14 +54,23 @@ opt(C.OPT_PIPELINE, 1)
 ms0, r0, st0 = run()
 print("%s B=%d  single-kernel: %.3f ms  %.1f evals/s  status %s" % (name, nb, ms0, nb / ms0 * 1e3, st0[:5].tolist()), flush=True)
 W0, G0, D0 = r0["W"].clone(), r0["grad"].clone(), r0["dwg"].clone()
-for shape in (1, 2, 3):
-    opt(C.OPT_PIPELINE, 2)
-    opt(C.OPT_RESOLVE_SHAPE, shape)
+# (label, overlap[0 two streams / 1 sequential], resolve shape, chunk, scan shape)
+VARIANTS = [("two streams 8/SM, scan x3, resolve warp-per-row 80 regs x3", 0, 0, 0, 3),
+            ("two streams 8/SM, scan x3, resolve warp-per-row 128 regs x2 (P4 unroll 8)", 0, 1, 0, 3),
+            ("two streams 8/SM, scan x3, resolve pixel-per-thread rotated 256x3", 0, 2, 0, 3),
+            ("two streams 8/SM, scan x3, resolve pixel-per-thread rotated 512x2", 0, 3, 0, 3),
+            ("sequential one chunk, scan x3, resolve pixel-per-thread rotated 256x3", 1, 2, nb, 3),
+            ("sequential one chunk, scan x3, resolve warp-per-row 128 regs x2", 1, 1, nb, 3)]
+if len(sys.argv) > 3:
+    VARIANTS = [v for i, v in enumerate(VARIANTS) if str(i) in sys.argv[3].split(",")]
+for label, ov, shape, chunk, sc in VARIANTS:
+    opt(C.OPT_PIPELINE, 2); opt(C.OPT_OVERLAP, ov); opt(C.OPT_RESOLVE_SHAPE, shape); opt(C.OPT_SPLIT_CHUNK, chunk)
+    opt(C.OPT_SCAN_SHAPE, sc)
     ms, r, st = run()
     dW = (r["W"] - W0).abs().max().item()
     dD = (r["dwg"] - D0).abs().max().item()
     dG = ((r["grad"] - G0).abs().max() / G0.abs().max()).item()
-    print("%s B=%d  scan+resolve shape %d: %.3f ms  %.1f evals/s  max|dW| %.3g max|ddwg| %.3g max rel dgrad %.3g status %s" % (
-        name, nb, shape, ms, nb / ms * 1e3, dW, dD, dG, st[:5].tolist()), flush=True)
-opt(C.OPT_PIPELINE, 0)
-opt(C.OPT_RESOLVE_SHAPE, 0)
+    print("%s B=%d  %s: %.3f ms  %.1f evals/s  max|dW| %.3g max|ddwg| %.3g max rel dgrad %.3g status %s" % (
+        name, nb, label, ms, nb / ms * 1e3, dW, dD, dG, st[:5].tolist()), flush=True)
+for i in range(8):
+    opt(i, 0)

@@ -65,8 +65,11 @@ SIGNATURES = {
 DEV_SIGNATURES = {
     "wfot_fp32_peak_probe": (C.c_int, [_i, _i, _p, _p, _p]),
     "wfot_dev_set_option": (C.c_int, [_i, _i]),
+    "wfot_dev_capture_iray": (None, [_p]),
+    "wfot_dev_kernel_launches": (C.c_longlong, []),
 }
-OPT_PIPELINE, OPT_RESOLVE_SHAPE, OPT_FUSED_THREADS, OPT_CLUSTER_MAX, OPT_TILE, OPT_SPLIT_CHUNK = range(6)
+(OPT_PIPELINE, OPT_RESOLVE_SHAPE, OPT_FUSED_THREADS, OPT_CLUSTER_MAX, OPT_TILE, OPT_SPLIT_CHUNK, OPT_OVERLAP,
+ OPT_SCAN_SHAPE) = range(8)
 
 for _name, (_res, _args) in list(SIGNATURES.items()) + list(DEV_SIGNATURES.items()):
     _f = getattr(lib, _name)       # AttributeError here = header/library mismatch

@@ -95,36 +95,82 @@ def optfunc_ricker(x, data, forward):
     return w2, deriv
 
 
-def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfunc="W2", Wopt="Wavg"):
+def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfunc="W2", Wopt="Wavg",
+                       chunk_models=512):
     """Batched libs/loc_cmt_util.py:251-296.  seis_pred (M, nr, nc, nt) predicted seismograms of M
     trial models; obs_grids[i][j] = (t0,t1,u0,u1,Nu,Nt) per station/component (u-box from the
     observed window, :430-446); targets = Target with one row per (i,j) (built from the arctan-
     transformed observations); J (M, P, nr*nc*nt) Jacobian d(seis)/d(model) or None.
-    Returns mis (M,), dmis (M, P) or None, dr (M, nr, nc, nt)."""
+    Returns mis (M,), dmis (M, P) or None, dr (M, nr, nc, nt).
+
+    seis_pred / J may be NumPy arrays, pinned host tensors or device tensors.  Host inputs are streamed in
+    chunks of `chunk_models` models on a copy stream while the previous chunk is evaluated (the Jacobians are the
+    bulk: 132 KB per model at the Figs 9-11 shape), so the host -> device transfer hides behind the kernels; with
+    pinned tensors the copies are fully asynchronous."""
     import torch
-    seis = np.ascontiguousarray(seis_pred)
+    dev = _B._device()
+    as_t = lambda x: x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+    seis = as_t(seis_pred)
     M, nr, nc, nt = seis.shape
+    nw = nr * nc
+    Jt = None if J is None else as_t(J)
+    P = 0 if Jt is None else int(Jt.shape[1])
     Nu, Nt = int(obs_grids[0][0][4]), int(obs_grids[0][0][5])
     flat = [tuple(obs_grids[i][j][:4]) + (Nu, Nt) for i in range(nr) for j in range(nc)]
     g = _B.pack_grids(flat)                                    # (nr*nc, 80 B): window b = m*(nr*nc) + i*nc + j uses
     #                                                            grid / observed window b % (nr*nc) (no per-model copies)
-    r = _B.misfit_grad_batch(t, seis.reshape(M * nr * nc, nt), g, Nu, Nt, lambdav, targets, distfunc=distfunc,
-                             transform=True)
-    W = r["W"].reshape(M, nr * nc, 2)
-    gr = r["grad"].reshape(M, nr * nc, 2, nt)
-    if Wopt == "Wavg":                                          # OTlib.py:1136,1150
-        mis = 0.5 * (W[..., 0] + W[..., 1]).sum(dim=1)
-        dr = 0.5 * (gr[:, :, 0] + gr[:, :, 1])
-    elif Wopt == "Wt":
-        mis, dr = W[..., 0].sum(dim=1), gr[:, :, 0]
-    else:
-        mis, dr = W[..., 1].sum(dim=1), gr[:, :, 1]
-    dmis = None
-    if J is not None:
-        dmis = _B.chain_batch(J, dr.reshape(M, nr * nc * nt).contiguous())        # :296
-    torch.cuda.current_stream().synchronize()
-    r["status"].raise_for_reference(what="misfit_grad_models")
-    return mis.cpu().numpy(), None if dmis is None else dmis.cpu().numpy(), dr.reshape(M, nr, nc, nt).cpu().numpy()
+    t_dev = _B._as_device(t, torch.float64)
+    f64 = dict(dtype=torch.float64, device=dev)
+    mis_all = torch.empty(M, **f64)
+    dmis_all = torch.empty((M, P), **f64) if Jt is not None else None
+    dr_all = torch.empty((M, nw, nt), **f64)
+    status = _B.Status()
+    main = torch.cuda.current_stream()
+    copy = torch.cuda.Stream(device=dev)
+    copy.wait_stream(main)
+    cm = max(1, min(int(chunk_models), M))
+    ws = torch.empty(_B.C.lib.wfot_misfit_grad_workspace_bytes(cm * nw, nt, Nu, Nt), dtype=torch.uint8, device=dev)
+    staged = {}
+
+    def stage(c0):
+        c1 = min(c0 + cm, M)
+        with torch.cuda.stream(copy):
+            sd = seis[c0:c1].reshape((c1 - c0) * nw, nt).to(dev, dtype=torch.float64, non_blocking=True)
+            jd = None if Jt is None else Jt[c0:c1].to(dev, dtype=torch.float64, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        staged[c0] = (sd, jd, ev, c1)
+
+    stage(0)
+    for c0 in range(0, M, cm):
+        sd, jd, ev, c1 = staged.pop(c0)
+        main.wait_event(ev)
+        r = _B.misfit_grad_batch(t_dev, sd, g, Nu, Nt, lambdav, targets, distfunc=distfunc, transform=True,
+                                 status=status, workspace=ws)
+        if c1 < M:
+            stage(c1)                                           # next chunk's copies run under this chunk's kernels
+        m = c1 - c0
+        W = r["W"].reshape(m, nw, 2)
+        gr = r["grad"].reshape(m, nw, 2, nt)
+        if Wopt == "Wavg":                                      # OTlib.py:1136,1150
+            mis_all[c0:c1] = 0.5 * (W[..., 0] + W[..., 1]).sum(dim=1)
+            dr = 0.5 * (gr[:, :, 0] + gr[:, :, 1])
+        elif Wopt == "Wt":
+            mis_all[c0:c1] = W[..., 0].sum(dim=1)
+            dr = gr[:, :, 0]
+        else:
+            mis_all[c0:c1] = W[..., 1].sum(dim=1)
+            dr = gr[:, :, 1]
+        dr_all[c0:c1] = dr
+        if jd is not None:
+            dmis_all[c0:c1] = _B.chain_batch(jd, dr_all[c0:c1].reshape(m, nw * nt))        # :296
+        sd.record_stream(main)
+        if jd is not None:
+            jd.record_stream(main)
+    main.synchronize()
+    status.raise_for_reference(what="misfit_grad_models")
+    return (mis_all.cpu().numpy(), None if dmis_all is None else dmis_all.cpu().numpy(),
+            dr_all.reshape(M, nr, nc, nt).cpu().numpy())
 
 
 def optfunc_ricker_batch(X, data):

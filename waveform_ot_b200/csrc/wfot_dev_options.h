@@ -6,12 +6,14 @@ namespace wfot {
 
 enum DevOption {
     kOptPipeline = 0,      // fused path: 0 auto, 1 single-kernel form, 2 two-kernel (scan + resolve) form
-    kOptResolveShape = 1,  // k_resolve CTA shape: 0 auto, 1 = 256 thr x 2/SM, 2 = 256 x 3, 3 = 512 x 2
+    kOptResolveShape = 1,  // k_resolve: 0 auto, 1 = 128 registers x 2 CTAs/SM, 2 = 80 registers x 3 CTAs/SM
     kOptFusedThreads = 2,  // k_misfit_grad threads per CTA: 0 auto, 64 / 128 / 256
     kOptClusterMax = 3,    // largest thread-block cluster per window: 0 auto (8), 1 = no clusters
     kOptTile = 4,          // argmin tile: 0 auto, 8 or 16 segments
     kOptSplitChunk = 5,    // windows per scan/resolve launch pair: 0 auto
-    kOptCount = 8
+    kOptOverlap = 6,       // two-kernel form: 0 auto (resolve of chunk c next to the scan of chunk c + 1), 1 sequential
+    kOptScanShape = 7,     // k_scan CTAs per SM: 0 auto (3, 80 registers), 2 = 2 per SM (128 registers)
+    kOptCount = 12
 };
 
 int dev_option(int id);

@@ -204,6 +204,8 @@ __device__ __forceinline__ unsigned tile_mask(const SegTable& tb, int tile, floa
 
 // FP64 reference-order evaluation of the candidate segments of one tile, ascending (strict '<'
 // keeps np.argmin's first-minimum rule across calls made in ascending tile order).
+// (Measured and dropped: evaluating candidates in consecutive pairs with a shared vertex load - two independent
+// FP64 chains per pass - costs registers and an unused evaluation for lone candidates: -4 % on cfg5.)
 template <int T>
 __device__ __forceinline__ void eval_candidates(const double2* __restrict__ pn, int tile, unsigned mask,
                                                 double px, double py, PixelHit& hit) {
@@ -534,7 +536,7 @@ struct PrepOut {
     double2* pn;    // [nt]
     float4* A;      // [Spad]  pair layout, see SegTable
     float* H;       // [Spad]
-    float4* bbox;   // [Spad / tile]  per-tile vertex bounding boxes (scaled frame)
+    float4* bbox;   // [Spad / tile]  per-tile vertex bounding boxes (scaled frame); nullptr: not wanted
     int tile;       // segments per tile (8 or 16)
     float* pxs;     // [ntg]  scaled local pixel time coordinates
     float* pys;     // [nug]
@@ -624,7 +626,7 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
         tabE[at] = A.x; tabE[at + 2] = A.y; tabM[at] = A.z; tabM[at + 2] = A.w;
         o.H[s] = h;
     }
-    for (int tile = tid; tile < Spad / o.tile; tile += nth) {
+    for (int tile = tid; o.bbox != nullptr && tile < Spad / o.tile; tile += nth) {
         const int s0 = min(tile * o.tile, S), s1 = min(s0 + o.tile, S);      // vertices s0 .. s1 inclusive
         double xlo = CUDART_INF, xhi = -CUDART_INF, ylo = CUDART_INF, yhi = -CUDART_INF;
         for (int j = s0; j <= s1; ++j) {

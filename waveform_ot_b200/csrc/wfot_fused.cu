@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     (void)s_margt; (void)s_margu; (void)s_Rt; (void)s_Ru; (void)s_cf; (void)s_E; (void)s_tk; (void)s_dx;
-    (void)s_gbins; (void)s_posf;
+    (void)s_gbins; (void)s_posf; (void)s_colpart;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     // Small batches (fewer windows than resident CTAs) are launched as thread-block clusters: the CTAs of a
@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
         //                  (the pruned scan makes their cost uneven).
         const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(s_pxs[a.ntg - 1] - s_pxs[0]),
                                            fabsf(s_pys[a.nug - 1] - s_pys[0]));
+        int32_t* const dbg = a.dbg_iray ? a.dbg_iray + (size_t)b * npix : nullptr;
         for (;;) {
             int f = 0;
             if (lane == 0) f = atomicAdd(s_qcount + 1, 1) * csize + crank;     // this CTA's share of the footprints
@@ -106,22 +107,22 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
                 PixelHit hit;
                 if (!resolve_pixel<T>(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, kb1, lt1[k], lb2[k], lb3[k], hit)) {
                     const int qi = atomicAdd(s_qcount, 1);
-                    if (qi < kFQCap) { s_queue[qi] = FQEntry{iu * a.ntg + it, kb1}; continue; }
+                    if (qi < a.L.qcap) { s_queue[qi] = FQEntry{iu * a.ntg + it, kb1}; continue; }
                     ++slow;
                     resolve_pixel_full(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, kb1, hit);
                 }
-                store_pixel(a, s_pn, slab, it, iu, hit, pyd, zero_dist);
+                store_pixel(a, s_pn, slab, it, iu, hit, pyd, zero_dist, dbg);
             }
         }
         __syncthreads();
         {
-            const int nq = min(*s_qcount, kFQCap);
+            const int nq = min(*s_qcount, a.L.qcap);
             for (int e = warp; e < nq; e += NT / 32) {
                 const FQEntry qe = s_queue[e];
                 const int it = qe.pix % a.ntg, iu = qe.pix / a.ntg;
                 PixelHit hit;
                 resolve_pixel_warp(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], s_xu[iu], qe.b1, hit);
-                if (lane == 0) { store_pixel(a, s_pn, slab, it, iu, hit, s_xu[iu], zero_dist); ++slow; }
+                if (lane == 0) { store_pixel(a, s_pn, slab, it, iu, hit, s_xu[iu], zero_dist, dbg); ++slow; }
             }
         }
         __syncthreads();   // scratch slab complete (block-scope visibility of global writes)
@@ -153,6 +154,7 @@ using namespace wfot;
 
 namespace wfot {
 static int g_dev_options[kOptCount] = {0};
+static int32_t* g_iray_capture = nullptr;
 int dev_option(int id) { return (id >= 0 && id < kOptCount) ? g_dev_options[id] : 0; }
 }  // namespace wfot
 
@@ -161,6 +163,7 @@ int dev_option(int id) { return (id >= 0 && id < kOptCount) ? g_dev_options[id] 
 static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     const int nt = a.nt, nug = a.nug, ntg = a.ntg, B = a.B;
     a.rlambda = 1.0 / a.lambda;
+    a.dbg_iray = g_iray_capture;
     a.Spad = seg_pad(nt); a.ntg_pad = pad4(ntg); a.nug_pad = pad4(nug);
     a.nmax = pad4(ntg > nug ? ntg : nug);
     a.L = make_layout(nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax);
@@ -227,6 +230,7 @@ static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaS
     else { if (nthreads == 64) WFOT_LAUNCH(64, 16); else if (nthreads == 128) WFOT_LAUNCH(128, 16); else WFOT_LAUNCH(256, 16); }
 #undef WFOT_LAUNCH
     if (le != cudaSuccess) return cuda_fail(le, "wfot_misfit_grad_batch launch");
+    note_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_misfit_grad_batch launch");
     return WFOT_OK;
@@ -244,6 +248,8 @@ int wfot_dev_set_option(int id, int value) {
 // Scratch: 28 bytes per pixel per resident CTA (sized for SM count x 8 CTAs so the query needs no
 // occupancy call), plus - for batches that take the two-kernel form - 8 bytes per pixel per window
 // of one scan/resolve launch pair.
+void wfot_dev_capture_iray(int32_t* iray) { g_iray_capture = iray; }
+
 size_t wfot_misfit_grad_workspace_bytes(int B, int nt, int nug, int ntg) {
     if (B <= 0 || nt < 2 || nug < 1 || ntg < 1) return 0;
     int sms = wfot_device_sm_count();

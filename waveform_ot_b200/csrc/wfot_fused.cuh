@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "wfot_device.cuh"
 #include "wfot_host.h"
@@ -18,17 +19,29 @@ namespace wfot {
 
 constexpr int kFQCap = 512;
 struct FQEntry { int pix; float b1; };
+// Column sums of the density are defined as: rows split into kRowGroups groups by (row mod kRowGroups), each group
+// summed in ascending row order, the group sums combined as ((g0+g1)+(g2+g3))+((g4+g5)+(g6+g7)).  Every form of the
+// path (slab pass of the single-kernel form, warp-per-row accumulation of the resolve kernel) realises this order,
+// so the marginals - and the CDFs compared for exact equality - do not depend on the launch shape.
+constexpr int kRowGroups = 8;
 
 // Shared-memory layout (byte offsets from the dynamic shared base).  Pointers are formed
 // from the `extern __shared__` symbol inside each kernel so the compiler keeps them in the
 // shared address space (LDS/STS instead of generic loads).
 struct SmemLayout {
     int pn, A, H, bbox, keys, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
+    int colpart;    // resolve kernel: per-row-group column sums of the density, [kRowGroups][ntg_pad] doubles
+    int qcap;       // entries of the ambiguous-pixel queue
     int total;
 };
 
-inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nmax) {
+enum LayoutKind { kLayoutFused = 0, kLayoutScan = 1, kLayoutResolve = 2 };
+
+// kLayoutScan keeps only what prep_window + scan_block touch; kLayoutResolve drops the tile boxes and keys (and
+// halves the queue) so that four 256-thread CTAs fit one SM.
+inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nmax, int kind = kLayoutFused) {
     SmemLayout L;
+    memset(&L, 0, sizeof(L));
     int o = 0;
     auto take = [&](int bytes) { const int at = o; o += (bytes + 15) & ~15; return at; };
     L.pn = take(nt * 16);
@@ -37,27 +50,33 @@ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nm
     const int ubase = o;
     L.A = take(Spad * 16);
     L.H = take(Spad * 4);
-    const int ntiles = Spad / tile_for(nt);
-    L.bbox = take(ntiles * 16);
-    L.keys = take(8 * ntiles * 4);                // best-first tile keys, one array per warp (<= 8 warps)
+    if (kind != kLayoutResolve) {
+        const int ntiles = Spad / tile_for(nt);
+        L.bbox = take(ntiles * 16);
+        L.keys = take(8 * ntiles * 4);            // best-first tile keys, one array per warp (<= 8 warps)
+    }
     const int uend_scan = o;
-    o = ubase;
-    L.cf = take(nmax * 8);
-    L.E = take(nmax * 8);
-    L.tk = take(nmax * 16);
-    L.dx = take(nmax * 16);
-    L.posf = take(nmax * 4);
-    L.gbins = take(nt * 8);
-    o = o > uend_scan ? o : uend_scan;
-    L.margt = take(ntg_pad * 8);
-    L.margu = take(nug_pad * 8);
-    L.Rt = take(ntg_pad * 8);
-    L.Ru = take(nug_pad * 8);
-    L.xt = take(ntg_pad * 8);
-    L.xu = take(nug_pad * 8);
+    if (kind != kLayoutScan) {
+        o = ubase;
+        L.cf = take(nmax * 8);
+        L.E = take(nmax * 8);
+        L.tk = take(nmax * 16);
+        L.dx = take(nmax * 16);
+        L.posf = take(nmax * 4);
+        L.gbins = take(nt * 8);
+        o = o > uend_scan ? o : uend_scan;
+        L.margt = take(ntg_pad * 8);
+        L.margu = take(nug_pad * 8);
+        L.Rt = take(ntg_pad * 8);
+        L.Ru = take(nug_pad * 8);
+        L.xt = take(ntg_pad * 8);
+        L.xu = take(nug_pad * 8);
+        if (kind == kLayoutResolve) L.colpart = take(kRowGroups * ntg_pad * 8);
+        L.qcap = (kind == kLayoutResolve) ? kFQCap / 2 : kFQCap;
+        L.queue = take(L.qcap * (int)sizeof(FQEntry));
+    }
     L.red = take(64 * 8);
     L.hdr = take(128);
-    L.queue = take(kFQCap * (int)sizeof(FQEntry));
     L.pxs = take(ntg_pad * 4);
     L.pys = take(nug_pad * 4);
     L.qcount = take(16);
@@ -75,6 +94,8 @@ struct FusedArgs {
     // observed-window mode (wfot_marginal_cdfs_batch): stop after the CDFs of the two marginals and write them
     // (B, ntg) / (B, nug) and the 2-D amplitude (B,) instead of running the OT against a target
     double* out_cdf_t; double* out_cdf_u; double* out_amp;
+    // measurement aid (wfot_dev.h): nearest-segment index of every pixel of every window, (B, nug * ntg) int32
+    int32_t* dbg_iray;
     // per-CTA scratch slabs
     double* s_pdf; double* s_wa; double* s_wb; int32_t* s_idx;
     int32_t* status;
@@ -112,6 +133,7 @@ constexpr unsigned kScanFlag2 = 1u << 30, kScanFlag3 = 1u << 31, kScanTileMask =
     double* const s_dx = reinterpret_cast<double*>(smem_raw + (L).dx);                   \
     double* const s_red = reinterpret_cast<double*>(smem_raw + (L).red);                 \
     double* const s_gbins = reinterpret_cast<double*>(smem_raw + (L).gbins);             \
+    double* const s_colpart = reinterpret_cast<double*>(smem_raw + (L).colpart);         \
     int* const s_posf = reinterpret_cast<int*>(smem_raw + (L).posf);                     \
     FQEntry* const s_queue = reinterpret_cast<FQEntry*>(smem_raw + (L).queue);           \
     WinHdr* const s_hdr = reinterpret_cast<WinHdr*>(smem_raw + (L).hdr);                 \
@@ -123,8 +145,10 @@ constexpr unsigned kScanFlag2 = 1u << 30, kScanFlag3 = 1u << 31, kScanTileMask =
 // fused-multiply-add corrections: d = D r + (D - (D r)^2) r / 2, the quotients by Markstein's q0 = a y,
 // q = q0 + (a - b q0) y with y = RN(1 / b) (correctly rounded but for rare half-ulp cases; the density then
 // differs from the materialising kernel's by <= 1 ulp of the exponent, i.e. ~1e-15 relative).
-__device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* pn, size_t slab,
-                                            int it, int iu, const PixelHit& hit, double py, int& zero_dist) {
+template <bool STORE_PDF = true>
+__device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2* pn, size_t slab,
+                                              int it, int iu, const PixelHit& hit, double py, int& zero_dist,
+                                              int32_t* dbg_iray = nullptr) {
     const double* const pny = reinterpret_cast<const double*>(pn) + 1;
     const double ay = pny[2 * hit.s], by = pny[2 * hit.s + 2];
     const double cy = __dsub_rn(by, ay);
@@ -149,10 +173,12 @@ __device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* p
     double wgt = pdf * g;                                      // pdf * dddx_y
     if (a.q == 2) wgt *= 2.0 * d;                              // :214-217
     const size_t k = slab + (size_t)iu * a.ntg + it;
-    a.s_pdf[k] = pdf;
+    if (STORE_PDF) a.s_pdf[k] = pdf;
     a.s_wa[k] = (1.0 - hit.lam) * wgt;                         // -> sample iray    (:223)
     a.s_wb[k] = hit.lam * wgt;                                 // -> sample iray+1  (:224)
     a.s_idx[k] = hit.s;
+    if (dbg_iray) dbg_iray[(size_t)iu * a.ntg + it] = hit.s;
+    return pdf;
 }
 
 // ------------------------------------------------------------------ window tail: P2-P4
@@ -163,37 +189,54 @@ __device__ __forceinline__ void store_pixel(const FusedArgs& a, const double2* p
 //       equal nearest segment and adds each run to the window's gradient rows with fire-and-forget FP64
 //       reductions in L2 (RED.ADD.F64; shared-memory FP64 atomics are CAS loops).  The rows were zeroed in P0.
 // Returns the number of exact source/target CDF coincidences (libs/OTlib.py:663-666) in thread 0.
-template <int NT>
+template <int NT, bool HAVE_SUMS = false, int P4R = 4>
 __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* smem_raw, int b, size_t slab,
                                            const WinHdr& hdr) {
     WFOT_SMEM_POINTERS(a.L);
     (void)s_pn; (void)s_A; (void)s_H; (void)s_bbox; (void)s_keys; (void)s_pxs; (void)s_pys; (void)s_queue;
-    (void)s_hdr; (void)s_qcount;
+    (void)s_hdr; (void)s_qcount; (void)s_colpart;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // ---------------- P2 (8 independent loads in flight per thread)
-    for (int c = tid; c < a.ntg; c += NT) {
-        const double* col = a.s_pdf + slab + c;
-        double s0 = 0.0;
-        int iu = 0;
-        for (; iu + 8 <= a.nug; iu += 8) {
-            double v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldcg(col + (size_t)(iu + j) * a.ntg);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s0 += v[j];
+    // ---------------- P2: column sums (kRowGroups groups of rows, see above)
+    if (HAVE_SUMS) {   // the resolve kernel accumulated the groups (s_colpart) and the raw row sums (s_margu) in P1
+        for (int c = tid; c < a.ntg; c += NT) {
+            const double* g = s_colpart + c;
+            const int st = a.ntg_pad;
+            s_margt[c] = ((g[0] + g[st]) + (g[2 * st] + g[3 * st])) + ((g[4 * st] + g[5 * st]) + (g[6 * st] + g[7 * st]));
         }
-        for (; iu < a.nug; ++iu) s0 += __ldcg(col + (size_t)iu * a.ntg);
-        s_margt[c] = s0;
+    } else {
+        for (int c = tid; c < a.ntg; c += NT) {
+            const double* col = a.s_pdf + slab + c;
+            double g[kRowGroups];
+#pragma unroll
+            for (int j = 0; j < kRowGroups; ++j) g[j] = 0.0;
+            int iu = 0;
+            for (; iu + kRowGroups <= a.nug; iu += kRowGroups) {
+                double v[kRowGroups];
+#pragma unroll
+                for (int j = 0; j < kRowGroups; ++j) v[j] = __ldcg(col + (size_t)(iu + j) * a.ntg);
+#pragma unroll
+                for (int j = 0; j < kRowGroups; ++j) g[j] += v[j];
+            }
+#pragma unroll
+            for (int j = 0; j < kRowGroups; ++j)
+                if (iu + j < a.nug) g[j] += __ldcg(col + (size_t)(iu + j) * a.ntg);
+            s_margt[c] = ((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]));
+        }
     }
     __syncthreads();
     const double A = canon_sum(s_margt, a.ntg, s_red);               // OTpdf.amp (OTlib.py:92), launch-shape independent
-    for (int iu = warp; iu < a.nug; iu += NT / 32) {
-        const double* row = a.s_pdf + slab + (size_t)iu * a.ntg;
-        double s0 = 0.0;
-        for (int c = lane; c < a.ntg; c += 32) s0 += __ldcg(row + c);
+    if (HAVE_SUMS) {
+        for (int iu = tid; iu < a.nug; iu += NT) s_margu[iu] = s_margu[iu] / A;
+    } else {
+        // row sums: lane l adds columns l, l + 32, ... in ascending order, then a xor-shuffle tree
+        for (int iu = warp; iu < a.nug; iu += NT / 32) {
+            const double* row = a.s_pdf + slab + (size_t)iu * a.ntg;
+            double s0 = 0.0;
+            for (int c = lane; c < a.ntg; c += 32) s0 += __ldcg(row + c);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-        if (lane == 0) s_margu[iu] = s0 / A;                        // OTlib.py:93,156
+            for (int off = 16; off > 0; off >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+            if (lane == 0) s_margu[iu] = s0 / A;                        // OTlib.py:93,156
+        }
     }
     for (int c = tid; c < a.ntg; c += NT) s_margt[c] = s_margt[c] / A;     // OTlib.py:93,155
     __syncthreads();
@@ -261,16 +304,16 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
             const double ct = s_Rt[c];
             int cur = -1;
             double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
-            for (int iu0 = 0; iu0 < a.nug; iu0 += 4) {
-                int idx[4];
-                double wa[4], wb[4];
+            for (int iu0 = 0; iu0 < a.nug; iu0 += P4R) {
+                int idx[P4R];
+                double wa[P4R], wb[P4R];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < P4R; ++j) {
                     const size_t k = slab + (size_t)min(iu0 + j, a.nug - 1) * a.ntg + c;
                     idx[j] = __ldcg(a.s_idx + k); wa[j] = __ldcg(a.s_wa + k); wb[j] = __ldcg(a.s_wb + k);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < P4R; ++j) {
                     if (iu0 + j >= a.nug) break;
                     if (idx[j] != cur) {
                         if (cur >= 0) {

@@ -56,5 +56,7 @@ inline FpWorkspace fp_workspace_carve(void* base, int chunk, int nt, int nug, in
 
 extern thread_local char g_cuda_err[512];
 int cuda_fail(cudaError_t e, const char* what);
+// process-wide count of kernels launched by the library (wfot_dev_kernel_launches, bench.py's gpu_launches)
+void note_launches(int n);
 
 }  // namespace wfot

@@ -10,6 +10,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "wfot_device.cuh"
 #include "wfot_host.h"
 #include "../../include/wfot_dev.h"
@@ -18,6 +20,9 @@
 namespace wfot {
 
 thread_local char g_cuda_err[512] = "";
+
+static std::atomic<long long> g_kernel_launches{0};
+void note_launches(int n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
@@ -495,6 +500,7 @@ int wfot_fingerprint_batch(const void* t, const void* w, int in_dtype, long long
         const int nb = (int)((B - b0) < chunk ? (B - b0) : chunk);
         PrepArgs pa{t, w, in_dtype, t_stride, nt, grids, n_grids, b0, nug, ntg, 0, ws, pn, status, T};
         k_prep<<<nb, 256, 0, stream>>>(pa);
+        note_launches(2);
         FpArgs fa{ws, nt, b0, nug, ntg, lambda, q, dfield, iray, lray, xray, pdf, dddy, status};
         if (T == 8) k_fingerprint<R, 8><<<dim3(gx, nb), 256, smem, stream>>>(fa);
         else k_fingerprint<R, 16><<<dim3(gx, nb), 256, smem, stream>>>(fa);
@@ -513,6 +519,7 @@ int wfot_marginals_batch(const double* pdf, int B, int nug, int ntg, double* amp
     cudaError_t e = cudaFuncSetAttribute(k_marginals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_marginals)");
     k_marginals<<<B, 256, smem, stream>>>(pdf, nug, ntg, amp, marg_t, marg_u, status);
+    note_launches(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_marginals_batch launch");
     return WFOT_OK;
@@ -527,6 +534,7 @@ int wfot_otpdf1d_batch(const void* f, int in_dtype, int n, int B, double* amp, d
     cudaError_t e = cudaFuncSetAttribute(k_otpdf1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_otpdf1d)");
     k_otpdf1d<<<B, 256, smem, stream>>>(f, in_dtype, n, amp, pdf_norm, cdf, status);
+    note_launches(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_otpdf1d_batch launch");
     return WFOT_OK;
@@ -544,6 +552,7 @@ int wfot_pdfderiv_batch(const double* pdf, const double* dfield, const int32_t* 
     cudaError_t e = cudaFuncSetAttribute(k_pdfderiv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_pdfderiv)");
     k_pdfderiv<<<dim3(B, nchain), 256, smem, stream>>>(pdf, dfield, iray, dddy, chain, nchain, npix, nt, lambda, q, out);
+    note_launches(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_pdfderiv_batch launch");
     return WFOT_OK;
@@ -556,6 +565,7 @@ int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M, lon
     const long long warps = (long long)M * P;
     const int blocks = (int)((warps * 32 + 255) / 256);
     k_chain<<<blocks, 256, 0, stream>>>(J, dr, P, L, M, J_stride_models, out);
+    note_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_chain_batch launch");
     return WFOT_OK;
@@ -567,6 +577,7 @@ int wfot_ricker_batch(const double* params, int M, double t0, double t1, double*
     if (!params || !t || !w || M <= 0) return WFOT_ERR_INVALID_ARG;
     const double pi = 3.141592653589793;
     k_ricker<<<M, 256, 0, stream>>>(params, M, t0, t1, pi * pi, t, w, dw);
+    note_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_ricker_batch launch");
     return WFOT_OK;
@@ -582,10 +593,13 @@ int wfot_sum_windows(const double* in, long long B, int C, double* out, void* wo
     const int G = (int)(B < kSumGroups ? B : kSumGroups);
     k_sum_windows<<<dim3(G, (C + 255) / 256), 256, 0, stream>>>(in, B, C, (double*)workspace, G);
     k_sum_partials<<<(C + 255) / 256, 256, 0, stream>>>((const double*)workspace, G, C, out);
+    note_launches(2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_sum_windows launch");
     return WFOT_OK;
 }
+
+long long wfot_dev_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 int wfot_fp32_peak_probe(int packed, int iters, float* sink, double* fma_ops, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -671,6 +671,7 @@ extern "C" int wfot_ot1d_batch(const void* f, const void* g, int in_dtype, const
     const long long need = ((long long)B + a.wpc - 1) / a.wpc;
     if (grid > need) grid = need;
     k_ot1d_warp<<<(int)grid, 32 * a.wpc, smem, stream>>>(a);
+    note_launches(1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_ot1d_batch launch");
     return WFOT_OK;

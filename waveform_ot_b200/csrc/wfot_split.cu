@@ -21,18 +21,21 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "wfot_fused.cuh"
 #include "wfot_dev_options.h"
 
 namespace wfot {
 
 // ------------------------------------------------------------------ k_scan
-template <int R, int T>
-__global__ void __launch_bounds__(256, 2) k_scan(FusedArgs a) {
+template <int R, int T, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     (void)s_margt; (void)s_margu; (void)s_Rt; (void)s_Ru; (void)s_xt; (void)s_xu; (void)s_cf; (void)s_E;
-    (void)s_tk; (void)s_dx; (void)s_gbins; (void)s_posf; (void)s_queue;
+    (void)s_tk; (void)s_dx; (void)s_gbins; (void)s_posf; (void)s_queue; (void)s_colpart;
     const int tid = threadIdx.x, lane = tid & 31;
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T};
@@ -102,24 +105,33 @@ __global__ void __launch_bounds__(256, 2) k_scan(FusedArgs a) {
 }
 
 // ------------------------------------------------------------------ k_resolve
-template <int NT, int MINB, int T>
-__global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
+// 256 threads.  A warp owns the rows (warp, warp + 8, ...) of the window and walks each row 32 pixels at a time:
+// every warp sees every column, so the warps of a CTA finish together whatever the waveform looks like (with a
+// fixed column block per warp, the warps over the busy part of the waveform kept the others waiting at the
+// barrier: 13 % of all warp time), and the marginals are accumulated on the way - the lane-strided row sum in a
+// register, the row-group column sums (kRowGroups = 8 = warps) in shared memory - so the density itself is never
+// stored or re-read.  A pixel whose near-ties span distant tiles (a handful per window) is resolved in place by
+// the whole warp.
+template <int MINB, int T>
+__global__ void __launch_bounds__(256, MINB) k_resolve(FusedArgs a) {
+    constexpr int NT = 256;
+    static_assert(NT == 32 * kRowGroups, "one warp per row group");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
-    (void)s_bbox; (void)s_keys; (void)s_margt; (void)s_margu; (void)s_Rt; (void)s_Ru; (void)s_cf; (void)s_E;
-    (void)s_tk; (void)s_dx; (void)s_gbins; (void)s_posf;
+    (void)s_bbox; (void)s_keys; (void)s_Rt; (void)s_Ru; (void)s_cf; (void)s_E; (void)s_queue;
+    (void)s_tk; (void)s_dx; (void)s_gbins; (void)s_posf; (void)s_margt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     const size_t slab = (size_t)blockIdx.x * npix;
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T};
     int zero_dist = 0, slow = 0, common = 0;
     int* const counter = a.next_window + 16;
-    const int dit = NT % a.ntg, diu = NT / a.ntg;
+    double* const colp = s_colpart + warp * a.ntg_pad;
     for (int i = blockIdx.x; i < a.B;) {
         const int b = a.b0 + i;
         const wfot_grid g = a.grids[b % a.n_grids];
         if (tid == 0) {
-            s_hdr->degenerate = 0; s_qcount[0] = 0;
+            s_hdr->degenerate = 0;
             s_qcount[2] = (int)gridDim.x + atomicAdd(counter, 1);
         }
         if (a.grad) {      // P4 accumulates into these rows with L2 reductions
@@ -127,8 +139,9 @@ __global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
             for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
             __threadfence();
         }
+        for (int c = lane; c < a.ntg; c += 32) colp[c] = 0.0;
         __syncthreads();
-        PrepOut po{s_pn, s_A, s_H, s_bbox, tb.tile, s_pxs, s_pys, s_hdr};
+        PrepOut po{s_pn, s_A, s_H, nullptr, tb.tile, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
         __syncthreads();
@@ -137,48 +150,51 @@ __global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
         for (int c = tid; c < a.nug; c += NT) s_xu[c] = lin_axis(hdr.U0, hdr.Ustep, hdr.Ulast, c, a.nug);
         __syncthreads();
 
-        // ---------------- P1: one pixel per thread, row-major
+        // ---------------- P1 + P2 sums
         const uint2* const in = a.scan_out + (size_t)i * npix;
-        int it = tid % a.ntg, iu = tid / a.ntg;
-        uint2 nxt = (tid < npix) ? __ldcs(in + tid) : make_uint2(0u, 0u);
+        int32_t* const dbg = a.dbg_iray ? a.dbg_iray + (size_t)b * npix : nullptr;
 #pragma unroll 1
-        for (int pix = tid; pix < npix; pix += NT) {
-            const uint2 v = nxt;
-            if (pix + NT < npix) nxt = __ldcs(in + pix + NT);
-            const float kb1 = __uint_as_float(v.x);
-            const float thr = kb1 + tau32(kb1);
+        for (int iu = warp; iu < a.nug; iu += kRowGroups) {
+            const uint2* const inrow = in + (size_t)iu * a.ntg;
             const double pyd = s_xu[iu];
-            PixelHit hit;
-            bool done = resolve_pixel_flagged<T>(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, thr,
-                                                 (int)(v.y & kScanTileMask), (v.y & kScanFlag2) != 0u,
-                                                 (v.y & kScanFlag3) != 0u, hit);
-            if (!done) {
-                const int qi = atomicAdd(s_qcount, 1);
-                if (qi < kFQCap) {
-                    s_queue[qi] = FQEntry{pix, kb1};
-                } else {
-                    ++slow;
-                    resolve_pixel_full(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, kb1, hit);
-                    done = true;
+            const float pyl = s_pys[iu];
+            double rowacc = 0.0;
+            uint2 nxt = (lane < a.ntg) ? __ldcs(inrow + lane) : make_uint2(0u, 0u);
+#pragma unroll 1
+            for (int c0 = 0; c0 < a.ntg; c0 += 32) {
+                const int it = min(c0 + lane, a.ntg - 1);             // lanes past the row end shadow its last pixel
+                const bool live = c0 + lane < a.ntg;
+                const uint2 v = nxt;
+                if (c0 + 32 + lane < a.ntg) nxt = __ldcs(inrow + c0 + 32 + lane);
+                const float kb1 = __uint_as_float(v.x);
+                const float thr = kb1 + tau32(kb1);
+                const float pxl = s_pxs[it];
+                const double pxd = s_xt[it];
+                PixelHit hit;
+                const bool done = resolve_pixel_flagged<T>(tb, s_pn, pxl, pyl, pxd, pyd, thr,
+                                                           (int)(v.y & kScanTileMask), (v.y & kScanFlag2) != 0u,
+                                                           (v.y & kScanFlag3) != 0u, hit);
+                unsigned amb = __ballot_sync(0xffffffffu, live && !done);
+                while (amb) {                                         // rare: all-segment rescan by the whole warp
+                    const int src = __ffs((int)amb) - 1;
+                    amb &= amb - 1u;
+                    PixelHit h2;
+                    resolve_pixel_warp(tb, s_pn, __shfl_sync(0xffffffffu, pxl, src), pyl,
+                                       __shfl_sync(0xffffffffu, pxd, src), pyd, __shfl_sync(0xffffffffu, kb1, src), h2);
+                    if (lane == src) { hit = h2; ++slow; }
+                }
+                if (live) {
+                    const double pdf = store_pixel<false>(a, s_pn, slab, it, iu, hit, pyd, zero_dist, dbg);
+                    rowacc += pdf;                                    // columns lane, lane + 32, ... in ascending order
+                    colp[it] += pdf;                                  // rows warp, warp + 8, ... in ascending order
                 }
             }
-            if (done) store_pixel(a, s_pn, slab, it, iu, hit, pyd, zero_dist);
-            it += dit; iu += diu;
-            if (it >= a.ntg) { it -= a.ntg; ++iu; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) rowacc += __shfl_xor_sync(0xffffffffu, rowacc, off);
+            if (lane == 0) s_margu[iu] = rowacc;
         }
-        __syncthreads();
-        {
-            const int nq = min(*s_qcount, kFQCap);
-            for (int e = warp; e < nq; e += NT / 32) {
-                const FQEntry qe = s_queue[e];
-                const int qt = qe.pix % a.ntg, qu = qe.pix / a.ntg;
-                PixelHit hit;
-                resolve_pixel_warp(tb, s_pn, s_pxs[qt], s_pys[qu], s_xt[qt], s_xu[qu], qe.b1, hit);
-                if (lane == 0) { store_pixel(a, s_pn, slab, qt, qu, hit, s_xu[qu], zero_dist); ++slow; }
-            }
-        }
-        __syncthreads();   // scratch slab complete (block-scope visibility of global writes)
-        common += window_tail<NT>(a, smem_raw, b, slab, hdr);
+        __syncthreads();   // sums and scratch slab complete (block-scope visibility of global writes)
+        common += window_tail<NT, true, (MINB == 2 ? 8 : 4)>(a, smem_raw, b, slab, hdr);
         i = s_qcount[2];
         __syncthreads();
     }
@@ -190,12 +206,26 @@ __global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
 }
 
 // ------------------------------------------------------------------ host side
-// Windows per scan/resolve launch pair: the scratch array holds 8 bytes per pixel of one chunk.
-static int split_chunk(int B, int nug, int ntg) {
-    if (const int o = dev_option(kOptSplitChunk)) return o < B ? o : B;
-    const long long cap = (4LL << 30) / ((long long)nug * ntg * 8);        // <= 4 GiB of scan results in flight
-    long long c = cap < 1 ? 1 : cap;
-    return (int)(c < B ? c : B);
+// The batch is cut into chunks; chunk c is scanned on the caller's stream and resolved on a helper stream.  Both
+// kernels are launched with their full stand-alone grids, so they do not share SMs while both have work (measured:
+// reduced grids sized for co-residency - one scan CTA + two resolve CTAs per SM - lose 10-15 %); what the second
+// stream buys is that the scan of chunk c + 1 moves onto SMs as the resolve CTAs of chunk c retire, i.e. the
+// tails of the persistent kernels (up to one window per CTA, ~7 % per chunk) are filled with the next chunk's work.
+// Three chunk-sized scan-result buffers rotate; events order scan(c) -> resolve(c) -> scan(c + 3).  The helper
+// stream joins the caller's stream before the call returns, so the call stays stream-ordered for the caller.
+constexpr int kScanBuffers = 3;
+constexpr int kMaxChunks = 30;           // two window counters per chunk in the 256-byte counter block
+
+static bool overlap_enabled() { return dev_option(kOptOverlap) != 1; }
+
+static int split_chunk(int B, int nug, int ntg, int sms) {
+    int c;
+    if (const int o = dev_option(kOptSplitChunk)) c = o;
+    else c = overlap_enabled() ? 8 * sms : 64 * sms;
+    const long long cap = (overlap_enabled() ? (1LL << 30) : (8LL << 30)) / ((long long)nug * ntg * 8);   // bytes per buffer
+    if (c > cap) c = (int)(cap < 1 ? 1 : cap);
+    if (c < (B + kMaxChunks - 1) / kMaxChunks) c = (B + kMaxChunks - 1) / kMaxChunks;
+    return c < B ? c : B;
 }
 
 bool split_wanted(int B, int nt, int nug, int ntg, int sms) {
@@ -203,56 +233,118 @@ bool split_wanted(int B, int nt, int nug, int ntg, int sms) {
     if (dev_option(kOptPipeline) == 1) return false;
     if (dev_option(kOptPipeline) == 2) return true;
     // large windows (the single-kernel form would run 256-thread CTAs) and at least four windows per SM
-    return false && (long long)nug * ntg > 16384 && B >= 4 * sms;
+    return (long long)nug * ntg > 16384 && B >= 4 * sms;
 }
 
 size_t split_workspace_bytes(int B, int nt, int nug, int ntg, int sms) {
     if (!split_wanted(B, nt, nug, ntg, sms)) return 0;
-    return (size_t)split_chunk(B, nug, ntg) * nug * ntg * 8 + 256;
+    const int chunk = split_chunk(B, nug, ntg, sms);
+    const int nbuf = (B + chunk - 1) / chunk < kScanBuffers ? (B + chunk - 1) / chunk : kScanBuffers;
+    return (size_t)nbuf * chunk * nug * ntg * 8 + 512;
+}
+
+// Helper stream + events per (device, caller stream); created on first use, kept for the life of the process.
+struct SideLane {
+    int dev; cudaStream_t user; cudaStream_t side;
+    cudaEvent_t scanned[kScanBuffers], resolved[kScanBuffers];
+};
+static std::mutex g_lane_mutex;
+static std::vector<SideLane> g_lanes;
+
+static SideLane* side_lane(cudaStream_t user) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_lane_mutex);
+    for (auto& l : g_lanes)
+        if (l.dev == dev && l.user == user) return &l;
+    if (g_lanes.size() >= 64) return nullptr;        // callers with many streams: sequential form
+    SideLane l;
+    l.dev = dev; l.user = user;
+    if (cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < kScanBuffers; ++i)
+        if (cudaEventCreateWithFlags(&l.scanned[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.resolved[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    g_lanes.reserve(64);
+    g_lanes.push_back(l);
+    return &g_lanes.back();
 }
 
 template <int T>
 static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaStream_t stream) {
-    const size_t smem = (size_t)a.L.total;
     const size_t npix = (size_t)a.nug * a.ntg;
+    int sms = wfot_device_sm_count();
+    if (sms <= 0) return cuda_fail(cudaGetLastError(), "device query");
+    FusedArgs as = a, ar = a;
+    as.L = make_layout(a.nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax, kLayoutScan);
+    ar.L = make_layout(a.nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax, kLayoutResolve);
+    const size_t smem_s = (size_t)as.L.total, smem_r = (size_t)ar.L.total;
+    // overlap needs a helper stream; not while the caller's stream is being captured into a CUDA graph
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap);
+    SideLane* lane = (overlap_enabled() && cap == cudaStreamCaptureStatusNone) ? side_lane(stream) : nullptr;
     int per_sm = 0;
-    const int scan_ctas = resident_ctas(k_scan<4, T>, smem, &per_sm, 256);
+    const int scan3 = dev_option(kOptScanShape) != 2;             // default: 80 registers, 3 CTAs per SM (2: 128 x 2)
+    const int scan_ctas = scan3 ? resident_ctas(k_scan<4, T, 3>, smem_s, &per_sm, 256)
+                                : resident_ctas(k_scan<4, T, 2>, smem_s, &per_sm, 256);
     if (scan_ctas < 1) return cuda_fail(cudaGetLastError(), "k_scan occupancy");
-    int shape = dev_option(kOptResolveShape);
-    if (shape < 1 || shape > 3) shape = 2;
-    int res_ctas = -1, res_threads = 256;
-    if (shape == 1) res_ctas = resident_ctas(k_resolve<256, 2, T>, smem, &per_sm, 256);
-    else if (shape == 2) res_ctas = resident_ctas(k_resolve<256, 3, T>, smem, &per_sm, 256);
-    else { res_threads = 512; res_ctas = resident_ctas(k_resolve<512, 2, T>, smem, &per_sm, 512); }
+    // resolve kernel: 128 registers x 2 CTAs per SM for long windows (deeper unrolled gradient assembly: its slab
+    // read-back is the latency sink of the kernel), 80 registers x 3 per SM for short ones
+    int rshape = dev_option(kOptResolveShape);
+    if (rshape != 1 && rshape != 2) rshape = smem_r > 48 * 1024 ? 1 : 2;
+    const int res_ctas = rshape == 1 ? resident_ctas(k_resolve<2, T>, smem_r, &per_sm, 256)
+                                     : resident_ctas(k_resolve<3, T>, smem_r, &per_sm, 256);
     if (res_ctas < 1) return cuda_fail(cudaGetLastError(), "k_resolve occupancy");
+    const size_t slab_px = 20;                         // bytes per pixel of the per-CTA scratch slab
     const int Btot = a.B;
-    const int chunk = split_chunk(Btot, a.nug, a.ntg);
-    // workspace: [scan results of one chunk][slabs of the resolve CTAs]
+    const int chunk = split_chunk(Btot, a.nug, a.ntg, sms);
+    const int nchunks = (Btot + chunk - 1) / chunk;
+    const int nbuf = nchunks < kScanBuffers ? nchunks : kScanBuffers;
+    // workspace: [scan results: nbuf chunks][slabs of the resolve CTAs]
     uintptr_t p = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
     const size_t scan_bytes = (size_t)chunk * npix * 8;
-    if (ws_bytes < (p - (uintptr_t)ws) + scan_bytes + npix * 28) return WFOT_ERR_WORKSPACE;
-    a.scan_out = (uint2*)p;
-    p += scan_bytes;
-    const size_t max_ctas = (ws_bytes - (p - (uintptr_t)ws)) / (npix * 28);
-    if ((size_t)res_ctas > max_ctas) res_ctas = (int)max_ctas;
+    if (ws_bytes < (p - (uintptr_t)ws) + nbuf * scan_bytes + npix * slab_px) return WFOT_ERR_WORKSPACE;
+    uint2* const scan_base = (uint2*)p;
+    p += nbuf * scan_bytes;
+    const size_t max_ctas = (ws_bytes - (p - (uintptr_t)ws)) / (npix * slab_px);
+    const int res_grid = (size_t)res_ctas > max_ctas ? (int)max_ctas : res_ctas;
     unsigned char* q = (unsigned char*)p;
-    a.s_pdf = (double*)q;   q += (size_t)res_ctas * npix * 8;
-    a.s_wa = (double*)q;    q += (size_t)res_ctas * npix * 8;
-    a.s_wb = (double*)q;    q += (size_t)res_ctas * npix * 8;
-    a.s_idx = (int32_t*)q;
-    a.cluster = 1;
-    for (int c0 = 0; c0 < Btot; c0 += chunk) {
+    ar.s_pdf = nullptr;      // the resolve kernel sums the density on the fly
+    ar.s_wa = (double*)q;    q += (size_t)res_grid * npix * 8;
+    ar.s_wb = (double*)q;    q += (size_t)res_grid * npix * 8;
+    ar.s_idx = (int32_t*)q;
+    as.cluster = ar.cluster = 1;
+    int* const counters = a.next_window;             // 64 ints, zeroed by the caller on `stream`
+    cudaStream_t rstream = lane ? lane->side : stream;
+    for (int c = 0; c < nchunks; ++c) {
+        const int c0 = c * chunk;
         const int nb = (Btot - c0 < chunk) ? Btot - c0 : chunk;
-        a.b0 = c0; a.B = nb;
-        if (c0 > 0 && cudaMemsetAsync(a.next_window, 0, 256, stream) != cudaSuccess)
-            return cuda_fail(cudaGetLastError(), "cudaMemsetAsync");
-        k_scan<4, T><<<scan_ctas < nb ? scan_ctas : nb, 256, smem, stream>>>(a);
-        const int rc = res_ctas < nb ? res_ctas : nb;
-        if (shape == 1) k_resolve<256, 2, T><<<rc, 256, smem, stream>>>(a);
-        else if (shape == 2) k_resolve<256, 3, T><<<rc, 256, smem, stream>>>(a);
-        else k_resolve<512, 2, T><<<rc, res_threads, smem, stream>>>(a);
+        const int buf = c % nbuf;
+        as.b0 = ar.b0 = c0; as.B = ar.B = nb;
+        as.scan_out = ar.scan_out = scan_base + (size_t)buf * chunk * npix;
+        as.next_window = counters + 2 * c;
+        ar.next_window = counters + 2 * c + 1 - 16;  // k_resolve counts at next_window + 16
+        if (lane && c >= nbuf && cudaStreamWaitEvent(stream, lane->resolved[buf], 0) != cudaSuccess)
+            return cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent");
+        if (scan3) k_scan<4, T, 3><<<scan_ctas < nb ? scan_ctas : nb, 256, smem_s, stream>>>(as);
+        else k_scan<4, T, 2><<<scan_ctas < nb ? scan_ctas : nb, 256, smem_s, stream>>>(as);
+        if (lane) {
+            if (cudaEventRecord(lane->scanned[buf], stream) != cudaSuccess ||
+                cudaStreamWaitEvent(rstream, lane->scanned[buf], 0) != cudaSuccess)
+                return cuda_fail(cudaGetLastError(), "cudaEventRecord");
+        }
+        const int rc = res_grid < nb ? res_grid : nb;
+        if (rshape == 1) k_resolve<2, T><<<rc, 256, smem_r, rstream>>>(ar);
+        else k_resolve<3, T><<<rc, 256, smem_r, rstream>>>(ar);
+        note_launches(2);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "wfot_misfit_grad_batch (scan + resolve) launch");
+        if (lane && cudaEventRecord(lane->resolved[buf], rstream) != cudaSuccess)
+            return cuda_fail(cudaGetLastError(), "cudaEventRecord");
+    }
+    if (lane) {                                      // join: later work on the caller's stream sees every result
+        for (int i = 0; i < nbuf; ++i)
+            if (cudaStreamWaitEvent(stream, lane->resolved[i], 0) != cudaSuccess)
+                return cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent");
     }
     return WFOT_OK;
 }
