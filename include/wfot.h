@@ -146,6 +146,21 @@ int wfot_ot1d_batch(const void* f, const void* g, int in_dtype,
                     double* amp_f, double* cdf_f, double* cdf_g, int32_t* merge_order,
                     int32_t* status, void* stream);
 
+/* ---- transport plan -----------------------------------------------------------
+ * Replaces the returnplan branch of wasser(): libs/OTlib.py:718-740, and the per-slice
+ * scatter of SlicedWasserstein(returnplan / calcWplan): libs/OTlib.py:1247-1262.
+ * From the outputs of wfot_ot1d_batch (cdf_f (B, n), cdf_g (B, m), merge_order (B, n+m-1),
+ * amp_f (B,)):  H (n, m) per pair with H[indf_k, indg_k] += dt_k over the merged knots, and
+ * (dH != NULL) dH (n, n, m) per pair with dH[l, indf_k, indg_k] += Diffdtk[l, k] (:682-686,
+ * 731-733), indf / indg = bisect_left ranks of the knot in the two CDFs.
+ * perm_f (B, n) / perm_g (B, m) (nullable int32): rows / columns (and the derivative index l)
+ * are scattered through these permutations - the argsort of a slice's projected positions.
+ * accumulate != 0: all B pairs add into ONE H (n, m) / dH (n, n, m) (the slice sum).
+ * H and dH are zeroed by the call. */
+int wfot_plan_batch(const double* cdf_f, const double* cdf_g, const int32_t* merge_order,
+                    const double* amp_f, const int32_t* perm_f, const int32_t* perm_g,
+                    int n, int m, int B, int accumulate, double* H, double* dH, void* stream);
+
 /* ---- gradient assembly (materialising path) --------------------------------
  * Replaces waveformFP.PDFderiv / PDFderivMarg: libs/FingerprintLib.py:182-228.
  * out (B, nchain, nt) = -1/lambda * segmented sum over pixels keyed by iray of

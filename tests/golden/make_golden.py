@@ -179,5 +179,43 @@ def main():
     np.savez_compressed(os.path.join(HERE, "sliced_plan.npz"), f=f, g=g, pos=pos, **out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+    sliced_avgplan_pending = True
+
+
+def sliced_avgplan():
+    """(8) slice-averaged transport plans of SlicedWasserstein (libs/OTlib.py:1222-1262,1287-1318): returnplan and
+    calcWplan, with and without derivatives, on a 4 x 5 grid (the derivative of the plan is n x n x n).
+    Run on its own:  python tests/golden/make_golden.py avgplan"""
+    rng = np.random.default_rng(2718)
+    nx, ny = 4, 5
+    X, Y = np.meshgrid(np.linspace(0, 1, ny), np.linspace(0, 1, nx))
+    pos = np.stack([X, Y], axis=-1)
+    f = rng.random((nx, ny)) + 0.05
+    g = rng.random((nx, ny)) + 0.05
+    out = dict(f=f, g=g, pos=pos, Nproj=5)
+    mk = lambda: (OT.OTpdf((f, pos)), OT.OTpdf((g, pos)))
+    for d in ("W1", "W2"):
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, 5, distfunc=d, returnplan=True)
+        out["rp_%s_w" % d], out["rp_%s_H" % d] = r[0], r[1]
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, 5, distfunc=d, returnplan=True, derivatives=True)
+        out["rpd_%s_w" % d], out["rpd_%s_dw" % d], out["rpd_%s_H" % d], out["rpd_%s_dH" % d] = r[0], r[1], r[2], r[3]
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, 5, distfunc=d, calcWplan=True)
+        out["cw_%s_wplan" % d], out["cw_%s_w" % d] = r[0], r[1]
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, 5, distfunc=d, calcWplan=True, derivatives=True, returnplan=True)
+        (out["cwd_%s_wplan" % d], out["cwd_%s_dwplan" % d], out["cwd_%s_w" % d], out["cwd_%s_dw" % d],
+         out["cwd_%s_H" % d], out["cwd_%s_dH" % d]) = r
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, 5, distfunc=d, calcWplan=True, calcAvgW=False)
+        assert len(r) == 1 and r[0] == out["cw_%s_wplan" % d]
+    np.savez_compressed(os.path.join(HERE, "sliced_avgplan.npz"), **out)
+    print("sliced_avgplan", {k: np.shape(v) for k, v in out.items()})
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or sys.argv[1] == "avgplan"):
+    sliced_avgplan()

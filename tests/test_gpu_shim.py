@@ -221,9 +221,44 @@ def test_sliced_wasserstein_golden(mods, golden):
         assert len(s.proj) == 6 and s.proj[0].n == g["f"].size and s.psorted.shape == (6, g["f"].size)
     s, t = OT.OTpdf((g["f"], g["pos"])), OT.OTpdf((g["g"], g["pos"]))
     assert OT.SlicedWasserstein(s, t, 4, distfunc="W2")[0] == pytest.approx(float(g["sw_noderiv"]), rel=1e-11)
-    with pytest.raises(NotImplementedError):
-        OT.SlicedWasserstein(s, t, 4, returnplan=True)
     pickle.loads(pickle.dumps(s))                       # stays picklable after setSliced
+
+
+def test_sliced_average_plan_golden(mods, golden):
+    """SlicedWasserstein(returnplan / calcWplan) (libs/OTlib.py:1222-1262,1287-1318): slice-averaged transport plan,
+    W^p from the plan, and their derivatives; the per-slice plans are scattered by one CUDA kernel (wfot_plan_batch)."""
+    _, OT, _ = mods
+    g = golden("sliced_avgplan")
+    N = int(g["Nproj"])
+    mk = lambda: (OT.OTpdf((g["f"], g["pos"])), OT.OTpdf((g["g"], g["pos"])))
+    for d in ("W1", "W2"):
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, N, distfunc=d, returnplan=True)
+        assert len(r) == 2 and r[0] == pytest.approx(float(g["rp_%s_w" % d]), rel=1e-11)
+        np.testing.assert_allclose(r[1], g["rp_%s_H" % d], atol=1e-14)
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, N, distfunc=d, returnplan=True, derivatives=True)
+        assert len(r) == 4 and r[0] == pytest.approx(float(g["rpd_%s_w" % d]), rel=1e-11)
+        np.testing.assert_allclose(r[1], g["rpd_%s_dw" % d], rtol=1e-8, atol=1e-13)
+        np.testing.assert_allclose(r[2], g["rpd_%s_H" % d], atol=1e-14)
+        np.testing.assert_allclose(r[3], g["rpd_%s_dH" % d], atol=1e-12)
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, N, distfunc=d, calcWplan=True)
+        assert len(r) == 2
+        assert r[0] == pytest.approx(float(g["cw_%s_wplan" % d]), rel=1e-11)
+        assert r[1] == pytest.approx(float(g["cw_%s_w" % d]), rel=1e-11)
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, N, distfunc=d, calcWplan=True, derivatives=True, returnplan=True)
+        assert len(r) == 6
+        assert r[0] == pytest.approx(float(g["cwd_%s_wplan" % d]), rel=1e-11)
+        np.testing.assert_allclose(r[1], g["cwd_%s_dwplan" % d], rtol=1e-8, atol=1e-13)
+        assert r[2] == pytest.approx(float(g["cwd_%s_w" % d]), rel=1e-11)
+        np.testing.assert_allclose(r[3], g["cwd_%s_dw" % d], rtol=1e-8, atol=1e-13)
+        np.testing.assert_allclose(r[4], g["cwd_%s_H" % d], atol=1e-14)
+        np.testing.assert_allclose(r[5], g["cwd_%s_dH" % d], atol=1e-12)
+        s, t = mk()
+        r = OT.SlicedWasserstein(s, t, N, distfunc=d, calcWplan=True, calcAvgW=False)
+        assert len(r) == 1 and r[0] == pytest.approx(float(g["cw_%s_wplan" % d]), rel=1e-11)
 
 
 def test_transport_plan_golden(mods, golden):

@@ -6,11 +6,12 @@ libwfot.so on the GPU.
 
 Also provided (diagnostics rather than the inversion
 hot loop): ``OTpdf.setSliced`` / ``SlicedWasserstein`` (all slices in ONE
-batched 1-D OT launch) and the transport plan of ``wasser(returnplan=True)``.
+batched 1-D OT launch), the transport plan of ``wasser(returnplan=True)`` and the
+slice-averaged plans of ``SlicedWasserstein(returnplan / calcWplan)`` (one scatter
+kernel over the merged knots, ``wfot_plan_batch``).
 
 Out of scope (NotImplementedError): user supplied cost matrices (``distfunc``
-as ndarray/tuple), plans averaged over slices (``SlicedWasserstein(returnplan /
-calcWplan)``), LP / Sinkhorn / POT cross-checks, barycentres, plotting.
+as ndarray/tuple), LP / Sinkhorn / POT cross-checks, barycentres, plotting.
 """
 from __future__ import annotations
 
@@ -226,29 +227,23 @@ def wasser(source, target, distfunc='W12', proj=-1, returnplan=False, derivative
 
 def _transport_plan(r, source, target, derivatives):
     """Optimal plan H and (with derivatives) dH/d(un-normalised source amplitudes); libs/OTlib.py:718-740.
-    Built on the device from the kernel's CDFs and merge order with torch index arithmetic: a diagnostic
-    output whose size (n x m, n x n x m) is its cost, not part of the inversion hot loop."""
-    import torch
-    n, m = source.n, target.n
-    cf, cg, order = r["cdf_f"][0], r["cdf_g"][0], r["merge_order"][0].long()
-    a = torch.cat([cf[:-1], cg])                                   # :668
-    tk = a[order]                                                  # :670
-    indf = torch.searchsorted(cf, tk, right=False)                 # bisect_left (:671-672)
-    indg = torch.searchsorted(cg, tk, right=False)
-    dtk = torch.cat([tk[:1], tk[1:] - tk[:-1]])                    # :673
-    H = torch.zeros((n, m), dtype=torch.float64, device=cf.device)
-    H.index_put_((indf, indg), dtk, accumulate=True)               # :720-723
-    out = [H.cpu().numpy()]
+    One scatter kernel over the merged knots (wfot_plan_batch) fed by the 1-D OT kernel's CDFs and merge order."""
+    H, dH, _ = _B.plan_batch(r, source.n, target.n, derivatives=derivatives)
+    _sync()
+    out = [H[0].cpu().numpy()]
     if derivatives:
-        Bm = torch.triu(torch.ones((n, m), dtype=torch.float64, device=cf.device))     # :682-686
-        Cm = (Bm - cf) / float(r["amp"][0])
-        D = torch.cat([Cm[:, :-1], torch.zeros((n, m), dtype=torch.float64, device=cf.device)], dim=1)
-        Difftk = D[:, order]
-        Diffdtk = torch.cat([Difftk[:, :1], Difftk[:, 1:] - Difftk[:, :-1]], dim=1)
-        dH = torch.zeros((n, n * m), dtype=torch.float64, device=cf.device)
-        dH.index_add_(1, indf * m + indg, Diffdtk)                  # :731-733
-        out += [dH.reshape(n, n, m).cpu().numpy()]
+        out += [dH[0].cpu().numpy()]
     return out
+
+
+def _point_distances(source, target, distfunc):
+    """libs/OTlib.py:187-217 for distfunc 'W1' / 'W2' between the 2-D point positions: |dx| + |dy| or dx^2 + dy^2."""
+    fx = source.x.reshape((source.n, 2))
+    gx = target.x.reshape((source.n, 2))
+    l = fx[:, None, :] - gx[None, :, :]
+    if distfunc == 'W1':
+        return np.abs(l[..., 0]) + np.abs(l[..., 1])
+    return l[..., 0] ** 2 + l[..., 1] ** 2
 
 
 def SlicedWasserstein(source, target, Nproj, distfunc='W2', derivatives=False, returnplan=False, verbose=False,
@@ -261,38 +256,66 @@ def SlicedWasserstein(source, target, Nproj, distfunc='W2', derivatives=False, r
         raise TargetSource2DShapeError
     if target.type != '2D':
         raise TargetSource2DShapeError
-    if returnplan or calcWplan:
-        raise NotImplementedError("waveform_ot_b200: slice-averaged transport plans are not provided")
     calcW1, calcW2 = _checkdistfunc(distfunc)
     if calcW1 and calcW2:
         raise SlicedWassersteinError("distfunc must be 'W1' or 'W2'")
     if derivatives and source.n != target.n:
         raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,) "
                          % (source.n, target.n, source.n))
+    plan = bool(returnplan or calcWplan)                              # :1238-1241 (distfunc is a string here)
     origin = np.asarray(origin, dtype=np.float64)
     if source.calcproj or source.nproj != Nproj:
         source.setSliced(Nproj, origin)                               # :1209-1210
     if target.calcproj or target.nproj != Nproj:
         target.setSliced(Nproj, origin)
     r = _B.ot1d_batch(source._slice_f, target._slice_f, source._slice_x, target._slice_x, distfunc,
-                      derivatives=derivatives)
+                      derivatives=derivatives, want_cdf=plan, want_merge=plan)
+    Hgp = dHgp = None
+    if plan:   # slice sum of the 1-D plans, scattered back through each slice's argsort (:1247-1262): one kernel
+        Hgp, dHgp, _keep = _B.plan_batch(r, source.n, target.n, perm_f=source.psorted, perm_g=target.psorted,
+                                         accumulate=True, derivatives=derivatives)
     _sync()
     st = r["status"].read()
     if st[1]:                                                         # wasser(..., checkCommonCDF=True) (:1266-1270)
         raise TargetSourceCDFError([])
     k = 0 if calcW1 else 1
     wp = float(r["W"][:, k].sum())                                    # :1288
+    n = source.n
+    pdf = source.pdf.reshape(n)
+    dwp = None
+    if derivatives:
+        dw = r["dW1"] if calcW1 else r["dW2"]                         # (Nproj, n), slice order
+        dwp_d = torch.zeros(n, dtype=torch.float64, device=dw.device)
+        dwp_d.index_add_(0, torch.from_numpy(source.psorted.reshape(-1)).to(dw.device), dw.reshape(-1))   # :1280
+        dwp = dwp_d.cpu().numpy()
+    if plan:
+        Hgp = Hgp.cpu().numpy()
+        if derivatives:
+            dHgp = dHgp.cpu().numpy()
     out = []
+    if calcWplan:                                                     # :1289-1300
+        Hgp = Hgp / Nproj
+        c = _point_distances(source, target, 'W1' if calcW1 else 'W2').reshape(n * target.n)
+        out += [float(c.dot(Hgp.reshape(n * target.n)))]
+        if derivatives:
+            dwplan = np.dot(dHgp.reshape(n, n * target.n), c) / Nproj
+            dwplan -= np.dot(dwplan, pdf)
+            dwplan /= source.amp
+            out += [dwplan.reshape((source.nx, source.ny))]
     if calcAvgW:
         out += [wp / Nproj]                                           # :1306
         if derivatives:
-            dw = r["dW1"] if calcW1 else r["dW2"]                     # (Nproj, n), slice order
-            dwp = torch.zeros(source.n, dtype=torch.float64, device=dw.device)
-            dwp.index_add_(0, torch.from_numpy(source.psorted.reshape(-1)).to(dw.device), dw.reshape(-1))   # :1280
-            dwp = dwp.cpu().numpy()
-            dwp -= np.dot(dwp, source.pdf.reshape(source.n))          # :1308-1310
+            dwp -= np.dot(dwp, pdf)                                   # :1308-1310
             dwp /= source.amp
             out += [dwp.reshape((source.nx, source.ny)) / Nproj]
+    if returnplan:                                                    # :1311-1316
+        out += [Hgp]
+        if derivatives:
+            # the reference subtracts np.dot(np.transpose(dHgp), pdf): an (m, n) array R[j, k] = sum_l dHgp[l, k, j] pdf[l]
+            # broadcast over the leading axis (n == m); reproduced as written
+            dHgp = dHgp - np.einsum('lkj,l->jk', dHgp, pdf)
+            dHgp /= source.amp
+            out += [dHgp / Nproj]
     if returnProjpoints:                                              # :1219-1229
         theta = source.angles
         fproj = np.zeros((Nproj, 2, source.n))

@@ -49,6 +49,7 @@ SIGNATURES = {
     "wfot_otpdf1d_batch": (C.c_int, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "wfot_ot1d_batch": (C.c_int, [_p, _p, _i, _p, _p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i,
                                   _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "wfot_plan_batch": (C.c_int, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "wfot_pdfderiv_batch": (C.c_int, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _i, _p, _p]),
     "wfot_misfit_grad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "wfot_misfit_grad_batch": (C.c_int, [_p, _p, _i, _ll, _i, _p, _i, _i, _i, _i, _d, _i, _i, _i,

@@ -215,6 +215,25 @@ def ot1d_batch(f, g, xf, xg, distfunc="W12", derivatives=False, want_cdf=False, 
                 status=st, _keepalive=(f, g, xf, xg))
 
 
+def plan_batch(r, n, m, perm_f=None, perm_g=None, accumulate=False, derivatives=False):
+    """Transport plan(s) from an ot1d_batch(..., want_cdf=True, want_merge=True) result `r`
+    (libs/OTlib.py:718-740): H (B, n, m) and, with derivatives, dH (B, n, n, m); with accumulate=True the
+    pairs add into one H (n, m) / dH (n, n, m), rows / columns scattered through perm_f (B, n) / perm_g (B, m)
+    (libs/OTlib.py:1247-1262)."""
+    dev = _device()
+    Bn = r["cdf_f"].shape[0]
+    f64 = dict(dtype=torch.float64, device=dev)
+    lead = () if accumulate else (Bn,)
+    H = torch.empty(lead + (n, m), **f64)
+    dH = torch.empty(lead + (n, n, m), **f64) if derivatives else None
+    as_i32 = lambda p: None if p is None else torch.as_tensor(np.ascontiguousarray(p), dtype=torch.int32).to(dev).contiguous()
+    pf, pg = as_i32(perm_f), as_i32(perm_g)
+    C.check(C.lib.wfot_plan_batch(C.ptr(r["cdf_f"]), C.ptr(r["cdf_g"]), C.ptr(r["merge_order"]), C.ptr(r["amp"]),
+                                  C.ptr(pf), C.ptr(pg), n, m, Bn, int(bool(accumulate)), C.ptr(H), C.ptr(dH), _stream()),
+            "wfot_plan_batch")
+    return H, dH, (pf, pg)
+
+
 def pdfderiv_batch(pdf, dfield, iray, dddy, chain, nt, lambdav, q=None):
     """PDFderiv / PDFderivMarg for B windows.  chain: None, (B,npix) or (B,nchain,npix)."""
     dev = _device()

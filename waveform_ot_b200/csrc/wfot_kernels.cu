@@ -327,6 +327,63 @@ __global__ void __launch_bounds__(256) k_chain(const double* __restrict__ J, con
     if (lane == 0) out[(size_t)mI * P + p] = s;
 }
 
+// ============================================================ k_plan_H / k_plan_dH
+// Optimal transport plan of wasser(returnplan=True) and its derivative w.r.t. the un-normalised source amplitudes
+// (libs/OTlib.py:718-740): H[indf_k, indg_k] += dt_k and dH[l, indf_k, indg_k] += Diffdtk[l, k] over the merged
+// knots k, from the CDFs and the merge order (tkarg) the 1-D OT kernel already produces.  indf / indg are the
+// bisect_left ranks of the knot value in the two CDFs (:671-672).  With perm_f / perm_g the rows / columns are
+// scattered through a permutation (the argsort of a slice's projected positions) and with H_stride = 0 all pairs
+// accumulate into ONE array: the slice-averaged plan of SlicedWasserstein (libs/OTlib.py:1247-1262).
+struct PlanArgs {
+    const double* cdf_f; const double* cdf_g; const int32_t* order; const double* amp;
+    const int32_t* perm_f; const int32_t* perm_g;
+    int n, m, K;
+    double* H; long long H_stride; double* dH; long long dH_stride;
+};
+
+__device__ __forceinline__ double plan_knot(const PlanArgs& a, long long b, int k, int& indf, int& indg, int& srcj) {
+    const double* cf = a.cdf_f + b * a.n;
+    const double* cg = a.cdf_g + b * a.m;
+    const int c = a.order[b * a.K + k];
+    srcj = c < a.n - 1 ? c : -1;                                   // source knot index, or -1 for a target knot
+    const double v = c < a.n - 1 ? cf[c] : cg[c - (a.n - 1)];
+    indf = lower_bound_d(cf, a.n, v);                              // bisect_left (:671-672)
+    indg = lower_bound_d(cg, a.m, v);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_plan_H(PlanArgs a) {
+    const long long b = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= a.K) return;
+    int indf, indg, sj, pf, pg, pj;
+    const double v = plan_knot(a, b, k, indf, indg, sj);
+    const double vp = k ? plan_knot(a, b, k - 1, pf, pg, pj) : 0.0;
+    const int row = a.perm_f ? a.perm_f[b * a.n + indf] : indf;
+    const int col = a.perm_g ? a.perm_g[b * a.m + indg] : indg;
+    atomicAdd(a.H + b * a.H_stride + (size_t)row * a.m + col, v - vp);          // dtk (:673,720-723)
+}
+
+// grid (ceil(K / 256), n, B): thread = (knot k, derivative row l)
+__global__ void __launch_bounds__(256) k_plan_dH(PlanArgs a) {
+    const long long b = blockIdx.z;
+    const int l = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= a.K) return;
+    const double* cf = a.cdf_f + b * a.n;
+    const double amp = a.amp[b];
+    int indf, indg, sj, pf, pg, pj = -1;
+    plan_knot(a, b, k, indf, indg, sj);
+    if (k) plan_knot(a, b, k - 1, pf, pg, pj);
+    // Difftk[l, k] = ([j >= l] - cf_j) / amp for source knot j, 0 for a target knot (:682-686)
+    const double cur = sj >= 0 ? ((sj >= l ? 1.0 : 0.0) - cf[sj]) / amp : 0.0;
+    const double prv = (k && pj >= 0) ? ((pj >= l ? 1.0 : 0.0) - cf[pj]) / amp : 0.0;
+    const int rl = a.perm_f ? a.perm_f[b * a.n + l] : l;
+    const int row = a.perm_f ? a.perm_f[b * a.n + indf] : indf;
+    const int col = a.perm_g ? a.perm_g[b * a.m + indg] : indg;
+    atomicAdd(a.dH + b * a.dH_stride + ((size_t)rl * a.n + row) * a.m + col, cur - prv);   // :731-733
+}
+
 // ============================================================ k_sum_windows
 // out[c] = sum_b in[b][c]  (fixed order: block i adds rows i, i+G, ... ; then one block adds the G partials)
 __global__ void __launch_bounds__(256) k_sum_windows(const double* __restrict__ in, long long B, int C,
@@ -596,6 +653,35 @@ int wfot_sum_windows(const double* in, long long B, int C, double* out, void* wo
     note_launches(2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wfot_sum_windows launch");
+    return WFOT_OK;
+}
+
+int wfot_plan_batch(const double* cdf_f, const double* cdf_g, const int32_t* merge_order, const double* amp_f,
+                    const int32_t* perm_f, const int32_t* perm_g, int n, int m, int B, int accumulate,
+                    double* H, double* dH, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!cdf_f || !cdf_g || !merge_order || !H || n < 1 || m < 1 || B <= 0 || (dH && !amp_f))
+        return WFOT_ERR_INVALID_ARG;
+    PlanArgs a;
+    a.cdf_f = cdf_f; a.cdf_g = cdf_g; a.order = merge_order; a.amp = amp_f; a.perm_f = perm_f; a.perm_g = perm_g;
+    a.n = n; a.m = m; a.K = n - 1 + m;
+    a.H = H; a.dH = dH;
+    a.H_stride = accumulate ? 0 : (long long)n * m;
+    a.dH_stride = accumulate ? 0 : (long long)n * n * m;
+    const size_t copies = accumulate ? 1 : (size_t)B;
+    if (cudaMemsetAsync(H, 0, copies * (size_t)n * m * 8, stream) != cudaSuccess ||
+        (dH && cudaMemsetAsync(dH, 0, copies * (size_t)n * n * m * 8, stream) != cudaSuccess))
+        return cuda_fail(cudaGetLastError(), "cudaMemsetAsync");
+    const int gx = (a.K + 255) / 256;
+    if (B > 65535 || n > 65535) return WFOT_ERR_UNSUPPORTED;
+    k_plan_H<<<dim3(gx, B), 256, 0, stream>>>(a);
+    note_launches(1);
+    if (dH) {
+        k_plan_dH<<<dim3(gx, n, B), 256, 0, stream>>>(a);
+        note_launches(1);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "wfot_plan_batch launch");
     return WFOT_OK;
 }
 
