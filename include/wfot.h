@@ -196,6 +196,11 @@ int wfot_ricker_batch(const double* params, int M, double t0, double t1,
  * pmask is WFOT_W1 or WFOT_W2.  If transform != 0 the arctan amplitude
  * transform of libs/ricker_util.py:270-275 is applied in-kernel with each
  * grid's (u0,u1) and the gradient is multiplied by d(un)/du (:393-397).
+ * Reproducibility: W and dwg are bit-identical from run to run and for every launch shape
+ * (fixed summation orders; single kernel, two kernels, clusters).  grad is assembled with
+ * FP64 reductions in L2 in arrival order (one per run of equal nearest segment in a pixel
+ * column): its last bits vary from run to run, by <= 1e-12 relative to the row's largest
+ * entry (tests/test_gpu_parity.py::test_fused_run_to_run).
  * Size limit: sample coordinates, segment table, marginals and the OT scratch of a
  * window share one SM's shared memory (about 36 B per sample + 40 B per grid point
  * of the longer axis), i.e. nt up to about 6 000; beyond that WFOT_ERR_UNSUPPORTED
@@ -236,8 +241,9 @@ int wfot_chain_batch(const double* J, const double* dr, int P, int L, int M,
                      long long J_stride_models, double* out, void* stream);
 
 /* ---- batch reduction -----------------------------------------------------------
- * out (C,) = sum over b of in (B, C), FP64, fixed summation order (run-to-run and
- * shard-order reproducible).  This is the local step before the single NCCL allreduce of
+ * out (C,) = sum over b of in (B, C), FP64, fixed summation order: the same input gives the
+ * same bits on every run and for every shard split that keeps the block structure (the
+ * gradient rows fed to it carry their own ~1e-15 run-to-run noise, see above).  This is the local step before the single NCCL allreduce of
  * [sum misfit, sum gradient] across GPUs; the reference's counterpart is
  * the Python accumulation `mis += w2p` in libs/loc_cmt_util.py:260-271. */
 size_t wfot_sum_windows_workspace_bytes(int C);

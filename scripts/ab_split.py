@@ -54,13 +54,13 @@ opt(C.OPT_PIPELINE, 1)
 ms0, r0, st0 = run()
 print("%s B=%d  single-kernel: %.3f ms  %.1f evals/s  status %s" % (name, nb, ms0, nb / ms0 * 1e3, st0[:5].tolist()), flush=True)
 W0, G0, D0 = r0["W"].clone(), r0["grad"].clone(), r0["dwg"].clone()
-# (label, overlap[0 two streams / 1 sequential], resolve shape, chunk, scan shape)
-VARIANTS = [("two streams 8/SM, scan x3, resolve warp-per-row 80 regs x3", 0, 0, 0, 3),
-            ("two streams 8/SM, scan x3, resolve warp-per-row 128 regs x2 (P4 unroll 8)", 0, 1, 0, 3),
-            ("two streams 8/SM, scan x3, resolve pixel-per-thread rotated 256x3", 0, 2, 0, 3),
-            ("two streams 8/SM, scan x3, resolve pixel-per-thread rotated 512x2", 0, 3, 0, 3),
-            ("sequential one chunk, scan x3, resolve pixel-per-thread rotated 256x3", 1, 2, nb, 3),
-            ("sequential one chunk, scan x3, resolve warp-per-row 128 regs x2", 1, 1, nb, 3)]
+# (label, overlap[0 two streams / 1 sequential], resolve shape [0 auto, 1: 128 regs x2/SM, 2: 80 regs x3/SM], chunk, scan shape [0: 80 regs x3, 2: 128 x2])
+VARIANTS = [("two-kernel default", 0, 0, 0, 0),
+            ("two-kernel, resolve 128 regs x2", 0, 1, 0, 0),
+            ("two-kernel, resolve 80 regs x3", 0, 2, 0, 0),
+            ("two-kernel, scan 128 regs x2", 0, 0, 0, 2),
+            ("two-kernel sequential one chunk", 1, 0, nb, 0),
+            ("two-kernel chunk 32/SM", 0, 0, 4736, 0)]
 if len(sys.argv) > 3:
     VARIANTS = [v for i, v in enumerate(VARIANTS) if str(i) in sys.argv[3].split(",")]
 for label, ov, shape, chunk, sc in VARIANTS:

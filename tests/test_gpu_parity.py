@@ -789,3 +789,34 @@ def test_sharded_periodic_rows_equal_unsharded(B, monkeypatch):
             monkeypatch.setenv("WORLD_SIZE", str(world))
             tot += wd.misfit_grad_sharded(t, w[rows:], g, nug, ntg, lam, tg)
         np.testing.assert_allclose(tot.cpu().numpy(), ref.cpu().numpy(), rtol=1e-11, atol=1e-14)
+
+
+def test_fused_run_to_run(B):
+    """Reproducibility contract of include/wfot.h: W and dwg bit-identical from run to run and across launch shapes
+    (single kernel / scan + resolve / clusters); grad (FP64 L2 reductions in arrival order) to <= 1e-12 of the
+    row's largest entry."""
+    from waveform_ot_b200 import _cabi as C
+    nt, nug, ntg, lam = 300, 160, 128, 0.04
+    nb = 4 * C.lib.wfot_device_sm_count() + 5                 # enough windows for the two-kernel form
+    w = torch.from_numpy(O.random_walk_windows(nb + 1, nt, seed=17)).cuda()
+    t = torch.linspace(0, 1, nt, device="cuda")
+    grid = (0.0, 1.0, -1.3, 1.3, nug, ntg)
+    tg = B.Target.from_waveform(t, w[0], grid, nug, ntg, lam)
+    runs = []
+    try:
+        for pipeline in (0, 0, 1, 2):                          # default twice, then forced single- / two-kernel form
+            C.lib.wfot_dev_set_option(C.OPT_PIPELINE, pipeline)
+            r = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg)
+            torch.cuda.synchronize()
+            runs.append((r["W"].clone(), r["dwg"].clone(), r["grad"].clone()))
+    finally:
+        C.lib.wfot_dev_set_option(C.OPT_PIPELINE, 0)
+    small = B.misfit_grad_batch(t, w[1:4], grid, nug, ntg, lam, tg)     # 3 windows: thread-block clusters
+    torch.cuda.synchronize()
+    W0, d0, g0 = runs[0]
+    scale = g0.abs().amax(dim=2, keepdim=True)
+    for W, d, g in runs[1:]:
+        assert torch.equal(W, W0) and torch.equal(d, d0)
+        assert float(((g - g0).abs() / scale).max()) <= 1e-12
+    assert torch.equal(small["W"], W0[:3]) and torch.equal(small["dwg"], d0[:3])
+    assert float(((small["grad"] - g0[:3]).abs() / scale[:3]).max()) <= 1e-12

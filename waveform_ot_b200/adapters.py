@@ -103,10 +103,10 @@ def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfu
     transformed observations); J (M, P, nr*nc*nt) Jacobian d(seis)/d(model) or None.
     Returns mis (M,), dmis (M, P) or None, dr (M, nr, nc, nt).
 
-    seis_pred / J may be NumPy arrays, pinned host tensors or device tensors.  Host inputs are streamed in
-    chunks of `chunk_models` models on a copy stream while the previous chunk is evaluated (the Jacobians are the
-    bulk: 132 KB per model at the Figs 9-11 shape), so the host -> device transfer hides behind the kernels; with
-    pinned tensors the copies are fully asynchronous."""
+    seis_pred / J may be NumPy arrays, pinned host tensors or device tensors.  The models go through in chunks of
+    `chunk_models`: the next chunk's host -> device copies (the Jacobians are the bulk: 132 KB per model at the
+    Figs 9-11 shape) and the previous chunk's device -> host results run on their own streams under the current
+    chunk's kernels; with pinned input tensors the uploads are fully asynchronous."""
     import torch
     dev = _B._device()
     as_t = lambda x: x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
@@ -120,57 +120,72 @@ def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfu
     g = _B.pack_grids(flat)                                    # (nr*nc, 80 B): window b = m*(nr*nc) + i*nc + j uses
     #                                                            grid / observed window b % (nr*nc) (no per-model copies)
     t_dev = _B._as_device(t, torch.float64)
-    f64 = dict(dtype=torch.float64, device=dev)
-    mis_all = torch.empty(M, **f64)
-    dmis_all = torch.empty((M, P), **f64) if Jt is not None else None
-    dr_all = torch.empty((M, nw, nt), **f64)
+    mis_h = np.empty(M)
+    dmis_h = np.empty((M, P)) if Jt is not None else None
+    dr_h = np.empty((M, nw, nt))
     status = _B.Status()
     main = torch.cuda.current_stream()
-    copy = torch.cuda.Stream(device=dev)
-    copy.wait_stream(main)
+    h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    h2d.wait_stream(main)
     cm = max(1, min(int(chunk_models), M))
     ws = torch.empty(_B.C.lib.wfot_misfit_grad_workspace_bytes(cm * nw, nt, Nu, Nt), dtype=torch.uint8, device=dev)
-    staged = {}
+    staged, finished = {}, {}
 
-    def stage(c0):
+    def stage(c0):                                   # host -> device copies of one chunk on the h2d stream
         c1 = min(c0 + cm, M)
-        with torch.cuda.stream(copy):
+        with torch.cuda.stream(h2d):
             sd = seis[c0:c1].reshape((c1 - c0) * nw, nt).to(dev, dtype=torch.float64, non_blocking=True)
             jd = None if Jt is None else Jt[c0:c1].to(dev, dtype=torch.float64, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record(copy)
+            ev.record(h2d)
         staged[c0] = (sd, jd, ev, c1)
 
+    def fetch(c0):                                   # device -> host of one finished chunk on the d2h stream
+        mis_d, dmis_d, dr_d, ev, c1 = finished.pop(c0)
+        d2h.wait_event(ev)
+        with torch.cuda.stream(d2h):
+            torch.from_numpy(mis_h[c0:c1]).copy_(mis_d)
+            torch.from_numpy(dr_h[c0:c1]).copy_(dr_d)
+            if dmis_d is not None:
+                torch.from_numpy(dmis_h[c0:c1]).copy_(dmis_d)
+        for x in (mis_d, dmis_d, dr_d):
+            if x is not None:
+                x.record_stream(d2h)
+
     stage(0)
+    prev = None
     for c0 in range(0, M, cm):
         sd, jd, ev, c1 = staged.pop(c0)
         main.wait_event(ev)
         r = _B.misfit_grad_batch(t_dev, sd, g, Nu, Nt, lambdav, targets, distfunc=distfunc, transform=True,
                                  status=status, workspace=ws)
-        if c1 < M:
-            stage(c1)                                           # next chunk's copies run under this chunk's kernels
         m = c1 - c0
         W = r["W"].reshape(m, nw, 2)
         gr = r["grad"].reshape(m, nw, 2, nt)
         if Wopt == "Wavg":                                      # OTlib.py:1136,1150
-            mis_all[c0:c1] = 0.5 * (W[..., 0] + W[..., 1]).sum(dim=1)
-            dr = 0.5 * (gr[:, :, 0] + gr[:, :, 1])
+            mis_d = 0.5 * (W[..., 0] + W[..., 1]).sum(dim=1)
+            dr_d = 0.5 * (gr[:, :, 0] + gr[:, :, 1])
         elif Wopt == "Wt":
-            mis_all[c0:c1] = W[..., 0].sum(dim=1)
-            dr = gr[:, :, 0]
+            mis_d, dr_d = W[..., 0].sum(dim=1), gr[:, :, 0].contiguous()
         else:
-            mis_all[c0:c1] = W[..., 1].sum(dim=1)
-            dr = gr[:, :, 1]
-        dr_all[c0:c1] = dr
-        if jd is not None:
-            dmis_all[c0:c1] = _B.chain_batch(jd, dr_all[c0:c1].reshape(m, nw * nt))        # :296
+            mis_d, dr_d = W[..., 1].sum(dim=1), gr[:, :, 1].contiguous()
+        dmis_d = None if jd is None else _B.chain_batch(jd, dr_d.reshape(m, nw * nt))      # :296
+        done = torch.cuda.Event()
+        done.record(main)
+        finished[c0] = (mis_d, dmis_d, dr_d, done, c1)
         sd.record_stream(main)
         if jd is not None:
             jd.record_stream(main)
+        if c1 < M:
+            stage(c1)                                           # next chunk's copies run under this chunk's kernels
+        if prev is not None:
+            fetch(prev)                                         # the previous chunk's results go home meanwhile
+        prev = c0
+    fetch(prev)
     main.synchronize()
+    d2h.synchronize()
     status.raise_for_reference(what="misfit_grad_models")
-    return (mis_all.cpu().numpy(), None if dmis_all is None else dmis_all.cpu().numpy(),
-            dr_all.reshape(M, nr, nc, nt).cpu().numpy())
+    return mis_h, dmis_h, dr_h.reshape(M, nr, nc, nt)
 
 
 def optfunc_ricker_batch(X, data):

@@ -221,9 +221,12 @@ static bool overlap_enabled() { return dev_option(kOptOverlap) != 1; }
 static int split_chunk(int B, int nug, int ntg, int sms) {
     int c;
     if (const int o = dev_option(kOptSplitChunk)) c = o;
-    else c = overlap_enabled() ? 8 * sms : 64 * sms;
-    const long long cap = (overlap_enabled() ? (1LL << 30) : (8LL << 30)) / ((long long)nug * ntg * 8);   // bytes per buffer
-    if (c > cap) c = (int)(cap < 1 ? 1 : cap);
+    else {
+        // about 512 MiB of scan results per buffer, between 8 and 64 windows per SM: long enough kernels to amortise
+        // their tails, small enough buffers for any batch size
+        const long long by_bytes = (512LL << 20) / ((long long)nug * ntg * 8);
+        c = (int)(by_bytes < 8LL * sms ? 8LL * sms : by_bytes > 64LL * sms ? 64LL * sms : by_bytes);
+    }
     if (c < (B + kMaxChunks - 1) / kMaxChunks) c = (B + kMaxChunks - 1) / kMaxChunks;
     return c < B ? c : B;
 }
@@ -232,8 +235,9 @@ bool split_wanted(int B, int nt, int nug, int ntg, int sms) {
     (void)nt;
     if (dev_option(kOptPipeline) == 1) return false;
     if (dev_option(kOptPipeline) == 2) return true;
-    // large windows (the single-kernel form would run 256-thread CTAs) and at least four windows per SM
-    return (long long)nug * ntg > 16384 && B >= 4 * sms;
+    // at least four windows per SM (smaller batches: the single-kernel form, with thread-block clusters for the smallest)
+    // and rows of at least one warp's width
+    return ntg >= 32 && (long long)nug * ntg >= 2048 && B >= 4 * sms;
 }
 
 size_t split_workspace_bytes(int B, int nt, int nug, int ntg, int sms) {
