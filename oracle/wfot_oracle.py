@@ -318,6 +318,14 @@ def merge_cdfs(cf, cg):
     return tkarg, tk, indf, indg, dtk
 
 
+# Test switch: with True, wasser() does not raise TargetSourceCDFError.  The check is an exact comparison of
+# floating-point CDF values (libs/OTlib.py:663-666): besides the structural case (identical windows) it fires on
+# chance coincidences of two doubles near 1, which depend on the last bit of every rounding and which no
+# implementation with a different summation order can share.  The randomised stress tests use the switch to compare
+# values in that case instead of the flag.
+IGNORE_COMMON_CDF = False
+
+
 def wasser(source: Pdf, target: Pdf, distfunc="W12", derivatives=False,
            checkCommonCDF=False, ignoreCommonCDFerror=False, return_merge=False, returnplan=False):
     """W_p^p (p=1,2), d/d(un-normalised source amplitudes), d/d(translation);
@@ -329,7 +337,7 @@ def wasser(source: Pdf, target: Pdf, distfunc="W12", derivatives=False,
     cf, cg, n = source.cdf, target.cdf, source.n
     if derivatives or checkCommonCDF:                             # :663-666
         cset = np.intersect1d(cg[:-1], cf[:-1])
-        if len(cset) != 0 and not ignoreCommonCDFerror:
+        if len(cset) != 0 and not (ignoreCommonCDFerror or IGNORE_COMMON_CDF):
             raise TargetSourceCDFError(str(cset))
     tkarg, tk, indf, indg, dtk = merge_cdfs(cf, cg)
     xft = source.x[indf]                                          # :676-678

@@ -559,9 +559,16 @@ def test_fused_random_shapes_stress(B):
                 W, dr, dg, _, _ = O.misfit_grad_window(t, wp[b], grid, tgt, lambdav=lam, distfunc=distfunc, q=q)
             except O.TargetSourceCDFError:
                 # density tails below the ulp of the CDF: both CDFs reach 1.0 early and the reference refuses
-                # (libs/OTlib.py:663-666); the kernel reports the same condition in its status counter
-                assert int(r["status"].read()[1]) > 0, msg
-                continue
+                # (libs/OTlib.py:663-666); the kernel's sequential CDF sum saturates the same way and reports the
+                # condition in its status counter.  What is left are chance coincidences of two doubles, which depend
+                # on the last bit of every rounding: there the values are compared instead.
+                if int(r["status"].read()[1]) > 0:
+                    continue
+                O.IGNORE_COMMON_CDF = True
+                try:
+                    W, dr, dg, _, _ = O.misfit_grad_window(t, wp[b], grid, tgt, lambdav=lam, distfunc=distfunc, q=q)
+                finally:
+                    O.IGNORE_COMMON_CDF = False
             np.testing.assert_allclose(r["W"][b].cpu().numpy(), W, rtol=1e-9, err_msg=msg)
             # the kernel's dwg is in normalised time units; the reference divides by Delt = tan(theta) (t1 - t0)
             # (libs/ricker_util.py:333), which adapters.py applies on the product path
@@ -626,8 +633,18 @@ def test_fused_variants_stress(B):
                 W, dr, dg, _, _ = O.misfit_grad_window(t64[b], wp64[b], gb, tgt, lambdav=lam, distfunc="W2",
                                                        theta=theta, transform=transform)
             except O.TargetSourceCDFError:
-                assert int(r["status"].read()[1]) > 0, msg
-                continue
+                if int(r["status"].read()[1]) > 0:
+                    continue
+                # a chance coincidence of two CDF doubles in the oracle's roundings (e.g. 0.9999999999997123 in both
+                # amplitude CDFs at lambda = 0.02, seed 20261018): not reproducible by a different summation order.
+                # The structural case (identical windows) has its own tests; here the VALUES must still agree.
+                O.IGNORE_COMMON_CDF = True
+                try:
+                    _, tgt = O.build_ot_from_waveform(t64[b], wo64[b], gb, lambdav=lam, transform=transform, theta=theta)
+                    W, dr, dg, _, _ = O.misfit_grad_window(t64[b], wp64[b], gb, tgt, lambdav=lam, distfunc="W2",
+                                                           theta=theta, transform=transform)
+                finally:
+                    O.IGNORE_COMMON_CDF = False
             np.testing.assert_allclose(r["W"][b].cpu().numpy(), W, rtol=rt_w, err_msg=msg)
             np.testing.assert_allclose(float(r["dwg"][b]) / (tant * (gb[1] - gb[0])), dg[0], rtol=10 * rt_w,
                                        atol=1e-11 * max(1.0, float(np.abs(W).max())), err_msg=msg)

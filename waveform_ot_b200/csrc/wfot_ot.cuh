@@ -104,9 +104,8 @@ __device__ __forceinline__ double block_cumsum(double* a, int n, double* red) {
 // (libs/OTlib.py:663-666 raises TargetSourceCDFError on common values; identical windows are the practical
 // trigger).  Observed and predicted CDFs are produced by different launches - different CTA sizes, one kernel
 // or two - so every sum that feeds a CDF bit uses an order that does not depend on the launch shape: warp 0
-// alone, lane k adding elements k, k + 32, ... in ascending order, then a xor-shuffle tree; the prefix sum
-// gives lane k the contiguous chunk [k c, (k + 1) c), c = ceil(n / 32), and scans the 32 chunk totals with
-// shuffles.  n is a grid axis (tens to ~1000 entries): a few hundred cycles per window.
+// alone, lane k adding elements k, k + 32, ... in ascending order, then a xor-shuffle tree; the prefix sum of
+// canon_cdf() is sequential (np.cumsum's own order).  n is a grid axis (tens to ~1000 entries).
 // Every thread of the block calls; `red` = 2 doubles of shared scratch.
 __device__ __forceinline__ double canon_sum(const double* a, int n, double* red) {
     if (threadIdx.x < 32) {
@@ -122,10 +121,14 @@ __device__ __forceinline__ double canon_sum(const double* a, int n, double* red)
     return r;
 }
 
-// OTpdf of a 1-D density in shared memory (libs/OTlib.py:91-93,112-114), canonical order:
+// OTpdf of a 1-D density in shared memory (libs/OTlib.py:91-93,112-114):
 // a[0..n) un-normalised amplitudes -> CDF = cumsum(a / amp) / cumsum(a / amp)[-1].  Returns amp; *neg (nullable,
-// valid in every thread) = number of negative amplitudes.  Entries a parallel prefix sum rounds below their
-// predecessor (terms under the ulp of the running sum) are raised to the running maximum, see block_cumsum().
+// valid in every thread) = number of negative amplitudes.
+// The prefix sum is SEQUENTIAL, one lane, exactly np.cumsum's order (:113).  That is affordable here - n is a grid
+// axis, the chain is n dependent additions (~2 k cycles for 256 bins against ~10^6 per window) - and it buys the
+// reference's behaviour where a parallel scan only approximates it: the result is non-decreasing by construction,
+// and a density tail below the ulp of the running sum saturates to EXACTLY the total, so both CDFs of such a pair
+// hold 1.0 before their last entry and the reference's common-CDF check (:663-666) fires - here as there.
 __device__ __forceinline__ double canon_cdf(double* a, int n, double* red, int* neg) {
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
@@ -138,37 +141,16 @@ __device__ __forceinline__ double canon_cdf(double* a, int n, double* red, int* 
             ng += __shfl_xor_sync(0xffffffffu, ng, off);
         }
         const double amp = v;
-        const int c = (n + 31) >> 5, beg = min(lane * c, n), end = min(beg + c, n);
-        double run = 0.0;
-        for (int j = beg; j < end; ++j) { run += a[j] / amp; a[j] = run; }
-        double inc = run;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const double o = __shfl_up_sync(0xffffffffu, inc, off);
-            if (lane >= off) inc += o;
-        }
-        const double excl = inc - run;
-        for (int j = beg; j < end; ++j) a[j] += excl;
+        for (int j = lane; j < n; j += 32) a[j] = a[j] / amp;    // pdf / amp (:93)
         __syncwarp();
-        int viol = 0;
-        for (int j = max(beg, 1); j < end; ++j) viol |= (a[j] < a[j - 1]);
-        if (__any_sync(0xffffffffu, viol)) {                   // rare: restore the order with an exact running maximum
-            double m = 0.0;
-            for (int j = beg; j < end; ++j) { m = fmax(m, a[j]); a[j] = m; }
-            double mi = m;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double o = __shfl_up_sync(0xffffffffu, mi, off);
-                if (lane >= off) mi = fmax(mi, o);
-            }
-            double me = __shfl_up_sync(0xffffffffu, mi, 1);
-            if (lane == 0) me = 0.0;
-            for (int j = beg; j < end; ++j) a[j] = fmax(a[j], me);
+        if (lane == 0) {
+            double run = 0.0;
+            for (int j = 0; j < n; ++j) { run += a[j]; a[j] = run; }
         }
         __syncwarp();
         const double last = a[n - 1];
         __syncwarp();
-        for (int j = beg; j < end; ++j) a[j] = a[j] / last;
+        for (int j = lane; j < n; j += 32) a[j] = a[j] / last;   // cdf / cdf[-1] (:114)
         if (lane == 0) { red[0] = amp; red[1] = __longlong_as_double((long long)ng); }
     }
     __syncthreads();
