@@ -837,3 +837,57 @@ def test_fused_run_to_run(B):
         assert float(((g - g0).abs() / scale).max()) <= 1e-12
     assert torch.equal(small["W"], W0[:3]) and torch.equal(small["dwg"], d0[:3])
     assert float(((small["grad"] - g0[:3]).abs() / scale[:3]).max()) <= 1e-12
+
+
+@pytest.mark.parametrize("nt,nug,ntg,dtype,transform", [(40, 33, 47, np.float64, False), (77, 50, 32, np.float32, False),
+                                                        (61, 79, 61, np.float64, True), (130, 21, 96, np.float32, False)])
+def test_two_kernel_form_chunked_variants(B, nt, nug, ntg, dtype, transform):
+    """The throughput form (k_scan + k_resolve, chunks on two streams) on awkward shapes: odd / non-multiple-of-32 row
+    lengths, fewer rows than warps per group, per-window time axes, grids and observed windows, several chunks with a
+    ragged last one.  Every window must equal the single-kernel form bit for bit (W, dwg) / to 1e-12 (grad), and a
+    sample of windows is checked against the oracle."""
+    from waveform_ot_b200 import _cabi as C
+    rng = np.random.default_rng(nt * 1000 + ntg)
+    sms = C.lib.wfot_device_sm_count()
+    nb, lam = 4 * sms + 7, 0.05
+    tt = (np.sort(rng.random((nb, nt)), axis=1) * 3.0 + 0.5).astype(dtype)
+    wp = (rng.standard_normal((nb, nt)).cumsum(axis=1) * 0.1).astype(dtype)
+    wo = (rng.standard_normal((nb, nt)).cumsum(axis=1) * 0.1).astype(dtype)
+    t64, wp64, wo64 = tt.astype(np.float64), wp.astype(np.float64), wo.astype(np.float64)
+    grids = []
+    for b in range(nb):
+        lo, hi = min(wp64[b].min(), wo64[b].min()), max(wp64[b].max(), wo64[b].max())
+        pad = 0.15 * (hi - lo) + 1e-3
+        grids.append((float(t64[b, 0]) - 0.3, float(t64[b, -1]) + 0.2, float(lo - pad), float(hi + pad), nug, ntg))
+    if transform:
+        uo = np.stack([O.arctan_trans(wo64[b], *grids[b][2:4]) for b in range(nb)])
+        tgrids = [g[:2] + (0.0, 1.0, nug, ntg) for g in grids]
+    else:
+        uo, tgrids = wo64, grids
+    tg = B.Target.from_waveform(t64, uo, tgrids, nug, ntg, lam)
+    res = {}
+    try:
+        for name, pipeline, chunk in (("one", 1, 0), ("two", 2, 0), ("two_chunked", 2, 150)):
+            C.lib.wfot_dev_set_option(C.OPT_PIPELINE, pipeline)
+            C.lib.wfot_dev_set_option(C.OPT_SPLIT_CHUNK, chunk)
+            r = B.misfit_grad_batch(tt, wp, grids, nug, ntg, lam, tg, transform=transform)
+            torch.cuda.synchronize()
+            res[name] = (r["W"].clone(), r["dwg"].clone(), r["grad"].clone(), r["status"].read().copy())
+    finally:
+        C.lib.wfot_dev_set_option(C.OPT_PIPELINE, 0)
+        C.lib.wfot_dev_set_option(C.OPT_SPLIT_CHUNK, 0)
+    W0, d0, g0, st0 = res["one"]
+    scale = g0.abs().amax(dim=2, keepdim=True).clamp_min(1e-300)
+    for name in ("two", "two_chunked"):
+        W, d, g, st = res[name]
+        assert torch.equal(W, W0) and torch.equal(d, d0), name
+        assert float(((g - g0).abs() / scale).max()) <= 1e-12, name
+        assert list(st[:4]) == list(st0[:4]), name
+    rt_w, rt_g = (1e-7, 1e-5) if transform else (1e-9, 1e-7)
+    for b in (0, 149, 150, nb - 1):
+        _, tgt = O.build_ot_from_waveform(t64[b], wo64[b], grids[b], lambdav=lam, transform=transform)
+        Wr, dr, dg, _, _ = O.misfit_grad_window(t64[b], wp64[b], grids[b], tgt, lambdav=lam, distfunc="W2", transform=transform)
+        np.testing.assert_allclose(res["two_chunked"][0][b].cpu().numpy(), Wr, rtol=rt_w)
+        for i in range(2):
+            np.testing.assert_allclose(res["two_chunked"][2][b, i].cpu().numpy(), dr[i], rtol=rt_g,
+                                       atol=rt_g * 1e-2 * np.abs(dr[i]).max())
