@@ -507,6 +507,62 @@ def sweep_fixed_total(B, C, dist, world, rank, dev, total, t, grids, target, sta
                                                   float(acc[2].item()), float(acc[3:].sum().item())]
 
 
+def cfg4_models_sharded(B, C, dist, world, rank, dev):
+    """The small-batch regime (BASELINE.json configs[3] across GPUs): 4096 trial models x 30 windows of 61 samples,
+    device resident, the MODELS sharded over the ranks (strong scaling: 512 models = 15 360 tiny windows per GPU at
+    N = 8); per step the fused misfit + gradient, the Wavg combination, the Jacobian chain to 9 parameters and one
+    all-gather of (misfit, 9 derivatives) per model.  Returns models/s (max time over ranks)."""
+    import torch
+    from waveform_ot_b200 import dist as wd
+    M, nw, nt, nug, ntg, lam, P = 4096, 30, 61, 79, 61, 0.04, 9
+    lo, hi = wd.shard_bounds(M, rank, world)
+    m = hi - lo
+    w = make_windows_device(M * nw, nt, 4242, dev)[lo * nw:max(hi, lo + 1) * nw].contiguous()   # the same models for every N
+    obs = make_windows_device(nw, nt, 99, dev)
+    t = torch.linspace(0, 1, nt, device=dev, dtype=torch.float32)
+    grids = [(0.0, 1.0, -1.3 - 0.01 * i, 1.3 + 0.01 * i, nug, ntg) for i in range(nw)]     # one per station/component
+    g = B.pack_grids(grids)
+    tg = B.Target.from_waveform(t, obs, grids, nug, ntg, lam)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(777)
+    J = torch.randn((M, P, nw * nt), generator=gen, dtype=torch.float64, device=dev)[lo:max(hi, lo + 1)].contiguous()
+    ws = torch.empty(C.lib.wfot_misfit_grad_workspace_bytes(max(m, 1) * nw, nt, nug, ntg), dtype=torch.uint8, device=dev)
+    out_all = torch.empty((M, 1 + P), dtype=torch.float64, device=dev)
+    sizes = [wd.shard_bounds(M, r, world)[1] - wd.shard_bounds(M, r, world)[0] for r in range(world)]
+    res = {"r": None}
+
+    def step():
+        r = res["r"] = B.misfit_grad_batch(t, w, g, nug, ntg, lam, tg, distfunc="W2", workspace=ws, out=res["r"])
+        W = r["W"].reshape(-1, nw, 2)
+        gr = r["grad"].reshape(-1, nw, 2, nt)
+        mis = 0.5 * (W[..., 0] + W[..., 1]).sum(dim=1)
+        dr = (0.5 * (gr[:, :, 0] + gr[:, :, 1])).reshape(-1, nw * nt)
+        mine = torch.cat([mis[:, None], B.chain_batch(J, dr)], dim=1)
+        if world > 1:
+            dist.all_gather(list(out_all.split(sizes)), mine[:m].contiguous())
+        else:
+            out_all.copy_(mine)
+
+    step()
+    torch.cuda.synchronize()
+    best = 1e30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(); step(); e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        best = min(best, float(ms.item()))
+    return {"models": M, "models_per_gpu": m, "windows_per_gpu": m * nw, "ms": best, "models_per_s": M / best * 1e3,
+            "scaling": "strong (fixed 4096 models)", "checksum": float(out_all[:, 0].sum().item()),
+            "note": "device-resident seismograms + Jacobians, fused misfit + gradient, Jacobian chain, one all-gather of "
+                    "(misfit, 9 derivatives) per model"}
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -702,6 +758,8 @@ def run_ours(args):
                  "note": "windows generated on the device inside the timed region, batches of %d, one allreduce at the "
                          "end; identical windows for every GPU count (checksums comparable across N)" % SWEEP_BATCH}
 
+    cfg4_sharded = cfg4_models_sharded(B, C, dist, world, rank, dev) if args.secondary else None
+
     st = status.read()
     if rank == 0:
         total_windows = world * nb * args.steps
@@ -745,6 +803,7 @@ def run_ours(args):
             "parity_check": parity,
             "allreduce_check": allreduce_check,
             "sweep_4M": sweep,
+            "cfg4_4096_models_sharded": cfg4_sharded,
             "status_counters": {"slow_pixels": int(st[4]), "common_cdf": int(st[1]), "zero_dist": int(st[2])},
         }
         if world == 1 and args.secondary:

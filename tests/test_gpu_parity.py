@@ -809,9 +809,9 @@ def test_sharded_periodic_rows_equal_unsharded(B, monkeypatch):
 
 
 def test_fused_run_to_run(B):
-    """Reproducibility contract of include/wfot.h: W and dwg bit-identical from run to run and across launch shapes
-    (single kernel / scan + resolve / clusters); grad (FP64 L2 reductions in arrival order) to <= 1e-12 of the
-    row's largest entry."""
+    """Reproducibility contract of include/wfot.h: W and dwg bit-identical from run to run, and across the forms of the
+    path when they use the same CTA size (here 256 threads: single kernel / scan + resolve / clusters); grad (FP64 L2
+    reductions in arrival order) to <= 1e-12 of the row's largest entry."""
     from waveform_ot_b200 import _cabi as C
     nt, nug, ntg, lam = 300, 160, 128, 0.04
     nb = 4 * C.lib.wfot_device_sm_count() + 5                 # enough windows for the two-kernel form
@@ -844,8 +844,8 @@ def test_fused_run_to_run(B):
 def test_two_kernel_form_chunked_variants(B, nt, nug, ntg, dtype, transform):
     """The throughput form (k_scan + k_resolve, chunks on two streams) on awkward shapes: odd / non-multiple-of-32 row
     lengths, fewer rows than warps per group, per-window time axes, grids and observed windows, several chunks with a
-    ragged last one.  Every window must equal the single-kernel form bit for bit (W, dwg) / to 1e-12 (grad), and a
-    sample of windows is checked against the oracle."""
+    ragged last one.  Every window must equal the single-kernel form to rounding, the chunked run must equal the
+    unchunked one bit for bit, and a sample of windows is checked against the oracle."""
     from waveform_ot_b200 import _cabi as C
     rng = np.random.default_rng(nt * 1000 + ntg)
     sms = C.lib.wfot_device_sm_count()
@@ -878,9 +878,13 @@ def test_two_kernel_form_chunked_variants(B, nt, nug, ntg, dtype, transform):
         C.lib.wfot_dev_set_option(C.OPT_SPLIT_CHUNK, 0)
     W0, d0, g0, st0 = res["one"]
     scale = g0.abs().amax(dim=2, keepdim=True).clamp_min(1e-300)
+    assert torch.equal(res["two"][0], res["two_chunked"][0]) and torch.equal(res["two"][1], res["two_chunked"][1])
     for name in ("two", "two_chunked"):
         W, d, g, st = res[name]
-        assert torch.equal(W, W0) and torch.equal(d, d0), name
+        # the single-kernel form runs these small windows with 64 / 128 threads per CTA: same CDFs, but the final sums
+        # over the merged knots are block reductions (include/wfot.h): agreement to rounding, not bitwise
+        np.testing.assert_allclose(W.cpu().numpy(), W0.cpu().numpy(), rtol=1e-13, err_msg=name)
+        np.testing.assert_allclose(d.cpu().numpy(), d0.cpu().numpy(), rtol=1e-12, atol=1e-13, err_msg=name)
         assert float(((g - g0).abs() / scale).max()) <= 1e-12, name
         assert list(st[:4]) == list(st0[:4]), name
     rt_w, rt_g = (1e-7, 1e-5) if transform else (1e-9, 1e-7)
