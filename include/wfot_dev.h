@@ -21,6 +21,11 @@ int wfot_fp32_peak_probe(int packed, int iters, float* sink, double* fma_ops, vo
  * library's own choice.  Returns the previous value, or -1 for an unknown id. */
 int wfot_dev_set_option(int id, int value);
 
+/* The two elementary functions of the fused path's density epilogue on arbitrary arguments (n device doubles):
+ * exp_neg_out[i] = exp(-x[i]) (table + degree-5 polynomial, csrc/wfot_exp.cuh), rsqrt_out[i] = 1/sqrt(x[i])
+ * (one MUFU + third-order correction).  For the accuracy tests. */
+int wfot_dev_epilogue_math(const double* x, double* exp_neg_out, double* rsqrt_out, int n, void* stream);
+
 /* Number of kernels the library has launched in this process so far (bench.py's gpu_launches). */
 long long wfot_dev_kernel_launches(void);
 

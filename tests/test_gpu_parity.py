@@ -895,3 +895,32 @@ def test_two_kernel_form_chunked_variants(B, nt, nug, ntg, dtype, transform):
         for i in range(2):
             np.testing.assert_allclose(res["two_chunked"][2][b, i].cpu().numpy(), dr[i], rtol=rt_g,
                                        atol=rt_g * 1e-2 * np.abs(dr[i]).max())
+
+
+def test_epilogue_math_accuracy(B):
+    """exp(-x) (64-entry table + degree-5 polynomial) and 1/sqrt(x) (MUFU + third-order correction) of the fused
+    path's density epilogue against correctly rounded references: <= 1 ulp / <= 1.5 ulp, exact at the ends of the
+    range (exp(-0) = 1, gradual underflow, 0 beyond)."""
+    from decimal import Decimal, getcontext
+    from waveform_ot_b200 import _cabi as C
+    getcontext().prec = 50
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.uniform(0, 60, 200000), rng.uniform(0, 745, 50000), 10.0 ** rng.uniform(-300, 2, 50000),
+                        np.array([0.0, 1e-320 * 0 + 5e-324, 708.0, 744.0, 745.2, 800.0, 1399.0, 1500.0, 1e300])])
+    xd = torch.from_numpy(x).cuda()
+    e, r = torch.empty_like(xd), torch.empty_like(xd)
+    C.check(C.lib.wfot_dev_epilogue_math(C.ptr(xd), C.ptr(e), C.ptr(r), x.size, None))
+    torch.cuda.synchronize()
+    e, r = e.cpu().numpy(), r.cpu().numpy()
+    idx = np.concatenate([rng.integers(0, 250000, 4000), np.arange(x.size - 9, x.size)])
+    ref = np.array([float((-Decimal(float(v))).exp()) for v in x[idx]])
+    ok = ref > 2.3e-308
+    assert np.max(np.abs(e[idx][ok] - ref[ok]) / ref[ok]) <= 2.0 ** -52           # 1 ulp
+    assert np.all(np.abs(e[idx][~ok] - ref[~ok]) <= 5e-324 * 2 ** 12)             # subnormal results: absolute
+    assert e[x.size - 9] == 1.0 and e[-1] == 0.0 and e[-2] == 0.0
+    # against NumPy's exp (what the reference calls): within 2 ulp everywhere it is normal
+    big = np.exp(-x) > 2.3e-308
+    assert np.max(np.abs(e[big] - np.exp(-x[big])) / np.exp(-x[big])) <= 2.0 ** -51
+    pos = x > 1e-290
+    rr = 1.0 / np.sqrt(x[pos].astype(np.longdouble))
+    assert np.max(np.abs(r[pos].astype(np.longdouble) - rr) / rr) <= 1.5 * 2.0 ** -52

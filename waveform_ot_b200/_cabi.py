@@ -68,6 +68,7 @@ DEV_SIGNATURES = {
     "wfot_dev_set_option": (C.c_int, [_i, _i]),
     "wfot_dev_capture_iray": (None, [_p]),
     "wfot_dev_kernel_launches": (C.c_longlong, []),
+    "wfot_dev_epilogue_math": (C.c_int, [_p, _p, _p, _i, _p]),
 }
 (OPT_PIPELINE, OPT_RESOLVE_SHAPE, OPT_FUSED_THREADS, OPT_CLUSTER_MAX, OPT_TILE, OPT_SPLIT_CHUNK, OPT_OVERLAP,
  OPT_SCAN_SHAPE) = range(8)

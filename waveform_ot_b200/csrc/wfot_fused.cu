@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     const size_t slab = (size_t)cid * npix;
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T};
     int zero_dist = 0, slow = 0, common = 0, degen = 0, tiles = 0;
+    load_exp_table(s_etab);      // visible behind the first barrier of the window loop
 
     // windows are drawn from a global counter (the pruned scan makes their cost uneven): the first window of a
     // CTA is blockIdx.x, the following ones come from the counter, which starts at gridDim.x.  Clusters take
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
                     ++slow;
                     resolve_pixel_full(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], pyd, kb1, hit);
                 }
-                store_pixel(a, s_pn, slab, it, iu, hit, pyd, zero_dist, dbg);
+                store_pixel(a, s_pn, s_etab, slab, it, iu, hit, pyd, zero_dist, dbg);
             }
         }
         __syncthreads();
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
                 const int it = qe.pix % a.ntg, iu = qe.pix / a.ntg;
                 PixelHit hit;
                 resolve_pixel_warp(tb, s_pn, s_pxs[it], s_pys[iu], s_xt[it], s_xu[iu], qe.b1, hit);
-                if (lane == 0) { store_pixel(a, s_pn, slab, it, iu, hit, s_xu[iu], zero_dist, dbg); ++slow; }
+                if (lane == 0) { store_pixel(a, s_pn, s_etab, slab, it, iu, hit, s_xu[iu], zero_dist, dbg); ++slow; }
             }
         }
         __syncthreads();   // scratch slab complete (block-scope visibility of global writes)
@@ -148,6 +149,18 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     }
 }
 
+}  // namespace wfot
+
+namespace wfot {
+// wfot_dev_epilogue_math: the fused path's exp(-x) and 1/sqrt(x) on arbitrary arguments (accuracy tests)
+__global__ void __launch_bounds__(256) k_epilogue_math(const double* __restrict__ x, double* __restrict__ e,
+                                                       double* __restrict__ r, int n) {
+    __shared__ double2 tab[64];
+    load_exp_table(tab);
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) { e[i] = exp_neg(x[i], tab); r[i] = rsqrt_lean(x[i]); }
+}
 }  // namespace wfot
 
 using namespace wfot;
@@ -249,6 +262,13 @@ int wfot_dev_set_option(int id, int value) {
 // occupancy call), plus - for batches that take the two-kernel form - 8 bytes per pixel per window
 // of one scan/resolve launch pair.
 void wfot_dev_capture_iray(int32_t* iray) { g_iray_capture = iray; }
+
+int wfot_dev_epilogue_math(const double* x, double* exp_neg_out, double* rsqrt_out, int n, void* stream) {
+    if (!x || !exp_neg_out || !rsqrt_out || n <= 0) return WFOT_ERR_INVALID_ARG;
+    k_epilogue_math<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, exp_neg_out, rsqrt_out, n);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? WFOT_OK : cuda_fail(e, "wfot_dev_epilogue_math launch");
+}
 
 size_t wfot_misfit_grad_workspace_bytes(int B, int nt, int nug, int ntg) {
     if (B <= 0 || nt < 2 || nug < 1 || ntg < 1) return 0;

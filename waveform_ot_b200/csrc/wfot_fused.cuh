@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "wfot_device.cuh"
+#include "wfot_exp.cuh"
 #include "wfot_host.h"
 #include "wfot_ot.cuh"
 
@@ -30,6 +31,7 @@ constexpr int kRowGroups = 8;
 // shared address space (LDS/STS instead of generic loads).
 struct SmemLayout {
     int pn, A, H, bbox, keys, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
+    int etab;       // 2^(j/64) table of exp_neg() (1 KB)
     int colpart;    // resolve kernel: per-row-group column sums of the density, [kRowGroups][ntg_pad] doubles
     int qcap;       // entries of the ambiguous-pixel queue
     int total;
@@ -75,6 +77,7 @@ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nm
         L.qcap = (kind == kLayoutResolve) ? kFQCap / 2 : kFQCap;
         L.queue = take(L.qcap * (int)sizeof(FQEntry));
     }
+    if (kind != kLayoutScan) L.etab = take(128 * 8);
     L.red = take(64 * 8);
     L.hdr = take(128);
     L.pxs = take(ntg_pad * 4);
@@ -134,6 +137,7 @@ constexpr unsigned kScanFlag2 = 1u << 30, kScanFlag3 = 1u << 31, kScanTileMask =
     double* const s_red = reinterpret_cast<double*>(smem_raw + (L).red);                 \
     double* const s_gbins = reinterpret_cast<double*>(smem_raw + (L).gbins);             \
     double* const s_colpart = reinterpret_cast<double*>(smem_raw + (L).colpart);         \
+    double2* const s_etab = reinterpret_cast<double2*>(smem_raw + (L).etab);             \
     int* const s_posf = reinterpret_cast<int*>(smem_raw + (L).posf);                     \
     FQEntry* const s_queue = reinterpret_cast<FQEntry*>(smem_raw + (L).queue);           \
     WinHdr* const s_hdr = reinterpret_cast<WinHdr*>(smem_raw + (L).hdr);                 \
@@ -141,12 +145,26 @@ constexpr unsigned kScanFlag2 = 1u << 30, kScanFlag3 = 1u << 31, kScanTileMask =
 
 // pixel -> scratch: density and the two gradient weights of its nearest segment.
 // The throughput path needs d = sqrt(D) only to form exp(-d / lambda) and (xclose_y - p_y) / d, so the three
-// slow FP64 library sequences (IEEE sqrt, two IEEE divisions: ~70 instructions) are replaced by one rsqrt and
-// fused-multiply-add corrections: d = D r + (D - (D r)^2) r / 2, the quotients by Markstein's q0 = a y,
+// slow FP64 library sequences (IEEE sqrt, two IEEE divisions: ~70 instructions) are replaced by one reciprocal
+// square root (rsqrt_lean) and fused-multiply-add corrections: d = D r + (D - (D r)^2) r / 2, the quotients by Markstein's q0 = a y,
 // q = q0 + (a - b q0) y with y = RN(1 / b) (correctly rounded but for rare half-ulp cases; the density then
 // differs from the materialising kernel's by <= 1 ulp of the exponent, i.e. ~1e-15 relative).
+// 1 / sqrt(D) for normal D > 0: one MUFU (rsqrt.approx.f64, ~2^-22) and a third-order correction
+// y = y0 (1 + e/2 + 3 e^2 / 8), e = 1 - D y0^2 (truncation 5 e^3 / 16 ~ 2^-66): 6 instructions against ~17 for rsqrt().
+__device__ __forceinline__ double rsqrt_lean(double D) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(D));
+    const double e = fma(-(D * y0), y0, 1.0);
+    return fma(y0 * e, fma(0.375, e, 0.5), y0);
+}
+
+// Copy the exp table to shared memory (every thread of the CTA calls; a barrier must follow before store_pixel).
+__device__ __forceinline__ void load_exp_table(double2* s_etab) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) reinterpret_cast<double*>(s_etab)[i] = kExp2Tab[i];
+}
+
 template <bool STORE_PDF = true>
-__device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2* pn, size_t slab,
+__device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2* pn, const double2* etab, size_t slab,
                                               int it, int iu, const PixelHit& hit, double py, int& zero_dist,
                                               int32_t* dbg_iray = nullptr) {
     const double* const pny = reinterpret_cast<const double*>(pn) + 1;
@@ -156,7 +174,7 @@ __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2*
     const double num = xcy - py;
     double d, g;
     if (hit.D > 0.0) {
-        const double rs = rsqrt(hit.D);
+        const double rs = rsqrt_lean(hit.D);
         const double d0 = hit.D * rs;
         d = fma(fma(-d0, d0, hit.D), 0.5 * rs, d0);            // (:263)
         const double g0 = num * rs;
@@ -169,7 +187,7 @@ __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2*
     const double e = (a.q == 2) ? d * d : d;                   // exp(-d^2/lambda) (:174) or exp(-|d|/lambda) (:176)
     const double q0 = e * a.rlambda;
     const double x = fma(fma(-q0, a.lambda, e), a.rlambda, q0);
-    const double pdf = exp(-x);
+    const double pdf = exp_neg(x, etab);
     double wgt = pdf * g;                                      // pdf * dddx_y
     if (a.q == 2) wgt *= 2.0 * d;                              // :214-217
     const size_t k = slab + (size_t)iu * a.ntg + it;
@@ -194,7 +212,7 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
                                            const WinHdr& hdr) {
     WFOT_SMEM_POINTERS(a.L);
     (void)s_pn; (void)s_A; (void)s_H; (void)s_bbox; (void)s_keys; (void)s_pxs; (void)s_pys; (void)s_queue;
-    (void)s_hdr; (void)s_qcount; (void)s_colpart;
+    (void)s_hdr; (void)s_qcount; (void)s_colpart; (void)s_etab;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---------------- P2: column sums (kRowGroups groups of rows, see above)
     if (HAVE_SUMS) {   // the resolve kernel accumulated the groups (s_colpart) and the raw row sums (s_margu) in P1

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     (void)s_margt; (void)s_margu; (void)s_Rt; (void)s_Ru; (void)s_xt; (void)s_xu; (void)s_cf; (void)s_E;
-    (void)s_tk; (void)s_dx; (void)s_gbins; (void)s_posf; (void)s_queue; (void)s_colpart;
+    (void)s_tk; (void)s_dx; (void)s_gbins; (void)s_posf; (void)s_queue; (void)s_colpart; (void)s_etab;
     const int tid = threadIdx.x, lane = tid & 31;
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T};
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(FusedArgs a) {
     int zero_dist = 0, slow = 0, common = 0;
     int* const counter = a.next_window + 16;
     double* const colp = s_colpart + warp * a.ntg_pad;
+    load_exp_table(s_etab);      // visible behind the first barrier of the window loop
     for (int i = blockIdx.x; i < a.B;) {
         const int b = a.b0 + i;
         const wfot_grid g = a.grids[b % a.n_grids];
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(FusedArgs a) {
                     if (lane == src) { hit = h2; ++slow; }
                 }
                 if (live) {
-                    const double pdf = store_pixel<false>(a, s_pn, slab, it, iu, hit, pyd, zero_dist, dbg);
+                    const double pdf = store_pixel<false>(a, s_pn, s_etab, slab, it, iu, hit, pyd, zero_dist, dbg);
                     rowacc += pdf;                                    // columns lane, lane + 32, ... in ascending order
                     colp[it] += pdf;                                  // rows warp, warp + 8, ... in ascending order
                 }
