@@ -35,6 +35,12 @@ long long wfot_dev_kernel_launches(void);
  * against the CPU oracle after the timed region.  NULL switches the capture off. */
 void wfot_dev_capture_iray(int32_t* iray);
 
+/* While `cycles` is non-NULL, k_resolve (two-kernel form) adds the SM clock cycles its CTAs spend per phase to
+ * cycles[0..5] (uint64, device memory): [0] window preparation, [1] P1 per-pixel resolve + density, [2] P2 + P3
+ * marginals and 1-D OT, [3] P4 gradient assembly, [4] windows, [5] unused.  Thread 0 of every CTA reads the clock
+ * at the phase boundaries; for scripts/phase_cycles.py.  NULL switches it off. */
+void wfot_dev_phase_cycles(unsigned long long* cycles);
+
 #ifdef __cplusplus
 }
 #endif

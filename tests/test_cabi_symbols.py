@@ -50,6 +50,6 @@ def test_sass_is_blackwell_packed_fp32():
     for op in ("FFMA2", "FMUL2", "FMNMX3", "FADD.SAT",
                "VOTE.ANY",              # per-lane tile pruning of the scan: one vote per tile
                "CREDUX.MIN",            # best-first tile order: one warp minimum pops the next tile
-               "ATOMG.E.ADD.F64",       # gradient assembly: native FP64 reductions in L2
+               "REDG.E.ADD.F64",       # gradient assembly: native FP64 reductions in L2
                "UCGABAR_ARV"):          # thread-block cluster barrier (one window per cluster for small batches)
         assert op in out, op

@@ -67,11 +67,12 @@ DEV_SIGNATURES = {
     "wfot_fp32_peak_probe": (C.c_int, [_i, _i, _p, _p, _p]),
     "wfot_dev_set_option": (C.c_int, [_i, _i]),
     "wfot_dev_capture_iray": (None, [_p]),
+    "wfot_dev_phase_cycles": (None, [_p]),
     "wfot_dev_kernel_launches": (C.c_longlong, []),
     "wfot_dev_epilogue_math": (C.c_int, [_p, _p, _p, _i, _p]),
 }
 (OPT_PIPELINE, OPT_RESOLVE_SHAPE, OPT_FUSED_THREADS, OPT_CLUSTER_MAX, OPT_TILE, OPT_SPLIT_CHUNK, OPT_OVERLAP,
- OPT_SCAN_SHAPE) = range(8)
+ OPT_SCAN_SHAPE, OPT_SKIP_KERNEL) = range(9)
 
 for _name, (_res, _args) in list(SIGNATURES.items()) + list(DEV_SIGNATURES.items()):
     _f = getattr(lib, _name)       # AttributeError here = header/library mismatch

@@ -59,6 +59,12 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
     return r;
 }
 
+// Fire-and-forget FP64 addition in L2.  atomicAdd() with an unused result compiles to ATOMG (the value travels back
+// and holds a scoreboard) inside divergent code; the PTX reduction is REDG everywhere.
+__device__ __forceinline__ void red_add(double* p, double v) {
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
 // The segment table, tile boxes and tile keys always live in shared memory; the pointers reach the
 // scan / resolve functions through structs, where the compiler loses the address space and falls back
 // to generic loads (LD.E instead of LDS: longer latency, long-scoreboard tracking).  Telling it restores LDS.
@@ -239,6 +245,79 @@ __device__ __forceinline__ bool resolve_pixel_flagged(const SegTable& tb, const 
     eval_candidates<T>(pn, t1, m1, px, py, hit);
     if (m2) eval_candidates<T>(pn, t1 + 1, m2, px, py, hit);
     return true;
+}
+
+// Two pixels of one thread at a time (the resolve kernel): the FP32 re-evaluations and the FP64 reference-order
+// evaluations of the two pixels are written as straight-line code side by side, so that the two dependency chains
+// fill each other's latency slots (one pixel per thread leaves the warp waiting on its own previous instruction
+// most of the time).  Same candidate sets, same evaluation order per pixel, hence the same results as
+// resolve_pixel_flagged(); pixels whose candidates span several tiles take that function's path one by one.
+__device__ __forceinline__ void eval64x2(const double2* __restrict__ pn, const int (&s)[2], const double (&px)[2],
+                                         double py, double (&D)[2], double (&lam)[2]) {
+    double cx[2], cy[2], L[2], bx[2], by[2], num[2], l[2];
+    bool inside = false;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const double2 a = pn[s[p]];
+        const double2 b = pn[s[p] + 1];
+        cx[p] = __dsub_rn(b.x, a.x);
+        cy[p] = __dsub_rn(b.y, a.y);
+        L[p] = __dadd_rn(__dmul_rn(cx[p], cx[p]), __dmul_rn(cy[p], cy[p]));
+        bx[p] = __dsub_rn(px[p], a.x);
+        by[p] = __dsub_rn(py, a.y);
+        num[p] = __dadd_rn(__dmul_rn(bx[p], cx[p]), __dmul_rn(by[p], cy[p]));
+        l[p] = (num[p] <= 0.0) ? 0.0 : 1.0;
+        inside |= (num[p] > 0.0 && num[p] < L[p]);
+    }
+    if (inside) {      // see eval64(): outside (0, L) the clip decides whatever the quotient rounds to
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const double q = fmin(fmax(__ddiv_rn(num[p], L[p]), 0.0), 1.0);
+            l[p] = (num[p] > 0.0 && num[p] < L[p]) ? q : l[p];
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const double dx = __dsub_rn(bx[p], __dmul_rn(cx[p], l[p]));
+        const double dy = __dsub_rn(by[p], __dmul_rn(cy[p], l[p]));
+        D[p] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        lam[p] = l[p];
+    }
+}
+
+// code[p] = the scan's second word (tile | flags); done[p] = false -> the caller runs the all-segment rescan.
+template <int T>
+__device__ __forceinline__ void resolve_pixels2(const SegTable& tb, const double2* __restrict__ pn,
+                                                const float (&pxl)[2], float pyl, const double (&px)[2], double py,
+                                                const float (&thr)[2], const unsigned (&code)[2],
+                                                unsigned tilemask, unsigned flag2, unsigned flag3,
+                                                PixelHit (&hit)[2], bool (&done)[2]) {
+    unsigned m[2];
+    int t1[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        t1[p] = (int)(code[p] & tilemask);
+        hit[p].D = CUDART_INF; hit[p].lam = 0.0; hit[p].s = t1[p] * T;
+        m[p] = tile_mask<T>(tb, t1[p], pxl[p], pyl, thr[p]);
+        done[p] = true;
+    }
+    unsigned m0 = (code[0] & flag2) ? 0u : m[0], m1 = (code[1] & flag2) ? 0u : m[1];
+    while (m0 | m1) {
+        // an exhausted pixel re-evaluates its current segment: D < hit.D is false, nothing changes
+        const int j0 = m0 ? t1[0] * T + __ffs((int)m0) - 1 : hit[0].s;
+        const int j1 = m1 ? t1[1] * T + __ffs((int)m1) - 1 : hit[1].s;
+        m0 &= m0 - 1u; m1 &= m1 - 1u;
+        const int s[2] = {j0, j1};
+        double D[2], l[2];
+        eval64x2(pn, s, px, py, D, l);
+        if (D[0] < hit[0].D) { hit[0].D = D[0]; hit[0].lam = l[0]; hit[0].s = j0; }
+        if (D[1] < hit[1].D) { hit[1].D = D[1]; hit[1].lam = l[1]; hit[1].s = j1; }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+        if (code[p] & flag2)
+            done[p] = resolve_pixel_flagged<T>(tb, pn, pxl[p], pyl, px[p], py, thr[p], t1[p], true,
+                                               (code[p] & flag3) != 0u, hit[p]);
 }
 
 template <int T>

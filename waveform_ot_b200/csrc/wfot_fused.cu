@@ -53,17 +53,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
     for (int b = cid; b < a.B;) {
         // ---------------- P0: window -> shared memory
         const wfot_grid g = a.grids[b % a.n_grids];
-        if (tid == 0) {
-            s_hdr->degenerate = 0; s_qcount[0] = 0; s_qcount[1] = 0;
-            s_qcount[2] = csize > 1 ? b + nclusters
-                                    : (int)gridDim.x + atomicAdd(a.next_window, 1);      // this CTA's next window
-        }
+        if (tid == 0) { s_hdr->degenerate = 0; s_qcount[0] = 0; s_qcount[1] = 0; }
         if (a.grad && crank == 0) {      // P4 accumulates into these rows with L2 reductions
             double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
             for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
-            __threadfence();
+            if (csize > 1) __threadfence();      // the other CTAs of the cluster add to these rows too
         }
         __syncthreads();
+        // this CTA's next window: asked for now, needed after the tail (the round trip to L2 hides behind P1)
+        if (tid == 0) s_qcount[2] = csize > 1 ? b + nclusters : (int)gridDim.x + atomicAdd(a.next_window, 1);
         PrepOut po{s_pn, s_A, s_H, s_bbox, tb.tile, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
@@ -168,6 +166,7 @@ using namespace wfot;
 namespace wfot {
 static int g_dev_options[kOptCount] = {0};
 static int32_t* g_iray_capture = nullptr;
+static unsigned long long* g_phase_cycles = nullptr;
 int dev_option(int id) { return (id >= 0 && id < kOptCount) ? g_dev_options[id] : 0; }
 }  // namespace wfot
 
@@ -177,6 +176,7 @@ static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaS
     const int nt = a.nt, nug = a.nug, ntg = a.ntg, B = a.B;
     a.rlambda = 1.0 / a.lambda;
     a.dbg_iray = g_iray_capture;
+    a.dbg_phase = g_phase_cycles;
     a.Spad = seg_pad(nt); a.ntg_pad = pad4(ntg); a.nug_pad = pad4(nug);
     a.nmax = pad4(ntg > nug ? ntg : nug);
     a.L = make_layout(nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax);
@@ -262,6 +262,7 @@ int wfot_dev_set_option(int id, int value) {
 // occupancy call), plus - for batches that take the two-kernel form - 8 bytes per pixel per window
 // of one scan/resolve launch pair.
 void wfot_dev_capture_iray(int32_t* iray) { g_iray_capture = iray; }
+void wfot_dev_phase_cycles(unsigned long long* cycles) { g_phase_cycles = cycles; }
 
 int wfot_dev_epilogue_math(const double* x, double* exp_neg_out, double* rsqrt_out, int n, void* stream) {
     if (!x || !exp_neg_out || !rsqrt_out || n <= 0) return WFOT_ERR_INVALID_ARG;

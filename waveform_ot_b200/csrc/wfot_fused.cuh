@@ -99,6 +99,7 @@ struct FusedArgs {
     double* out_cdf_t; double* out_cdf_u; double* out_amp;
     // measurement aid (wfot_dev.h): nearest-segment index of every pixel of every window, (B, nug * ntg) int32
     int32_t* dbg_iray;
+    unsigned long long* dbg_phase;   // measurement aid (wfot_dev.h): per-phase cycle counters of k_resolve
     // per-CTA scratch slabs
     double* s_pdf; double* s_wa; double* s_wb; int32_t* s_idx;
     int32_t* status;
@@ -166,7 +167,7 @@ __device__ __forceinline__ void load_exp_table(double2* s_etab) {
 template <bool STORE_PDF = true>
 __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2* pn, const double2* etab, size_t slab,
                                               int it, int iu, const PixelHit& hit, double py, int& zero_dist,
-                                              int32_t* dbg_iray = nullptr) {
+                                              int32_t* dbg_iray = nullptr, bool live = true) {
     const double* const pny = reinterpret_cast<const double*>(pn) + 1;
     const double ay = pny[2 * hit.s], by = pny[2 * hit.s + 2];
     const double cy = __dsub_rn(by, ay);
@@ -182,7 +183,7 @@ __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2*
     } else {                                                   // pixel on the waveform: 0/0 as in the reference
         d = 0.0;
         g = num / d;
-        ++zero_dist;
+        zero_dist += live ? 1 : 0;
     }
     const double e = (a.q == 2) ? d * d : d;                   // exp(-d^2/lambda) (:174) or exp(-|d|/lambda) (:176)
     const double q0 = e * a.rlambda;
@@ -191,11 +192,18 @@ __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2*
     double wgt = pdf * g;                                      // pdf * dddx_y
     if (a.q == 2) wgt *= 2.0 * d;                              // :214-217
     const size_t k = slab + (size_t)iu * a.ntg + it;
-    if (STORE_PDF) a.s_pdf[k] = pdf;
-    a.s_wa[k] = (1.0 - hit.lam) * wgt;                         // -> sample iray    (:223)
-    a.s_wb[k] = hit.lam * wgt;                                 // -> sample iray+1  (:224)
-    a.s_idx[k] = hit.s;
-    if (dbg_iray) dbg_iray[(size_t)iu * a.ntg + it] = hit.s;
+    // weights of samples iray / iray + 1 (:223-224).  A pixel whose nearest point is the far vertex of its segment
+    // (lam = 1: all of its weight goes to sample iray + 1) is filed under the next segment with lam = 0 - the same
+    // contribution - so that the pixels around a vertex form one run for the gradient assembly (P4).
+    const bool far = hit.lam == 1.0 && hit.s + 2 < a.nt && (wgt - wgt == 0.0);   // finite weight: NaN goes where the reference puts it
+    const double wa = far ? wgt : (1.0 - hit.lam) * wgt, wb = far ? 0.0 : hit.lam * wgt;
+    if (live) {                        // a shadow lane (row tail) computes and stores nothing
+        if (STORE_PDF) a.s_pdf[k] = pdf;
+        a.s_wa[k] = wa;
+        a.s_wb[k] = wb;
+        a.s_idx[k] = hit.s + (far ? 1 : 0);
+        if (dbg_iray) dbg_iray[(size_t)iu * a.ntg + it] = hit.s;
+    }
     return pdf;
 }
 
@@ -209,7 +217,7 @@ __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2*
 // Returns the number of exact source/target CDF coincidences (libs/OTlib.py:663-666) in thread 0.
 template <int NT, bool HAVE_SUMS = false, int P4R = 4>
 __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* smem_raw, int b, size_t slab,
-                                           const WinHdr& hdr) {
+                                           const WinHdr& hdr, long long* t_p4 = nullptr) {
     WFOT_SMEM_POINTERS(a.L);
     (void)s_pn; (void)s_A; (void)s_H; (void)s_bbox; (void)s_keys; (void)s_pxs; (void)s_pys; (void)s_queue;
     (void)s_hdr; (void)s_qcount; (void)s_colpart; (void)s_etab;
@@ -301,6 +309,7 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
     }
 
     // ---------------- P4
+    if (t_p4) *t_p4 = clock64();
     if (a.grad) {
         // chain vectors: (R - <R, pbar>)/A  (OTlib.py:1144-1147)
         for (int c = tid; c < a.ntg; c += NT) s_Rt[c] = (s_Rt[c] - Gt) / A;
@@ -318,38 +327,65 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
         __syncthreads();
         double* const gt = a.grad + ((size_t)b * 2) * a.nt;
         double* const gu = gt + a.nt;
-        for (int c = tid; c < a.ntg; c += NT) {
+        // one L2 reduction per (sample, row of the gradient); nothing is sent for a sum of exact zeros (the weights of
+        // the 60-80 % of pixels whose nearest point is a vertex)
+        auto flush = [&](int j, double tv, double uv) {
+            if (tv != 0.0 || uv != 0.0) {
+                const double cj = s_gbins[j];
+                red_add(gt + j, tv * cj); red_add(gu + j, uv * cj);
+            }
+        };
+        // a thread walks a column; narrow grids are cut into row bands so that every warp has a column to walk
+        // (79 x 61 pixels: 4 bands of 20 rows x 64 lanes instead of 61 busy threads out of 256)
+        const int cpp = min(NT, (a.ntg + 31) & ~31), nbands = NT / cpp;
+        const int rows_band = (a.nug + nbands - 1) / nbands;
+        const int r_lo = min((tid / cpp) * rows_band, a.nug), r_hi = min(r_lo + rows_band, a.nug);
+        for (int c = tid % cpp; c < a.ntg && r_lo < r_hi; c += cpp) {
             const double ct = s_Rt[c];
-            int cur = -1;
+            // (t0, u0) / (t1, u1): running sums for samples cur / cur + 1.  When the nearest segment moves to a
+            // neighbouring one, the sums of the sample the two segments share are carried over instead of being sent.
+            int cur = -2;
             double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
-            for (int iu0 = 0; iu0 < a.nug; iu0 += P4R) {
-                int idx[P4R];
-                double wa[P4R], wb[P4R];
+            // the slab comes back from DRAM (the CTAs of a launch write far more than L2 holds): the rows of the next
+            // step are requested before the rows of this one are consumed, so a request is always in flight
+            int idx[P4R], nidx[P4R];
+            double wa[P4R], wb[P4R], nwa[P4R], nwb[P4R];
 #pragma unroll
-                for (int j = 0; j < P4R; ++j) {
-                    const size_t k = slab + (size_t)min(iu0 + j, a.nug - 1) * a.ntg + c;
-                    idx[j] = __ldcg(a.s_idx + k); wa[j] = __ldcg(a.s_wa + k); wb[j] = __ldcg(a.s_wb + k);
+            for (int j = 0; j < P4R; ++j) {
+                const size_t k = slab + (size_t)min(r_lo + j, r_hi - 1) * a.ntg + c;
+                nidx[j] = __ldcg(a.s_idx + k); nwa[j] = __ldcg(a.s_wa + k); nwb[j] = __ldcg(a.s_wb + k);
+            }
+            for (int iu0 = r_lo; iu0 < r_hi; iu0 += P4R) {
+#pragma unroll
+                for (int j = 0; j < P4R; ++j) { idx[j] = nidx[j]; wa[j] = nwa[j]; wb[j] = nwb[j]; }
+                if (iu0 + P4R < r_hi) {
+#pragma unroll
+                    for (int j = 0; j < P4R; ++j) {
+                        const size_t k = slab + (size_t)min(iu0 + P4R + j, r_hi - 1) * a.ntg + c;
+                        nidx[j] = __ldcg(a.s_idx + k); nwa[j] = __ldcg(a.s_wa + k); nwb[j] = __ldcg(a.s_wb + k);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < P4R; ++j) {
-                    if (iu0 + j >= a.nug) break;
+                    if (iu0 + j >= r_hi) break;
                     if (idx[j] != cur) {
-                        if (cur >= 0) {
-                            const double c0 = s_gbins[cur], c1 = s_gbins[cur + 1];
-                            atomicAdd(gt + cur, t0 * c0); atomicAdd(gt + cur + 1, t1 * c1);
-                            atomicAdd(gu + cur, u0 * c0); atomicAdd(gu + cur + 1, u1 * c1);
+                        if (idx[j] == cur + 1) {
+                            flush(cur, t0, u0);
+                            t0 = t1; u0 = u1; t1 = 0.0; u1 = 0.0;
+                        } else if (idx[j] == cur - 1) {
+                            flush(cur + 1, t1, u1);
+                            t1 = t0; u1 = u0; t0 = 0.0; u0 = 0.0;
+                        } else {
+                            if (cur >= 0) { flush(cur, t0, u0); flush(cur + 1, t1, u1); }
+                            t0 = t1 = u0 = u1 = 0.0;
                         }
-                        cur = idx[j]; t0 = t1 = u0 = u1 = 0.0;
+                        cur = idx[j];
                     }
                     const double cu = s_Ru[iu0 + j];
                     t0 += wa[j] * ct; t1 += wb[j] * ct; u0 += wa[j] * cu; u1 += wb[j] * cu;
                 }
             }
-            if (cur >= 0) {
-                const double c0 = s_gbins[cur], c1 = s_gbins[cur + 1];
-                atomicAdd(gt + cur, t0 * c0); atomicAdd(gt + cur + 1, t1 * c1);
-                atomicAdd(gu + cur, u0 * c0); atomicAdd(gu + cur + 1, u1 * c1);
-            }
+            if (cur >= 0) { flush(cur, t0, u0); flush(cur + 1, t1, u1); }
         }
     }
     return (tid == 0) ? (rt.common + ru.common) : 0;

@@ -44,11 +44,10 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
     for (int i = blockIdx.x; i < a.B;) {
         const int b = a.b0 + i;
         const wfot_grid g = a.grids[b % a.n_grids];
-        if (tid == 0) {
-            s_hdr->degenerate = 0; s_qcount[1] = 0;
-            s_qcount[2] = (int)gridDim.x + atomicAdd(a.next_window, 1);          // this CTA's next window
-        }
+        if (tid == 0) { s_hdr->degenerate = 0; s_qcount[1] = 0; }
         __syncthreads();
+        // this CTA's next window: asked for now, needed after the scan (the round trip to L2 hides behind it)
+        if (tid == 0) s_qcount[2] = (int)gridDim.x + atomicAdd(a.next_window, 1);
         PrepOut po{s_pn, s_A, s_H, s_bbox, tb.tile, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
@@ -112,10 +111,10 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
 // register, the row-group column sums (kRowGroups = 8 = warps) in shared memory - so the density itself is never
 // stored or re-read.  A pixel whose near-ties span distant tiles (a handful per window) is resolved in place by
 // the whole warp.
-template <int MINB, int T>
-__global__ void __launch_bounds__(256, MINB) k_resolve(FusedArgs a) {
-    constexpr int NT = 256;
-    static_assert(NT == 32 * kRowGroups, "one warp per row group");
+template <int MINB, int T, int PX, int NT = 256>
+__global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
+    constexpr int NW = NT / 32;
+    static_assert(kRowGroups % NW == 0, "a row group (row mod kRowGroups) belongs to one warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     (void)s_bbox; (void)s_keys; (void)s_Rt; (void)s_Ru; (void)s_cf; (void)s_E; (void)s_queue;
@@ -126,22 +125,22 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(FusedArgs a) {
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T};
     int zero_dist = 0, slow = 0, common = 0;
     int* const counter = a.next_window + 16;
-    double* const colp = s_colpart + warp * a.ntg_pad;
     load_exp_table(s_etab);      // visible behind the first barrier of the window loop
+    long long ph[5] = {0, 0, 0, 0, 0};
+    const bool timed = a.dbg_phase != nullptr && tid == 0;
     for (int i = blockIdx.x; i < a.B;) {
         const int b = a.b0 + i;
         const wfot_grid g = a.grids[b % a.n_grids];
-        if (tid == 0) {
-            s_hdr->degenerate = 0;
-            s_qcount[2] = (int)gridDim.x + atomicAdd(counter, 1);
-        }
-        if (a.grad) {      // P4 accumulates into these rows with L2 reductions
+        const long long tk0 = timed ? clock64() : 0;
+        if (tid == 0) s_hdr->degenerate = 0;
+        if (a.grad) {      // P4 accumulates into these rows with L2 reductions (ordered behind these stores by the barriers in between)
             double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
             for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
-            __threadfence();
         }
-        for (int c = lane; c < a.ntg; c += 32) colp[c] = 0.0;
+        for (int c = tid; c < kRowGroups * a.ntg_pad; c += NT) s_colpart[c] = 0.0;
         __syncthreads();
+        // this CTA's next window: asked for now, needed after the tail (the round trip to L2 hides behind P1)
+        if (tid == 0) s_qcount[2] = (int)gridDim.x + atomicAdd(counter, 1);
         PrepOut po{s_pn, s_A, s_H, nullptr, tb.tile, s_pxs, s_pys, s_hdr};
         prep_window(a.t, a.w, a.dtype, (long long)b * a.t_stride, (long long)b * a.nt, a.nt, g,
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
@@ -152,42 +151,78 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(FusedArgs a) {
         __syncthreads();
 
         // ---------------- P1 + P2 sums
+        const long long tk1 = timed ? clock64() : 0;
         const uint2* const in = a.scan_out + (size_t)i * npix;
         int32_t* const dbg = a.dbg_iray ? a.dbg_iray + (size_t)b * npix : nullptr;
+        uint2 nxt[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p)
+            nxt[p] = (warp < a.nug && 32 * p + lane < a.ntg) ? __ldcs(in + (size_t)warp * a.ntg + 32 * p + lane)
+                                                             : make_uint2(0u, 0u);
 #pragma unroll 1
-        for (int iu = warp; iu < a.nug; iu += kRowGroups) {
+        for (int iu = warp; iu < a.nug; iu += NW) {
             const uint2* const inrow = in + (size_t)iu * a.ntg;
+            double* const colp = s_colpart + (iu & (kRowGroups - 1)) * a.ntg_pad;
             const double pyd = s_xu[iu];
             const float pyl = s_pys[iu];
             double rowacc = 0.0;
-            uint2 nxt = (lane < a.ntg) ? __ldcs(inrow + lane) : make_uint2(0u, 0u);
 #pragma unroll 1
-            for (int c0 = 0; c0 < a.ntg; c0 += 32) {
-                const int it = min(c0 + lane, a.ntg - 1);             // lanes past the row end shadow its last pixel
-                const bool live = c0 + lane < a.ntg;
-                const uint2 v = nxt;
-                if (c0 + 32 + lane < a.ntg) nxt = __ldcs(inrow + c0 + 32 + lane);
-                const float kb1 = __uint_as_float(v.x);
-                const float thr = kb1 + tau32(kb1);
-                const float pxl = s_pxs[it];
-                const double pxd = s_xt[it];
-                PixelHit hit;
-                const bool done = resolve_pixel_flagged<T>(tb, s_pn, pxl, pyl, pxd, pyd, thr,
-                                                           (int)(v.y & kScanTileMask), (v.y & kScanFlag2) != 0u,
-                                                           (v.y & kScanFlag3) != 0u, hit);
-                unsigned amb = __ballot_sync(0xffffffffu, live && !done);
-                while (amb) {                                         // rare: all-segment rescan by the whole warp
-                    const int src = __ffs((int)amb) - 1;
-                    amb &= amb - 1u;
-                    PixelHit h2;
-                    resolve_pixel_warp(tb, s_pn, __shfl_sync(0xffffffffu, pxl, src), pyl,
-                                       __shfl_sync(0xffffffffu, pxd, src), pyd, __shfl_sync(0xffffffffu, kb1, src), h2);
-                    if (lane == src) { hit = h2; ++slow; }
+            for (int c0 = 0; c0 < a.ntg; c0 += 32 * PX) {
+                int it[PX];
+                bool live[PX], done[PX];
+                uint2 v[PX];
+                float kb1[PX], thr[PX], pxl[PX];
+                double pxd[PX];
+                PixelHit hit[PX];
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    const int c = c0 + 32 * p + lane;
+                    it[p] = min(c, a.ntg - 1);                        // lanes past the row end shadow its last pixel
+                    live[p] = c < a.ntg;
+                    v[p] = nxt[p];
+                    // next chunk of this row, or the first chunk of the warp's next row (its latency would otherwise
+                    // be exposed once per row)
+                    const bool last = c0 + 32 * PX >= a.ntg;
+                    const int cn = last ? 32 * p + lane : c + 32 * PX;
+                    const uint2* const rn = last ? inrow + (size_t)NW * a.ntg : inrow;
+                    if (cn < a.ntg && (!last || iu + NW < a.nug)) nxt[p] = __ldcs(rn + cn);
+                    kb1[p] = __uint_as_float(v[p].x);
+                    thr[p] = kb1[p] + tau32(kb1[p]);
+                    pxl[p] = s_pxs[it[p]];
+                    pxd[p] = s_xt[it[p]];
                 }
-                if (live) {
-                    const double pdf = store_pixel<false>(a, s_pn, s_etab, slab, it, iu, hit, pyd, zero_dist, dbg);
-                    rowacc += pdf;                                    // columns lane, lane + 32, ... in ascending order
-                    colp[it] += pdf;                                  // rows warp, warp + 8, ... in ascending order
+                if constexpr (PX == 1) {
+                    done[0] = resolve_pixel_flagged<T>(tb, s_pn, pxl[0], pyl, pxd[0], pyd, thr[0],
+                                                       (int)(v[0].y & kScanTileMask), (v[0].y & kScanFlag2) != 0u,
+                                                       (v[0].y & kScanFlag3) != 0u, hit[0]);
+                } else {
+                    const unsigned code[2] = {v[0].y, v[1].y};
+                    resolve_pixels2<T>(tb, s_pn, pxl, pyl, pxd, pyd, thr, code, kScanTileMask, kScanFlag2, kScanFlag3,
+                                       hit, done);
+                }
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    unsigned amb = __ballot_sync(0xffffffffu, live[p] && !done[p]);
+                    while (amb) {                                     // rare: all-segment rescan by the whole warp
+                        const int src = __ffs((int)amb) - 1;
+                        amb &= amb - 1u;
+                        PixelHit h2;
+                        resolve_pixel_warp(tb, s_pn, __shfl_sync(0xffffffffu, pxl[p], src), pyl,
+                                           __shfl_sync(0xffffffffu, pxd[p], src), pyd,
+                                           __shfl_sync(0xffffffffu, kb1[p], src), h2);
+                        if (lane == src) { hit[p] = h2; ++slow; }
+                    }
+                }
+                double pdf[PX];
+#pragma unroll
+                for (int p = 0; p < PX; ++p)
+                    pdf[p] = store_pixel<false>(a, s_pn, s_etab, slab, it[p], iu, hit[p], pyd, zero_dist, dbg, live[p]);
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    if (live[p]) {
+                        rowacc += pdf[p];                             // columns lane, lane + 32, ... in ascending order
+                        colp[it[p]] += pdf[p];                        // rows of one group (row mod 8) in ascending order
+                    }
                 }
             }
 #pragma unroll
@@ -195,15 +230,23 @@ __global__ void __launch_bounds__(256, MINB) k_resolve(FusedArgs a) {
             if (lane == 0) s_margu[iu] = rowacc;
         }
         __syncthreads();   // sums and scratch slab complete (block-scope visibility of global writes)
-        common += window_tail<NT, true, (MINB == 2 ? 8 : 4)>(a, smem_raw, b, slab, hdr);
+        long long tk3 = 0;
+        const long long tk2 = timed ? clock64() : 0;
+        common += window_tail<NT, true, (MINB == 2 ? 8 : 4)>(a, smem_raw, b, slab, hdr, timed ? &tk3 : nullptr);
         i = s_qcount[2];
         __syncthreads();
+        if (timed) {
+            const long long tk4 = clock64();
+            ph[0] += tk1 - tk0; ph[1] += tk2 - tk1; ph[2] += tk3 - tk2; ph[3] += tk4 - tk3; ph[4] += 1;
+        }
     }
     if (a.status) {
         if (zero_dist) atomicAdd(a.status + WFOT_STAT_ZERO_DIST, zero_dist);
         if (slow) atomicAdd(a.status + WFOT_STAT_SLOW_PIXELS, slow);
         if (common) atomicAdd(a.status + WFOT_STAT_COMMON_CDF, common);
     }
+    if (timed)
+        for (int k = 0; k < 5; ++k) atomicAdd(a.dbg_phase + k, (unsigned long long)ph[k]);
 }
 
 // ------------------------------------------------------------------ host side
@@ -295,9 +338,13 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
     // resolve kernel: 128 registers x 2 CTAs per SM for long windows (deeper unrolled gradient assembly: its slab
     // read-back is the latency sink of the kernel), 80 registers x 3 per SM for short ones
     int rshape = dev_option(kOptResolveShape);
-    if (rshape != 1 && rshape != 2) rshape = smem_r > 48 * 1024 ? 1 : 2;
-    const int res_ctas = rshape == 1 ? resident_ctas(k_resolve<2, T>, smem_r, &per_sm, 256)
-                                     : resident_ctas(k_resolve<3, T>, smem_r, &per_sm, 256);
+    if (rshape < 1 || rshape > 5) rshape = smem_r > 48 * 1024 ? 1 : 2;
+    const int rthreads = rshape == 5 ? 128 : 256;
+    const int res_ctas = rshape == 1 ? resident_ctas(k_resolve<2, T, 1>, smem_r, &per_sm, 256)
+                       : rshape == 2 ? resident_ctas(k_resolve<3, T, 1>, smem_r, &per_sm, 256)
+                       : rshape == 3 ? resident_ctas(k_resolve<2, T, 2>, smem_r, &per_sm, 256)
+                       : rshape == 4 ? resident_ctas(k_resolve<3, T, 2>, smem_r, &per_sm, 256)
+                                     : resident_ctas(k_resolve<6, T, 1, 128>, smem_r, &per_sm, 128);
     if (res_ctas < 1) return cuda_fail(cudaGetLastError(), "k_resolve occupancy");
     const size_t slab_px = 20;                         // bytes per pixel of the per-CTA scratch slab
     const int Btot = a.B;
@@ -330,7 +377,9 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
         ar.next_window = counters + 2 * c + 1 - 16;  // k_resolve counts at next_window + 16
         if (lane && c >= nbuf && cudaStreamWaitEvent(stream, lane->resolved[buf], 0) != cudaSuccess)
             return cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent");
-        if (scan3) k_scan<4, T, 3><<<scan_ctas < nb ? scan_ctas : nb, 256, smem_s, stream>>>(as);
+        const int skip = dev_option(kOptSkipKernel);
+        if (skip == 2) {}
+        else if (scan3) k_scan<4, T, 3><<<scan_ctas < nb ? scan_ctas : nb, 256, smem_s, stream>>>(as);
         else k_scan<4, T, 2><<<scan_ctas < nb ? scan_ctas : nb, 256, smem_s, stream>>>(as);
         if (lane) {
             if (cudaEventRecord(lane->scanned[buf], stream) != cudaSuccess ||
@@ -338,8 +387,12 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
                 return cuda_fail(cudaGetLastError(), "cudaEventRecord");
         }
         const int rc = res_grid < nb ? res_grid : nb;
-        if (rshape == 1) k_resolve<2, T><<<rc, 256, smem_r, rstream>>>(ar);
-        else k_resolve<3, T><<<rc, 256, smem_r, rstream>>>(ar);
+        if (skip == 1) {}
+        else if (rshape == 1) k_resolve<2, T, 1><<<rc, 256, smem_r, rstream>>>(ar);
+        else if (rshape == 2) k_resolve<3, T, 1><<<rc, 256, smem_r, rstream>>>(ar);
+        else if (rshape == 3) k_resolve<2, T, 2><<<rc, 256, smem_r, rstream>>>(ar);
+        else if (rshape == 4) k_resolve<3, T, 2><<<rc, 256, smem_r, rstream>>>(ar);
+        else k_resolve<6, T, 1, 128><<<rc, rthreads, smem_r, rstream>>>(ar);
         note_launches(2);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "wfot_misfit_grad_batch (scan + resolve) launch");
