@@ -54,13 +54,11 @@ opt(C.OPT_PIPELINE, 1)
 ms0, r0, st0 = run()
 print("%s B=%d  single-kernel: %.3f ms  %.1f evals/s  status %s" % (name, nb, ms0, nb / ms0 * 1e3, st0[:5].tolist()), flush=True)
 W0, G0, D0 = r0["W"].clone(), r0["grad"].clone(), r0["dwg"].clone()
-# (label, overlap[0 two streams / 1 sequential], resolve shape [0 auto, 1: 128 regs x2/SM, 2: 80 regs x3/SM, 3 / 4: the same with 2 pixels per lane], chunk, scan shape [0: 80 regs x3, 2: 128 x2])
+# (label, overlap[0 two streams / 1 sequential], resolve shape [0 auto, 1: 128 regs x2/SM, 2: 80 regs x3/SM, 5: 128 threads x6/SM], chunk, scan shape [0: 80 regs x3, 2: 128 x2])
 VARIANTS = [("two-kernel default", 0, 0, 0, 0),
             ("two-kernel, resolve 128 regs x2", 0, 1, 0, 0),
             ("two-kernel, resolve 80 regs x3", 0, 2, 0, 0),
             ("two-kernel, scan 128 regs x2", 0, 0, 0, 2),
-            ("two-kernel, resolve 128 regs x2, 2 pixels/lane", 0, 3, 0, 0),
-            ("two-kernel, resolve 80 regs x3, 2 pixels/lane", 0, 4, 0, 0),
             ("two-kernel, resolve 128 threads x6", 0, 5, 0, 0),
             ("two-kernel sequential one chunk", 1, 0, nb, 0),
             ("two-kernel chunk 32/SM", 0, 0, 4736, 0)]

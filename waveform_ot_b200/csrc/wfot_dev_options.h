@@ -6,7 +6,7 @@ namespace wfot {
 
 enum DevOption {
     kOptPipeline = 0,      // fused path: 0 auto, 1 single-kernel form, 2 two-kernel (scan + resolve) form
-    kOptResolveShape = 1,  // k_resolve: 0 auto, 1 = 128 registers x 2 CTAs/SM, 2 = 80 registers x 3 CTAs/SM (one pixel per lane), 3 / 4 = the same with two pixels per lane
+    kOptResolveShape = 1,  // k_resolve: 0 auto, 1 = 128 registers x 2 CTAs/SM, 2 = 80 registers x 3 CTAs/SM, 5 = 128 threads, 6 CTAs/SM
     kOptFusedThreads = 2,  // k_misfit_grad threads per CTA: 0 auto, 64 / 128 / 256
     kOptClusterMax = 3,    // largest thread-block cluster per window: 0 auto (8), 1 = no clusters
     kOptTile = 4,          // argmin tile: 0 auto, 8 or 16 segments

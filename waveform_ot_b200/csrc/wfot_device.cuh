@@ -183,13 +183,12 @@ struct PixelHit {
 // FP32 re-evaluation of the T segments of one tile for one pixel: bit j set <=> D32(segment) <= thr.
 // Padding segments evaluate to kPadD > thr, so no bounds check is needed.
 template <int T>
-__device__ __forceinline__ unsigned tile_mask(const SegTable& tb, int tile, float px, float py, float thr) {
+__device__ __forceinline__ void tile_dists(const SegTable& tb, int tile, float px, float py, float (&d)[T]) {
     WFOT_ASSUME_SHARED(tb.A); WFOT_ASSUME_SHARED(tb.H);
     const float4* __restrict__ E = tb.A + tile * (T / 2);
     const float4* __restrict__ M = E + (tb.Spad >> 1);
     const float2* __restrict__ H2 = reinterpret_cast<const float2*>(tb.H + tile * T);
     const uint64_t px2 = pack2(px, px), py2 = pack2(py, py);
-    unsigned mask = 0u;
 #pragma unroll
     for (int p = 0; p < T / 2; ++p) {            // two segments per step, the same FP32 operations as the scan
         const float4 e = E[p], m = M[p];
@@ -197,15 +196,27 @@ __device__ __forceinline__ unsigned tile_mask(const SegTable& tb, int tile, floa
         const uint64_t ex2 = pack2(e.x, e.y), ey2 = pack2(e.z, e.w), nex2 = pack2(-e.x, -e.y);
         const uint64_t P = ffma2(px2, ex2, pack2(m.x, m.y));
         const uint64_t Q = ffma2(px2, ey2, pack2(m.z, m.w));
-        float al0, al1, d0, d1;
+        float al0, al1;
         unpack2(ffma2(py2, ey2, P), al0, al1);
         const uint64_t pe = ffma2(py2, nex2, Q);
         const uint64_t tm = pack2(__saturatef(__fadd_rn(fabsf(al0), -h.x)), __saturatef(__fadd_rn(fabsf(al1), -h.y)));
-        unpack2(ffma2(tm, tm, fmul2(pe, pe)), d0, d1);
-        mask |= (d0 <= thr) ? (1u << (2 * p)) : 0u;
-        mask |= (d1 <= thr) ? (2u << (2 * p)) : 0u;
+        unpack2(ffma2(tm, tm, fmul2(pe, pe)), d[2 * p], d[2 * p + 1]);
     }
+}
+
+template <int T>
+__device__ __forceinline__ unsigned dists_mask(const float (&d)[T], float thr) {
+    unsigned mask = 0u;
+#pragma unroll
+    for (int j = 0; j < T; ++j) mask |= (d[j] <= thr) ? (1u << j) : 0u;
     return mask;
+}
+
+template <int T>
+__device__ __forceinline__ unsigned tile_mask(const SegTable& tb, int tile, float px, float py, float thr) {
+    float d[T];
+    tile_dists<T>(tb, tile, px, py, d);
+    return dists_mask<T>(d, thr);
 }
 
 // FP64 reference-order evaluation of the candidate segments of one tile, ascending (strict '<'
@@ -247,77 +258,34 @@ __device__ __forceinline__ bool resolve_pixel_flagged(const SegTable& tb, const 
     return true;
 }
 
-// Two pixels of one thread at a time (the resolve kernel): the FP32 re-evaluations and the FP64 reference-order
-// evaluations of the two pixels are written as straight-line code side by side, so that the two dependency chains
-// fill each other's latency slots (one pixel per thread leaves the warp waiting on its own previous instruction
-// most of the time).  Same candidate sets, same evaluation order per pixel, hence the same results as
-// resolve_pixel_flagged(); pixels whose candidates span several tiles take that function's path one by one.
-__device__ __forceinline__ void eval64x2(const double2* __restrict__ pn, const int (&s)[2], const double (&px)[2],
-                                         double py, double (&D)[2], double (&lam)[2]) {
-    double cx[2], cy[2], L[2], bx[2], by[2], num[2], l[2];
-    bool inside = false;
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const double2 a = pn[s[p]];
-        const double2 b = pn[s[p] + 1];
-        cx[p] = __dsub_rn(b.x, a.x);
-        cy[p] = __dsub_rn(b.y, a.y);
-        L[p] = __dadd_rn(__dmul_rn(cx[p], cx[p]), __dmul_rn(cy[p], cy[p]));
-        bx[p] = __dsub_rn(px[p], a.x);
-        by[p] = __dsub_rn(py, a.y);
-        num[p] = __dadd_rn(__dmul_rn(bx[p], cx[p]), __dmul_rn(by[p], cy[p]));
-        l[p] = (num[p] <= 0.0) ? 0.0 : 1.0;
-        inside |= (num[p] > 0.0 && num[p] < L[p]);
-    }
-    if (inside) {      // see eval64(): outside (0, L) the clip decides whatever the quotient rounds to
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const double q = fmin(fmax(__ddiv_rn(num[p], L[p]), 0.0), 1.0);
-            l[p] = (num[p] > 0.0 && num[p] < L[p]) ? q : l[p];
-        }
-    }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const double dx = __dsub_rn(bx[p], __dmul_rn(cx[p], l[p]));
-        const double dy = __dsub_rn(by[p], __dmul_rn(cy[p], l[p]));
-        D[p] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        lam[p] = l[p];
-    }
-}
-
-// code[p] = the scan's second word (tile | flags); done[p] = false -> the caller runs the all-segment rescan.
+// The same from the scan's 4-byte result (tile | flags) alone: the FP32 minimum b1 is the smallest of the winning
+// tile's distances, which the re-evaluation produces anyway (same operations as the scan: the same bits).
 template <int T>
-__device__ __forceinline__ void resolve_pixels2(const SegTable& tb, const double2* __restrict__ pn,
-                                                const float (&pxl)[2], float pyl, const double (&px)[2], double py,
-                                                const float (&thr)[2], const unsigned (&code)[2],
-                                                unsigned tilemask, unsigned flag2, unsigned flag3,
-                                                PixelHit (&hit)[2], bool (&done)[2]) {
-    unsigned m[2];
-    int t1[2];
+__device__ __forceinline__ bool resolve_pixel_coded(const SegTable& tb, const double2* __restrict__ pn,
+                                                    float pxl, float pyl, double px, double py,
+                                                    int t1, bool other, bool many, PixelHit& hit, float& b1) {
+    float d[T];
+    tile_dists<T>(tb, t1, pxl, pyl, d);
+    float mn = d[0];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        t1[p] = (int)(code[p] & tilemask);
-        hit[p].D = CUDART_INF; hit[p].lam = 0.0; hit[p].s = t1[p] * T;
-        m[p] = tile_mask<T>(tb, t1[p], pxl[p], pyl, thr[p]);
-        done[p] = true;
+    for (int j = 1; j < T; ++j) mn = fminf(mn, d[j]);
+    b1 = mn;
+    const float thr = mn + tau32(mn);
+    const unsigned m1 = dists_mask<T>(d, thr);
+    hit.D = CUDART_INF; hit.lam = 0.0; hit.s = t1 * T;
+    if (!other) {                                     // the common case: one tile
+        eval_candidates<T>(pn, t1, m1, px, py, hit);
+        return true;
     }
-    unsigned m0 = (code[0] & flag2) ? 0u : m[0], m1 = (code[1] & flag2) ? 0u : m[1];
-    while (m0 | m1) {
-        // an exhausted pixel re-evaluates its current segment: D < hit.D is false, nothing changes
-        const int j0 = m0 ? t1[0] * T + __ffs((int)m0) - 1 : hit[0].s;
-        const int j1 = m1 ? t1[1] * T + __ffs((int)m1) - 1 : hit[1].s;
-        m0 &= m0 - 1u; m1 &= m1 - 1u;
-        const int s[2] = {j0, j1};
-        double D[2], l[2];
-        eval64x2(pn, s, px, py, D, l);
-        if (D[0] < hit[0].D) { hit[0].D = D[0]; hit[0].lam = l[0]; hit[0].s = j0; }
-        if (D[1] < hit[1].D) { hit[1].D = D[1]; hit[1].lam = l[1]; hit[1].s = j1; }
-    }
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-        if (code[p] & flag2)
-            done[p] = resolve_pixel_flagged<T>(tb, pn, pxl[p], pyl, px[p], py, thr[p], t1[p], true,
-                                               (code[p] & flag3) != 0u, hit[p]);
+    if (many) return false;
+    const int ntiles = tb.Spad / T;
+    const unsigned m0 = (t1 > 0) ? tile_mask<T>(tb, t1 - 1, pxl, pyl, thr) : 0u;
+    const unsigned m2 = (t1 + 1 < ntiles) ? tile_mask<T>(tb, t1 + 1, pxl, pyl, thr) : 0u;
+    if ((m0 | m2) == 0u) return false;
+    if (m0) eval_candidates<T>(pn, t1 - 1, m0, px, py, hit);
+    eval_candidates<T>(pn, t1, m1, px, py, hit);
+    if (m2) eval_candidates<T>(pn, t1 + 1, m2, px, py, hit);
+    return true;
 }
 
 template <int T>

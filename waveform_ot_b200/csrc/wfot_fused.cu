@@ -54,11 +54,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_misfit_grad(FusedArgs a) {
         // ---------------- P0: window -> shared memory
         const wfot_grid g = a.grids[b % a.n_grids];
         if (tid == 0) { s_hdr->degenerate = 0; s_qcount[0] = 0; s_qcount[1] = 0; }
-        if (a.grad && crank == 0) {      // P4 accumulates into these rows with L2 reductions
-            double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
-            for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
-            if (csize > 1) __threadfence();      // the other CTAs of the cluster add to these rows too
-        }
         __syncthreads();
         // this CTA's next window: asked for now, needed after the tail (the round trip to L2 hides behind P1)
         if (tid == 0) s_qcount[2] = csize > 1 ? b + nclusters : (int)gridDim.x + atomicAdd(a.next_window, 1);
@@ -218,7 +213,7 @@ static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaS
     if (csize > 1) ctas = B * csize;
     else if (ctas > B) ctas = B;
     const size_t npix = (size_t)nug * ntg;
-    const size_t max_ctas = avail / (npix * 28);
+    const size_t max_ctas = avail / (npix * 24);
     if (max_ctas < 1) return WFOT_ERR_WORKSPACE;
     if (csize == 1 && (size_t)ctas > max_ctas) ctas = (int)max_ctas;
     if (csize > 1 && (size_t)(ctas / csize) > max_ctas) return WFOT_ERR_WORKSPACE;   // one slab per cluster
@@ -226,8 +221,7 @@ static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaS
     const size_t nslab = csize > 1 ? (size_t)(ctas / csize) : (size_t)ctas;
     a.s_pdf = (double*)p;   p += nslab * npix * 8;
     a.s_wa = (double*)p;    p += nslab * npix * 8;
-    a.s_wb = (double*)p;    p += nslab * npix * 8;
-    a.s_idx = (int32_t*)p;
+    a.s_wbi = (unsigned long long*)p;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];

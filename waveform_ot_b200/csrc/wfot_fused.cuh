@@ -101,14 +101,15 @@ struct FusedArgs {
     int32_t* dbg_iray;
     unsigned long long* dbg_phase;   // measurement aid (wfot_dev.h): per-phase cycle counters of k_resolve
     // per-CTA scratch slabs
-    double* s_pdf; double* s_wa; double* s_wb; int32_t* s_idx;
+    // s_wbi: weight of sample idx + 1 with idx in its 16 lowest mantissa bits (pack_wbi)
+    double* s_pdf; double* s_wa; unsigned long long* s_wbi;
     int32_t* status;
     int* next_window;     // global work counters (zeroed by the launcher): [0] fused / scan, [16] resolve
     int cluster;          // > 1: launched as thread-block clusters of this many CTAs, one window per CLUSTER
-    // split form: windows b0 .. b0 + B - 1 of the call; per-pixel scan results {b1 bits, tile | flags} of window
+    // split form: windows b0 .. b0 + B - 1 of the call; per-pixel scan results (tile | flags, 4 bytes) of window
     // b0 + i at scan_out[i * npix ...]
     int b0;
-    uint2* scan_out;
+    uint32_t* scan_out;
     int Spad, ntg_pad, nug_pad, nmax;
     SmemLayout L;
 };
@@ -164,6 +165,19 @@ __device__ __forceinline__ void load_exp_table(double2* s_etab) {
     for (int i = threadIdx.x; i < 128; i += blockDim.x) reinterpret_cast<double*>(s_etab)[i] = kExp2Tab[i];
 }
 
+// Slab entry of a pixel: 16 bytes.  wa (weight of sample idx) as a double; wb (weight of sample idx + 1) rounded to
+// a 36-bit mantissa (relative error 2^-37: the gradient keeps ~11 digits) with idx in the 16 bits that frees.
+// Every byte of the slab crosses DRAM twice (the CTAs of a launch write far more than L2 holds) and the resolve
+// kernel's gradient phase runs at the speed of that read-back.
+__device__ __forceinline__ unsigned long long pack_wbi(double wb, int idx) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(wb) + 0x8000ull;    // round to nearest
+    return (u & ~0xffffull) | (unsigned long long)(unsigned)idx;
+}
+__device__ __forceinline__ void unpack_wbi(unsigned long long u, double& wb, int& idx) {
+    idx = (int)(u & 0xffffull);
+    wb = __longlong_as_double((long long)(u & ~0xffffull));
+}
+
 template <bool STORE_PDF = true>
 __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2* pn, const double2* etab, size_t slab,
                                               int it, int iu, const PixelHit& hit, double py, int& zero_dist,
@@ -200,8 +214,7 @@ __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2*
     if (live) {                        // a shadow lane (row tail) computes and stores nothing
         if (STORE_PDF) a.s_pdf[k] = pdf;
         a.s_wa[k] = wa;
-        a.s_wb[k] = wb;
-        a.s_idx[k] = hit.s + (far ? 1 : 0);
+        a.s_wbi[k] = pack_wbi(wb, hit.s + (far ? 1 : 0));
         if (dbg_iray) dbg_iray[(size_t)iu * a.ntg + it] = hit.s;
     }
     return pdf;
@@ -312,6 +325,12 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
     if (t_p4) *t_p4 = clock64();
     if (a.grad) {
         // chain vectors: (R - <R, pbar>)/A  (OTlib.py:1144-1147)
+        // the window's gradient rows are zeroed here, not at the start of the window: the L2 reductions below then
+        // find their lines in L2 (a window's worth of slab traffic would have evicted them in between)
+        {
+            double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
+            for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
+        }
         for (int c = tid; c < a.ntg; c += NT) s_Rt[c] = (s_Rt[c] - Gt) / A;
         for (int c = tid; c < a.nug; c += NT) s_Ru[c] = (s_Ru[c] - Gu) / A;
         const double scale = -1.0 / (a.lambda * hdr.du);             // FingerprintLib.py:228,376-378
@@ -346,25 +365,17 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
             // neighbouring one, the sums of the sample the two segments share are carried over instead of being sent.
             int cur = -2;
             double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
-            // the slab comes back from DRAM (the CTAs of a launch write far more than L2 holds): the rows of the next
-            // step are requested before the rows of this one are consumed, so a request is always in flight
-            int idx[P4R], nidx[P4R];
-            double wa[P4R], wb[P4R], nwa[P4R], nwb[P4R];
-#pragma unroll
-            for (int j = 0; j < P4R; ++j) {
-                const size_t k = slab + (size_t)min(r_lo + j, r_hi - 1) * a.ntg + c;
-                nidx[j] = __ldcg(a.s_idx + k); nwa[j] = __ldcg(a.s_wa + k); nwb[j] = __ldcg(a.s_wb + k);
-            }
             for (int iu0 = r_lo; iu0 < r_hi; iu0 += P4R) {
+                int idx[P4R];
+                double wa[P4R], wb[P4R];
+                unsigned long long wbi[P4R];
 #pragma unroll
-                for (int j = 0; j < P4R; ++j) { idx[j] = nidx[j]; wa[j] = nwa[j]; wb[j] = nwb[j]; }
-                if (iu0 + P4R < r_hi) {
-#pragma unroll
-                    for (int j = 0; j < P4R; ++j) {
-                        const size_t k = slab + (size_t)min(iu0 + P4R + j, r_hi - 1) * a.ntg + c;
-                        nidx[j] = __ldcg(a.s_idx + k); nwa[j] = __ldcg(a.s_wa + k); nwb[j] = __ldcg(a.s_wb + k);
-                    }
+                for (int j = 0; j < P4R; ++j) {      // P4R rows in flight (the slab comes back from DRAM)
+                    const size_t k = slab + (size_t)min(iu0 + j, r_hi - 1) * a.ntg + c;
+                    wa[j] = __ldcg(a.s_wa + k); wbi[j] = __ldcg(a.s_wbi + k);
                 }
+#pragma unroll
+                for (int j = 0; j < P4R; ++j) unpack_wbi(wbi[j], wb[j], idx[j]);
 #pragma unroll
                 for (int j = 0; j < P4R; ++j) {
                     if (iu0 + j >= r_hi) break;

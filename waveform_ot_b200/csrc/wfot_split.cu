@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T};
     int degen = 0, tiles = 0;
-    const bool vec = (a.ntg & 1) == 0;      // both pixels of a column pair exist and their 16 bytes are aligned
+    const bool vec = (a.ntg & 1) == 0;      // both pixels of a column pair exist and their 8 bytes are aligned
     for (int i = blockIdx.x; i < a.B;) {
         const int b = a.b0 + i;
         const wfot_grid g = a.grids[b % a.n_grids];
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
         __syncthreads();
         degen += (tid == 0) ? s_hdr->degenerate : 0;
-        uint2* const out = a.scan_out + (size_t)i * npix;
+        uint32_t* const out = a.scan_out + (size_t)i * npix;
         const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(s_pxs[a.ntg - 1] - s_pxs[0]),
                                            fabsf(s_pys[a.nug - 1] - s_pys[0]));
         for (;;) {
@@ -82,13 +82,12 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
             for (int r = 0; r < R; ++r) {
                 const int iu = rg * R + r;
                 if (iu >= a.nug) break;
-                uint2* const dst = out + (size_t)iu * a.ntg + it0;
+                uint32_t* const dst = out + (size_t)iu * a.ntg + it0;
                 if (vec) {
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(__float_as_uint(b1[2 * r]), code[2 * r],
-                                                                __float_as_uint(b1[2 * r + 1]), code[2 * r + 1]);
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(code[2 * r], code[2 * r + 1]);
                 } else {
-                    dst[0] = make_uint2(__float_as_uint(b1[2 * r]), code[2 * r]);
-                    if (it0 + 1 < a.ntg) dst[1] = make_uint2(__float_as_uint(b1[2 * r + 1]), code[2 * r + 1]);
+                    dst[0] = code[2 * r];
+                    if (it0 + 1 < a.ntg) dst[1] = code[2 * r + 1];
                 }
             }
         }
@@ -111,7 +110,7 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
 // register, the row-group column sums (kRowGroups = 8 = warps) in shared memory - so the density itself is never
 // stored or re-read.  A pixel whose near-ties span distant tiles (a handful per window) is resolved in place by
 // the whole warp.
-template <int MINB, int T, int PX, int NT = 256>
+template <int MINB, int T, int NT = 256>
 __global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
     constexpr int NW = NT / 32;
     static_assert(kRowGroups % NW == 0, "a row group (row mod kRowGroups) belongs to one warp");
@@ -133,10 +132,6 @@ __global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
         const wfot_grid g = a.grids[b % a.n_grids];
         const long long tk0 = timed ? clock64() : 0;
         if (tid == 0) s_hdr->degenerate = 0;
-        if (a.grad) {      // P4 accumulates into these rows with L2 reductions (ordered behind these stores by the barriers in between)
-            double* const g0 = a.grad + ((size_t)b * 2) * a.nt;
-            for (int j = tid; j < 2 * a.nt; j += NT) g0[j] = 0.0;
-        }
         for (int c = tid; c < kRowGroups * a.ntg_pad; c += NT) s_colpart[c] = 0.0;
         __syncthreads();
         // this CTA's next window: asked for now, needed after the tail (the round trip to L2 hides behind P1)
@@ -152,77 +147,48 @@ __global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
 
         // ---------------- P1 + P2 sums
         const long long tk1 = timed ? clock64() : 0;
-        const uint2* const in = a.scan_out + (size_t)i * npix;
+        const uint32_t* const in = a.scan_out + (size_t)i * npix;
         int32_t* const dbg = a.dbg_iray ? a.dbg_iray + (size_t)b * npix : nullptr;
-        uint2 nxt[PX];
-#pragma unroll
-        for (int p = 0; p < PX; ++p)
-            nxt[p] = (warp < a.nug && 32 * p + lane < a.ntg) ? __ldcs(in + (size_t)warp * a.ntg + 32 * p + lane)
-                                                             : make_uint2(0u, 0u);
+        uint32_t nxt = (warp < a.nug && lane < a.ntg) ? __ldcs(in + (size_t)warp * a.ntg + lane) : 0u;
 #pragma unroll 1
         for (int iu = warp; iu < a.nug; iu += NW) {
-            const uint2* const inrow = in + (size_t)iu * a.ntg;
+            const uint32_t* const inrow = in + (size_t)iu * a.ntg;
             double* const colp = s_colpart + (iu & (kRowGroups - 1)) * a.ntg_pad;
             const double pyd = s_xu[iu];
             const float pyl = s_pys[iu];
             double rowacc = 0.0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < a.ntg; c0 += 32 * PX) {
-                int it[PX];
-                bool live[PX], done[PX];
-                uint2 v[PX];
-                float kb1[PX], thr[PX], pxl[PX];
-                double pxd[PX];
-                PixelHit hit[PX];
-#pragma unroll
-                for (int p = 0; p < PX; ++p) {
-                    const int c = c0 + 32 * p + lane;
-                    it[p] = min(c, a.ntg - 1);                        // lanes past the row end shadow its last pixel
-                    live[p] = c < a.ntg;
-                    v[p] = nxt[p];
-                    // next chunk of this row, or the first chunk of the warp's next row (its latency would otherwise
+            for (int c0 = 0; c0 < a.ntg; c0 += 32) {
+                const int c = c0 + lane;
+                const int it = min(c, a.ntg - 1);                     // lanes past the row end shadow its last pixel
+                const bool live = c < a.ntg;
+                const uint32_t v = nxt;
+                {   // next chunk of this row, or the first chunk of the warp's next row (its latency would otherwise
                     // be exposed once per row)
-                    const bool last = c0 + 32 * PX >= a.ntg;
-                    const int cn = last ? 32 * p + lane : c + 32 * PX;
-                    const uint2* const rn = last ? inrow + (size_t)NW * a.ntg : inrow;
-                    if (cn < a.ntg && (!last || iu + NW < a.nug)) nxt[p] = __ldcs(rn + cn);
-                    kb1[p] = __uint_as_float(v[p].x);
-                    thr[p] = kb1[p] + tau32(kb1[p]);
-                    pxl[p] = s_pxs[it[p]];
-                    pxd[p] = s_xt[it[p]];
+                    const bool last = c0 + 32 >= a.ntg;
+                    const int cn = last ? lane : c + 32;
+                    const uint32_t* const rn = last ? inrow + (size_t)NW * a.ntg : inrow;
+                    if (cn < a.ntg && (!last || iu + NW < a.nug)) nxt = __ldcs(rn + cn);
                 }
-                if constexpr (PX == 1) {
-                    done[0] = resolve_pixel_flagged<T>(tb, s_pn, pxl[0], pyl, pxd[0], pyd, thr[0],
-                                                       (int)(v[0].y & kScanTileMask), (v[0].y & kScanFlag2) != 0u,
-                                                       (v[0].y & kScanFlag3) != 0u, hit[0]);
-                } else {
-                    const unsigned code[2] = {v[0].y, v[1].y};
-                    resolve_pixels2<T>(tb, s_pn, pxl, pyl, pxd, pyd, thr, code, kScanTileMask, kScanFlag2, kScanFlag3,
-                                       hit, done);
+                const float pxl = s_pxs[it];
+                const double pxd = s_xt[it];
+                PixelHit hit;
+                float kb1;
+                const bool done = resolve_pixel_coded<T>(tb, s_pn, pxl, pyl, pxd, pyd, (int)(v & kScanTileMask),
+                                                         (v & kScanFlag2) != 0u, (v & kScanFlag3) != 0u, hit, kb1);
+                unsigned amb = __ballot_sync(0xffffffffu, live && !done);
+                while (amb) {                                         // rare: all-segment rescan by the whole warp
+                    const int src = __ffs((int)amb) - 1;
+                    amb &= amb - 1u;
+                    PixelHit h2;
+                    resolve_pixel_warp(tb, s_pn, __shfl_sync(0xffffffffu, pxl, src), pyl,
+                                       __shfl_sync(0xffffffffu, pxd, src), pyd, __shfl_sync(0xffffffffu, kb1, src), h2);
+                    if (lane == src) { hit = h2; ++slow; }
                 }
-#pragma unroll
-                for (int p = 0; p < PX; ++p) {
-                    unsigned amb = __ballot_sync(0xffffffffu, live[p] && !done[p]);
-                    while (amb) {                                     // rare: all-segment rescan by the whole warp
-                        const int src = __ffs((int)amb) - 1;
-                        amb &= amb - 1u;
-                        PixelHit h2;
-                        resolve_pixel_warp(tb, s_pn, __shfl_sync(0xffffffffu, pxl[p], src), pyl,
-                                           __shfl_sync(0xffffffffu, pxd[p], src), pyd,
-                                           __shfl_sync(0xffffffffu, kb1[p], src), h2);
-                        if (lane == src) { hit[p] = h2; ++slow; }
-                    }
-                }
-                double pdf[PX];
-#pragma unroll
-                for (int p = 0; p < PX; ++p)
-                    pdf[p] = store_pixel<false>(a, s_pn, s_etab, slab, it[p], iu, hit[p], pyd, zero_dist, dbg, live[p]);
-#pragma unroll
-                for (int p = 0; p < PX; ++p) {
-                    if (live[p]) {
-                        rowacc += pdf[p];                             // columns lane, lane + 32, ... in ascending order
-                        colp[it[p]] += pdf[p];                        // rows of one group (row mod 8) in ascending order
-                    }
+                const double pdf = store_pixel<false>(a, s_pn, s_etab, slab, it, iu, hit, pyd, zero_dist, dbg, live);
+                if (live) {
+                    rowacc += pdf;                                    // columns lane, lane + 32, ... in ascending order
+                    colp[it] += pdf;                                  // rows of one group (row mod 8) in ascending order
                 }
             }
 #pragma unroll
@@ -268,7 +234,7 @@ static int split_chunk(int B, int nug, int ntg, int sms) {
     else {
         // about 512 MiB of scan results per buffer, between 8 and 64 windows per SM: long enough kernels to amortise
         // their tails, small enough buffers for any batch size
-        const long long by_bytes = (512LL << 20) / ((long long)nug * ntg * 8);
+        const long long by_bytes = (512LL << 20) / ((long long)nug * ntg * 4);
         c = (int)(by_bytes < 8LL * sms ? 8LL * sms : by_bytes > 64LL * sms ? 64LL * sms : by_bytes);
     }
     if (c < (B + kMaxChunks - 1) / kMaxChunks) c = (B + kMaxChunks - 1) / kMaxChunks;
@@ -288,7 +254,7 @@ size_t split_workspace_bytes(int B, int nt, int nug, int ntg, int sms) {
     if (!split_wanted(B, nt, nug, ntg, sms)) return 0;
     const int chunk = split_chunk(B, nug, ntg, sms);
     const int nbuf = (B + chunk - 1) / chunk < kScanBuffers ? (B + chunk - 1) / chunk : kScanBuffers;
-    return (size_t)nbuf * chunk * nug * ntg * 8 + 512;
+    return (size_t)nbuf * ((((size_t)chunk * nug * ntg * 4) + 255) & ~(size_t)255) + 512;
 }
 
 // Helper stream + events per (device, caller stream); created on first use, kept for the life of the process.
@@ -338,32 +304,29 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
     // resolve kernel: 128 registers x 2 CTAs per SM for long windows (deeper unrolled gradient assembly: its slab
     // read-back is the latency sink of the kernel), 80 registers x 3 per SM for short ones
     int rshape = dev_option(kOptResolveShape);
-    if (rshape < 1 || rshape > 5) rshape = smem_r > 48 * 1024 ? 1 : 2;
+    if (rshape != 1 && rshape != 2 && rshape != 5) rshape = smem_r > 48 * 1024 ? 1 : 2;
     const int rthreads = rshape == 5 ? 128 : 256;
-    const int res_ctas = rshape == 1 ? resident_ctas(k_resolve<2, T, 1>, smem_r, &per_sm, 256)
-                       : rshape == 2 ? resident_ctas(k_resolve<3, T, 1>, smem_r, &per_sm, 256)
-                       : rshape == 3 ? resident_ctas(k_resolve<2, T, 2>, smem_r, &per_sm, 256)
-                       : rshape == 4 ? resident_ctas(k_resolve<3, T, 2>, smem_r, &per_sm, 256)
-                                     : resident_ctas(k_resolve<6, T, 1, 128>, smem_r, &per_sm, 128);
+    const int res_ctas = rshape == 1 ? resident_ctas(k_resolve<2, T, 256>, smem_r, &per_sm, 256)
+                       : rshape == 2 ? resident_ctas(k_resolve<3, T, 256>, smem_r, &per_sm, 256)
+                                     : resident_ctas(k_resolve<6, T, 128>, smem_r, &per_sm, 128);
     if (res_ctas < 1) return cuda_fail(cudaGetLastError(), "k_resolve occupancy");
-    const size_t slab_px = 20;                         // bytes per pixel of the per-CTA scratch slab
+    const size_t slab_px = 16;                         // bytes per pixel of the per-CTA scratch slab
     const int Btot = a.B;
     const int chunk = split_chunk(Btot, a.nug, a.ntg, sms);
     const int nchunks = (Btot + chunk - 1) / chunk;
     const int nbuf = nchunks < kScanBuffers ? nchunks : kScanBuffers;
     // workspace: [scan results: nbuf chunks][slabs of the resolve CTAs]
     uintptr_t p = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
-    const size_t scan_bytes = (size_t)chunk * npix * 8;
+    const size_t scan_bytes = ((size_t)chunk * npix * 4 + 255) & ~(size_t)255;
     if (ws_bytes < (p - (uintptr_t)ws) + nbuf * scan_bytes + npix * slab_px) return WFOT_ERR_WORKSPACE;
-    uint2* const scan_base = (uint2*)p;
+    unsigned char* const scan_base = (unsigned char*)p;
     p += nbuf * scan_bytes;
     const size_t max_ctas = (ws_bytes - (p - (uintptr_t)ws)) / (npix * slab_px);
     const int res_grid = (size_t)res_ctas > max_ctas ? (int)max_ctas : res_ctas;
     unsigned char* q = (unsigned char*)p;
     ar.s_pdf = nullptr;      // the resolve kernel sums the density on the fly
     ar.s_wa = (double*)q;    q += (size_t)res_grid * npix * 8;
-    ar.s_wb = (double*)q;    q += (size_t)res_grid * npix * 8;
-    ar.s_idx = (int32_t*)q;
+    ar.s_wbi = (unsigned long long*)q;
     as.cluster = ar.cluster = 1;
     int* const counters = a.next_window;             // 64 ints, zeroed by the caller on `stream`
     cudaStream_t rstream = lane ? lane->side : stream;
@@ -372,7 +335,7 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
         const int nb = (Btot - c0 < chunk) ? Btot - c0 : chunk;
         const int buf = c % nbuf;
         as.b0 = ar.b0 = c0; as.B = ar.B = nb;
-        as.scan_out = ar.scan_out = scan_base + (size_t)buf * chunk * npix;
+        as.scan_out = ar.scan_out = (uint32_t*)(scan_base + (size_t)buf * scan_bytes);
         as.next_window = counters + 2 * c;
         ar.next_window = counters + 2 * c + 1 - 16;  // k_resolve counts at next_window + 16
         if (lane && c >= nbuf && cudaStreamWaitEvent(stream, lane->resolved[buf], 0) != cudaSuccess)
@@ -388,11 +351,9 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
         }
         const int rc = res_grid < nb ? res_grid : nb;
         if (skip == 1) {}
-        else if (rshape == 1) k_resolve<2, T, 1><<<rc, 256, smem_r, rstream>>>(ar);
-        else if (rshape == 2) k_resolve<3, T, 1><<<rc, 256, smem_r, rstream>>>(ar);
-        else if (rshape == 3) k_resolve<2, T, 2><<<rc, 256, smem_r, rstream>>>(ar);
-        else if (rshape == 4) k_resolve<3, T, 2><<<rc, 256, smem_r, rstream>>>(ar);
-        else k_resolve<6, T, 1, 128><<<rc, rthreads, smem_r, rstream>>>(ar);
+        else if (rshape == 1) k_resolve<2, T, 256><<<rc, 256, smem_r, rstream>>>(ar);
+        else if (rshape == 2) k_resolve<3, T, 256><<<rc, 256, smem_r, rstream>>>(ar);
+        else k_resolve<6, T, 128><<<rc, rthreads, smem_r, rstream>>>(ar);
         note_launches(2);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "wfot_misfit_grad_batch (scan + resolve) launch");
