@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwfot.so")
+LIB_PATH = os.environ.get("WFOT_LIB_PATH") or os.path.join(HERE, "libwfot.so")     # override: A/B of two builds (scripts/)
 
 STAT_NEG_PDF, STAT_COMMON_CDF, STAT_ZERO_DIST, STAT_DEGENERATE_SEG, STAT_SLOW_PIXELS = range(5)
 STAT_SCAN_TILES = 6          # slots 6-7: one 64-bit counter

@@ -232,13 +232,16 @@ static int split_chunk(int B, int nug, int ntg, int sms) {
     int c;
     if (const int o = dev_option(kOptSplitChunk)) c = o;
     else {
-        // about 512 MiB of scan results per buffer, between 8 and 64 windows per SM: long enough kernels to amortise
-        // their tails, small enough buffers for any batch size
-        const long long by_bytes = (512LL << 20) / ((long long)nug * ntg * 4);
+        // up to 2.5 GiB of scan results per buffer, between 8 and 64 windows per SM.  Measured on cfg5 (9472 windows):
+        // one launch pair 369 k evals/s, two to five overlapped pairs 363-365 k - the tails that the second stream
+        // fills cost less than the kernels lose while they share the SMs - so chunks are as large as memory allows
+        const long long by_bytes = (2560LL << 20) / ((long long)nug * ntg * 4);
         c = (int)(by_bytes < 8LL * sms ? 8LL * sms : by_bytes > 64LL * sms ? 64LL * sms : by_bytes);
     }
     if (c < (B + kMaxChunks - 1) / kMaxChunks) c = (B + kMaxChunks - 1) / kMaxChunks;
-    return c < B ? c : B;
+    if (c >= B) return B;
+    const int n = (B + c - 1) / c;        // equal chunks: no short last one
+    return (B + n - 1) / n;
 }
 
 bool split_wanted(int B, int nt, int nug, int ntg, int sms) {
