@@ -21,9 +21,8 @@ for r in csv.reader(open(path, newline="")):
     if r[0] == "Function Name":
         cur_fn = r[1]; continue
     if r[0] == "Line No":
-        hdr = {h: i for i, h in enumerate(r)}
-        n = len(r)
-        stall_cols = [(h, i - n) for h, i in hdr.items() if h.startswith("stall_") and "Not Issued" not in h]
+        hdr = {h: i for i, h in enumerate(r)}        # column positions ("Source" appears twice; not used by name)
+        stall_cols = [(h, i) for h, i in hdr.items() if h.startswith("stall_") and "Not Issued" not in h]
         continue
     if hdr is None or kfilter not in (cur_fn or ""):
         continue
@@ -33,11 +32,10 @@ for r in csv.reader(open(path, newline="")):
         line = int(r[0])
     except ValueError:
         continue
-    n = len(hdr)
     try:
-        S = int(r[hdr["# Samples"] - n] or 0)
-        IE = int(r[hdr["Instructions Executed"] - n] or 0)
-        TI = int(r[hdr["Thread Instructions Executed"] - n] or 0)
+        S = int(r[hdr["# Samples"]] or 0)
+        IE = int(r[hdr["Instructions Executed"]] or 0)
+        TI = int(r[hdr["Thread Instructions Executed"]] or 0)
     except (ValueError, IndexError, KeyError):
         continue
     a = agg.setdefault((cur_file, line), [0, 0, 0, r[1].strip()[:80], collections.Counter()])

@@ -10,7 +10,7 @@ cd "$(dirname "$0")/.."
 TAG=${1:?tag}; NOTE=${2:-}
 D=waveform_ot_b200/csrc/wfot_device.cuh; F=waveform_ot_b200/csrc/wfot_fused.cuh; S=waveform_ot_b200/csrc/wfot_split.cu
 ln() { grep -n -e "$2" "$1" < /dev/null | head -1 | cut -d: -f1; }
-tau=$(ln $D "float sqrt_approx("); e64=$(ln $D "void eval64("); hit=$(ln $D "^struct PixelHit"); tm=$(ln $D "unsigned tile_mask(")
+tau=$(ln $D "float sqrt_approx("); e64=$(ln $D "void eval64("); hit=$(ln $D "^struct PixelHit"); tm=$(ln $D "void tile_dists(")
 ec=$(ln $D "void eval_candidates("); rf=$(ln $D "bool resolve_pixel_flagged("); rfull=$(ln $D "void resolve_pixel_full(")
 foot=$(ln $D "^// -* warp footprints"); hot=$(ln $D "^// -* the hot loop"); prep=$(ln $D "window preparation"); epi=$(ln $D "per-pixel epilogue values")
 sp=$(ln $F "double store_pixel("); p2=$(ln $F "---------------- P2"); p3=$(ln $F "---------------- P3"); p4=$(ln $F "---------------- P4"); pe=$(ln $F "resident CTAs of a kernel")

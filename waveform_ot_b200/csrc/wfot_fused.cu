@@ -186,7 +186,7 @@ static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaS
     int sms = wfot_device_sm_count();
     if (sms <= 0) return cuda_fail(cudaGetLastError(), "device query");
     const int pipeline = dev_option(kOptPipeline);
-    if (pipeline == 2 || (pipeline == 0 && split_wanted(B, nt, nug, ntg, sms)))
+    if (pipeline != 1 && split_wanted(B, nt, nug, ntg, sms))
         return launch_split(a, (unsigned char*)base, avail, stream);
 
     int per_sm = 0;

@@ -106,17 +106,17 @@ struct FusedArgs {
     int32_t* status;
     int* next_window;     // global work counters (zeroed by the launcher): [0] fused / scan, [16] resolve
     int cluster;          // > 1: launched as thread-block clusters of this many CTAs, one window per CLUSTER
-    // split form: windows b0 .. b0 + B - 1 of the call; per-pixel scan results (tile | flags, 4 bytes) of window
+    // split form: windows b0 .. b0 + B - 1 of the call; per-pixel scan results (tile | flags, 2 bytes) of window
     // b0 + i at scan_out[i * npix ...]
     int b0;
-    uint32_t* scan_out;
+    uint16_t* scan_out;
     int Spad, ntg_pad, nug_pad, nmax;
     SmemLayout L;
 };
 
 // flags in the second word of a scan result: another tile / two other tiles hold a segment within the FP32
 // rounding tolerance of the pixel's minimum (see resolve_pixel)
-constexpr unsigned kScanFlag2 = 1u << 30, kScanFlag3 = 1u << 31, kScanTileMask = kScanFlag2 - 1u;
+constexpr unsigned kScanFlag2 = 1u << 14, kScanFlag3 = 1u << 15, kScanTileMask = kScanFlag2 - 1u;   // 16-bit results: < 16384 tiles
 
 #define WFOT_SMEM_POINTERS(L)                                                            \
     double2* const s_pn = reinterpret_cast<double2*>(smem_raw + (L).pn);                 \

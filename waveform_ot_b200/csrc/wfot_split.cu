@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
     const int npix = a.nug * a.ntg, S = a.nt - 1;
     SegTable tb{s_A, s_H, s_bbox, S, a.Spad, T};
     int degen = 0, tiles = 0;
-    const bool vec = (a.ntg & 1) == 0;      // both pixels of a column pair exist and their 8 bytes are aligned
+    const bool vec = (a.ntg & 1) == 0;      // both pixels of a column pair exist and their 4 bytes are aligned
     for (int i = blockIdx.x; i < a.B;) {
         const int b = a.b0 + i;
         const wfot_grid g = a.grids[b % a.n_grids];
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
                     a.nug, a.ntg, a.transform, po, s_red, nullptr);
         __syncthreads();
         degen += (tid == 0) ? s_hdr->degenerate : 0;
-        uint32_t* const out = a.scan_out + (size_t)i * npix;
+        uint16_t* const out = a.scan_out + (size_t)i * npix;
         const FootMap fm = make_footmap<R>(a.ntg, a.nug, fabsf(s_pxs[a.ntg - 1] - s_pxs[0]),
                                            fabsf(s_pys[a.nug - 1] - s_pys[0]));
         for (;;) {
@@ -82,12 +82,12 @@ __global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
             for (int r = 0; r < R; ++r) {
                 const int iu = rg * R + r;
                 if (iu >= a.nug) break;
-                uint32_t* const dst = out + (size_t)iu * a.ntg + it0;
+                uint16_t* const dst = out + (size_t)iu * a.ntg + it0;
                 if (vec) {
-                    *reinterpret_cast<uint2*>(dst) = make_uint2(code[2 * r], code[2 * r + 1]);
+                    *reinterpret_cast<uint32_t*>(dst) = code[2 * r] | (code[2 * r + 1] << 16);
                 } else {
-                    dst[0] = code[2 * r];
-                    if (it0 + 1 < a.ntg) dst[1] = code[2 * r + 1];
+                    dst[0] = (uint16_t)code[2 * r];
+                    if (it0 + 1 < a.ntg) dst[1] = (uint16_t)code[2 * r + 1];
                 }
             }
         }
@@ -147,12 +147,12 @@ __global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
 
         // ---------------- P1 + P2 sums
         const long long tk1 = timed ? clock64() : 0;
-        const uint32_t* const in = a.scan_out + (size_t)i * npix;
+        const uint16_t* const in = a.scan_out + (size_t)i * npix;
         int32_t* const dbg = a.dbg_iray ? a.dbg_iray + (size_t)b * npix : nullptr;
-        uint32_t nxt = (warp < a.nug && lane < a.ntg) ? __ldcs(in + (size_t)warp * a.ntg + lane) : 0u;
+        unsigned nxt = (warp < a.nug && lane < a.ntg) ? __ldcs(in + (size_t)warp * a.ntg + lane) : 0u;
 #pragma unroll 1
         for (int iu = warp; iu < a.nug; iu += NW) {
-            const uint32_t* const inrow = in + (size_t)iu * a.ntg;
+            const uint16_t* const inrow = in + (size_t)iu * a.ntg;
             double* const colp = s_colpart + (iu & (kRowGroups - 1)) * a.ntg_pad;
             const double pyd = s_xu[iu];
             const float pyl = s_pys[iu];
@@ -162,12 +162,12 @@ __global__ void __launch_bounds__(NT, MINB) k_resolve(FusedArgs a) {
                 const int c = c0 + lane;
                 const int it = min(c, a.ntg - 1);                     // lanes past the row end shadow its last pixel
                 const bool live = c < a.ntg;
-                const uint32_t v = nxt;
+                const unsigned v = nxt;
                 {   // next chunk of this row, or the first chunk of the warp's next row (its latency would otherwise
                     // be exposed once per row)
                     const bool last = c0 + 32 >= a.ntg;
                     const int cn = last ? lane : c + 32;
-                    const uint32_t* const rn = last ? inrow + (size_t)NW * a.ntg : inrow;
+                    const uint16_t* const rn = last ? inrow + (size_t)NW * a.ntg : inrow;
                     if (cn < a.ntg && (!last || iu + NW < a.nug)) nxt = __ldcs(rn + cn);
                 }
                 const float pxl = s_pxs[it];
@@ -232,10 +232,10 @@ static int split_chunk(int B, int nug, int ntg, int sms) {
     int c;
     if (const int o = dev_option(kOptSplitChunk)) c = o;
     else {
-        // up to 2.5 GiB of scan results per buffer, between 8 and 64 windows per SM.  Measured on cfg5 (9472 windows):
+        // up to 2.5 GiB of scan results per buffer (2 bytes per pixel), between 8 and 64 windows per SM.  Measured on cfg5 (9472 windows):
         // one launch pair 369 k evals/s, two to five overlapped pairs 363-365 k - the tails that the second stream
         // fills cost less than the kernels lose while they share the SMs - so chunks are as large as memory allows
-        const long long by_bytes = (2560LL << 20) / ((long long)nug * ntg * 4);
+        const long long by_bytes = (2560LL << 20) / ((long long)nug * ntg * 2);
         c = (int)(by_bytes < 8LL * sms ? 8LL * sms : by_bytes > 64LL * sms ? 64LL * sms : by_bytes);
     }
     if (c < (B + kMaxChunks - 1) / kMaxChunks) c = (B + kMaxChunks - 1) / kMaxChunks;
@@ -245,19 +245,19 @@ static int split_chunk(int B, int nug, int ntg, int sms) {
 }
 
 bool split_wanted(int B, int nt, int nug, int ntg, int sms) {
-    (void)nt;
     if (dev_option(kOptPipeline) == 1) return false;
-    if (dev_option(kOptPipeline) == 2) return true;
+    if (dev_option(kOptPipeline) == 2) return seg_pad(nt) / kTileMin < 16384;
     // at least four windows per SM (smaller batches: the single-kernel form, with thread-block clusters for the smallest)
     // and rows of at least one warp's width
-    return ntg >= 32 && (long long)nug * ntg >= 2048 && B >= 4 * sms;
+    // (16-bit scan results hold tile indices below 16384)
+    return ntg >= 32 && (long long)nug * ntg >= 2048 && B >= 4 * sms && seg_pad(nt) / kTileMin < 16384;
 }
 
 size_t split_workspace_bytes(int B, int nt, int nug, int ntg, int sms) {
     if (!split_wanted(B, nt, nug, ntg, sms)) return 0;
     const int chunk = split_chunk(B, nug, ntg, sms);
     const int nbuf = (B + chunk - 1) / chunk < kScanBuffers ? (B + chunk - 1) / chunk : kScanBuffers;
-    return (size_t)nbuf * ((((size_t)chunk * nug * ntg * 4) + 255) & ~(size_t)255) + 512;
+    return (size_t)nbuf * ((((size_t)chunk * nug * ntg * 2) + 255) & ~(size_t)255) + 512;
 }
 
 // Helper stream + events per (device, caller stream); created on first use, kept for the life of the process.
@@ -320,7 +320,7 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
     const int nbuf = nchunks < kScanBuffers ? nchunks : kScanBuffers;
     // workspace: [scan results: nbuf chunks][slabs of the resolve CTAs]
     uintptr_t p = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
-    const size_t scan_bytes = ((size_t)chunk * npix * 4 + 255) & ~(size_t)255;
+    const size_t scan_bytes = ((size_t)chunk * npix * 2 + 255) & ~(size_t)255;
     if (ws_bytes < (p - (uintptr_t)ws) + nbuf * scan_bytes + npix * slab_px) return WFOT_ERR_WORKSPACE;
     unsigned char* const scan_base = (unsigned char*)p;
     p += nbuf * scan_bytes;
@@ -338,7 +338,7 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
         const int nb = (Btot - c0 < chunk) ? Btot - c0 : chunk;
         const int buf = c % nbuf;
         as.b0 = ar.b0 = c0; as.B = ar.B = nb;
-        as.scan_out = ar.scan_out = (uint32_t*)(scan_base + (size_t)buf * scan_bytes);
+        as.scan_out = ar.scan_out = (uint16_t*)(scan_base + (size_t)buf * scan_bytes);
         as.next_window = counters + 2 * c;
         ar.next_window = counters + 2 * c + 1 - 16;  // k_resolve counts at next_window + 16
         if (lane && c >= nbuf && cudaStreamWaitEvent(stream, lane->resolved[buf], 0) != cudaSuccess)
