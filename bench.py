@@ -781,7 +781,7 @@ def run_ours(args):
             "config": {"workload": "cfg5: 1024-sample windows -> 256x256 fingerprint, W2 misfit + gradient",
                        "nt": NT, "nug": NUG, "ntg": NTG, "lambda": LAM, "windows_per_gpu_per_step": nb,
                        "global_windows_per_step": world * nb,
-                       "l2": "3 input batches cycled; per-step scratch (8 B/pixel scan results per window + 20 B/pixel x resident CTAs) + inputs exceed the 126 MB L2",
+                       "l2": "3 input batches cycled; per-step scratch (2 B/pixel scan results per window + 16 B/pixel slab x resident CTAs, 1.5 GB at 9472 windows) + inputs exceed the 126 MB L2",
                        "parallelism": "windows sharded over %d GPU(s), one allreduce of [sum misfit, sum grad]" % world},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak_tflops, "traffic": traffic,
@@ -794,7 +794,7 @@ def run_ours(args):
                          "peak_source": "FFMA2 probe measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core entry)",
                          "algorithmic_flop_per_window": ALG_FLOP_PER_WINDOW,
                          "note": "achieved = 15 FLOP x pixels x segments (brute-force Enumerate count, SURVEY 8d) / device time "
-                                 "of the call; the per-kernel split (scan ~38 %, resolve ~62 %) and their counters are in "
+                                 "of the call; the per-kernel split (scan ~39 %, resolve ~61 %) and their counters are in "
                                  "profiles/r02_*"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": nrep, "pipeline": "2 streams, copies of one step overlap the next step's kernel"},
