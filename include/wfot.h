@@ -201,9 +201,11 @@ int wfot_ricker_batch(const double* params, int M, double t0, double t1,
  * independent of the launch shape (single kernel, two kernels, clusters, threads per CTA); the
  * final sums of W over the merged knots are block reductions, so W / dwg agree across launch
  * shapes with different CTA sizes to ~1e-15 relative, not bitwise.  grad is assembled with
- * FP64 reductions in L2 in arrival order (one per run of equal nearest segment in a pixel
- * column): its last bits vary from run to run, by <= 1e-12 relative to the row's largest
- * entry (tests/test_gpu_parity.py::test_fused_run_to_run).
+ * FP64 reductions in L2 in arrival order (one per run of pixels of a column that feed the same
+ * sample): its last bits vary from run to run, by <= 1e-12 relative to the row's largest
+ * entry (tests/test_gpu_parity.py::test_fused_run_to_run).  One of the two per-pixel weights
+ * travels through the scratch slab with a 36-bit mantissa: grad agrees with the reference to
+ * ~1e-11 relative to the row's largest entry (1e-13 measured), not to the last digit.
  * Size limit: sample coordinates, segment table, marginals and the OT scratch of a
  * window share one SM's shared memory (about 36 B per sample + 40 B per grid point
  * of the longer axis), i.e. nt up to about 6 000; beyond that WFOT_ERR_UNSUPPORTED

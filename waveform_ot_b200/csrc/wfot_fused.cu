@@ -7,7 +7,7 @@
 //   P1  scan_block + resolve   nearest segment per pixel (FP32 scan with exact tile pruning over
 //                              warp footprints drawn from a shared counter, FP64 exact tie
 //                              resolution); per pixel {iray, pdf, wa, wb} go to a per-CTA
-//                              scratch slab (28 B/pixel, re-used for every window of the CTA)
+//                              scratch slab (24 B/pixel, re-used for every window of the CTA)
 //   P2-P4  window_tail()       marginals, 1-D OT per marginal, gradient assembly (wfot_fused.cuh)
 // Large batches of large windows take the two-kernel form of the same phases (wfot_split.cu).
 // Reference chain replaced: ricker_util.py:386-388 (BuildOTobjfromWaveform ->
@@ -252,8 +252,8 @@ int wfot_dev_set_option(int id, int value) {
     return old;
 }
 
-// Scratch: 28 bytes per pixel per resident CTA (sized for SM count x 8 CTAs so the query needs no
-// occupancy call), plus - for batches that take the two-kernel form - 8 bytes per pixel per window
+// Scratch: 28 bytes per pixel per resident CTA (24 used; sized for SM count x 8 CTAs so the query needs no
+// occupancy call), plus - for batches that take the two-kernel form - 2 bytes per pixel per window
 // of one scan/resolve launch pair.
 void wfot_dev_capture_iray(int32_t* iray) { g_iray_capture = iray; }
 void wfot_dev_phase_cycles(unsigned long long* cycles) { g_phase_cycles = cycles; }
