@@ -176,7 +176,7 @@ static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaS
     a.nmax = pad4(ntg > nug ? ntg : nug);
     a.L = make_layout(nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax);
     const size_t smem = (size_t)a.L.total;
-    if (smem > 227 * 1024) return WFOT_ERR_UNSUPPORTED;
+    if (smem > 227 * 1024 || nt > 65536) return WFOT_ERR_UNSUPPORTED;      // (slab entries carry 16-bit segment indices)
     uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     if (workspace_bytes < (base - (uintptr_t)workspace) + 256) return WFOT_ERR_WORKSPACE;
     a.next_window = (int*)base;                       // first 256 bytes: the window counters
