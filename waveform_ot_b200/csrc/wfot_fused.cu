@@ -174,7 +174,8 @@ static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaS
     a.dbg_phase = g_phase_cycles;
     a.Spad = seg_pad(nt); a.ntg_pad = pad4(ntg); a.nug_pad = pad4(nug);
     a.nmax = pad4(ntg > nug ? ntg : nug);
-    a.L = make_layout(nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax);
+    a.L = make_layout_auto(nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax, kLayoutFused,
+                           (long long)nug * ntg <= 8192 ? 8 : (long long)nug * ntg <= 16384 ? 4 : 2);
     const size_t smem = (size_t)a.L.total;
     if (smem > 227 * 1024 || nt > 65536) return WFOT_ERR_UNSUPPORTED;      // (slab entries carry 16-bit segment indices)
     uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;

@@ -31,6 +31,7 @@ constexpr int kRowGroups = 8;
 // shared address space (LDS/STS instead of generic loads).
 struct SmemLayout {
     int pn, A, H, bbox, keys, pxs, pys, margt, margu, Rt, Ru, xt, xu, cf, E, tk, dx, red, gbins, posf, queue, hdr, qcount;
+    int cf2, E2, tk2, dx2, posf2;   // OT scratch of the amplitude marginal (0: absent, the two problems share one warp)
     int etab;       // 2^(j/64) table of exp_neg() (1 KB)
     int colpart;    // resolve kernel: per-row-group column sums of the density, [kRowGroups][ntg_pad] doubles
     int qcap;       // entries of the ambiguous-pixel queue
@@ -41,7 +42,8 @@ enum LayoutKind { kLayoutFused = 0, kLayoutScan = 1, kLayoutResolve = 2 };
 
 // kLayoutScan keeps only what prep_window + scan_block touch; kLayoutResolve drops the tile boxes and keys (and
 // halves the queue) so that four 256-thread CTAs fit one SM.
-inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nmax, int kind = kLayoutFused) {
+inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nmax, int kind = kLayoutFused,
+                              bool pair = false) {
     SmemLayout L;
     memset(&L, 0, sizeof(L));
     int o = 0;
@@ -65,6 +67,13 @@ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nm
         L.tk = take(nmax * 16);
         L.dx = take(nmax * 16);
         L.posf = take(nmax * 4);
+        if (pair) {      // the two marginal problems side by side, one warp each (warp_ot1d)
+            L.cf2 = take(nmax * 8);
+            L.E2 = take(nmax * 8);
+            L.tk2 = take(nmax * 16);
+            L.dx2 = take(nmax * 16);
+            L.posf2 = take(nmax * 4);
+        }
         L.gbins = take(nt * 8);
         o = o > uend_scan ? o : uend_scan;
         L.margt = take(ntg_pad * 8);
@@ -85,6 +94,14 @@ inline SmemLayout make_layout(int nt, int Spad, int ntg_pad, int nug_pad, int nm
     L.qcount = take(16);
     L.total = o;
     return L;
+}
+
+// Layout with the second OT scratch set when that does not cost a resident CTA (`cta_cap` = CTAs per SM the registers allow)
+inline SmemLayout make_layout_auto(int nt, int Spad, int ntg_pad, int nug_pad, int nmax, int kind, int cta_cap) {
+    const SmemLayout L0 = make_layout(nt, Spad, ntg_pad, nug_pad, nmax, kind, false);
+    const SmemLayout L1 = make_layout(nt, Spad, ntg_pad, nug_pad, nmax, kind, true);
+    auto ctas = [&](int total) { const int c = (227 * 1024) / (total + 1024); return c < cta_cap ? c : cta_cap; };
+    return (L1.total <= 227 * 1024 && ctas(L1.total) >= ctas(L0.total)) ? L1 : L0;
 }
 
 struct FusedArgs {
@@ -296,25 +313,55 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
         return 0;
     }
 
-    // ---------------- P3
+    // ---------------- P3: both marginal problems by warp 0, without block barriers (warp_ot1d)
     const size_t trow = (size_t)(b % a.tgt_rows);
     OtScratch sc{s_cf, s_tk, s_dx, s_E, s_posf, s_red};
     for (int c = tid; c < a.ntg; c += NT) s_cf[c] = s_margt[c];
     __syncthreads();
-    const OtResult rt = block_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, a.ntg, s_xt,
-                                   a.tgt_x_t + trow * a.ntg, a.pmask,
-                                   (a.pmask & 1) ? s_Rt : nullptr, (a.pmask & 2) ? s_Rt : nullptr, nullptr);
-    double gp = 0.0;
-    for (int c = tid; c < a.ntg; c += NT) gp += s_margt[c] * s_Rt[c];
-    const double Gt = block_sum(gp, s_red);                         // <dwpmargX, pbar> (OTlib.py:1144)
-    for (int c = tid; c < a.nug; c += NT) s_cf[c] = s_margu[c];
+    if (a.L.cf2) {       // one warp per marginal
+        double* const s_cf2 = reinterpret_cast<double*>(smem_raw + a.L.cf2);
+        if (warp == 0) {
+            const WarpOtResult ot = warp_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, s_xt, a.tgt_x_t + trow * a.ntg,
+                                              a.pmask, s_Rt, s_margt);
+            if (lane == 0) {
+                s_red[0] = ot.r.W1; s_red[1] = ot.r.W2; s_red[2] = ot.r.dpos1; s_red[3] = ot.r.dpos2; s_red[4] = ot.G;
+                s_red[8] = __longlong_as_double((long long)ot.r.common);
+            }
+        } else if (warp == 1) {
+            const OtScratch sc2{s_cf2, reinterpret_cast<double*>(smem_raw + a.L.tk2),
+                                reinterpret_cast<double*>(smem_raw + a.L.dx2), reinterpret_cast<double*>(smem_raw + a.L.E2),
+                                reinterpret_cast<int*>(smem_raw + a.L.posf2), s_red};
+            for (int c = lane; c < a.nug; c += 32) s_cf2[c] = s_margu[c];
+            __syncwarp();
+            const WarpOtResult ou = warp_ot1d(sc2, a.nug, a.tgt_cdf_u + trow * a.nug, s_xu, a.tgt_x_u + trow * a.nug,
+                                              a.pmask, s_Ru, s_margu);
+            if (lane == 0) {
+                s_red[5] = ou.r.W1; s_red[6] = ou.r.W2; s_red[7] = ou.G;
+                s_red[9] = __longlong_as_double((long long)ou.r.common);
+            }
+        }
+    } else if (warp == 0) {
+        const WarpOtResult ot = warp_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, s_xt, a.tgt_x_t + trow * a.ntg,
+                                          a.pmask, s_Rt, s_margt);
+        __syncwarp();
+        for (int c = lane; c < a.nug; c += 32) s_cf[c] = s_margu[c];
+        __syncwarp();
+        const WarpOtResult ou = warp_ot1d(sc, a.nug, a.tgt_cdf_u + trow * a.nug, s_xu, a.tgt_x_u + trow * a.nug,
+                                          a.pmask, s_Ru, s_margu);
+        if (lane == 0) {
+            s_red[0] = ot.r.W1; s_red[1] = ot.r.W2; s_red[2] = ot.r.dpos1; s_red[3] = ot.r.dpos2; s_red[4] = ot.G;
+            s_red[5] = ou.r.W1; s_red[6] = ou.r.W2; s_red[7] = ou.G;
+            s_red[8] = __longlong_as_double((long long)ot.r.common);
+            s_red[9] = __longlong_as_double((long long)ou.r.common);
+        }
+    }
     __syncthreads();
-    const OtResult ru = block_ot1d(sc, a.nug, a.tgt_cdf_u + trow * a.nug, a.nug, s_xu,
-                                   a.tgt_x_u + trow * a.nug, a.pmask,
-                                   (a.pmask & 1) ? s_Ru : nullptr, (a.pmask & 2) ? s_Ru : nullptr, nullptr);
-    gp = 0.0;
-    for (int c = tid; c < a.nug; c += NT) gp += s_margu[c] * s_Ru[c];
-    const double Gu = block_sum(gp, s_red);                         // OTlib.py:1145
+    OtResult rt, ru;
+    rt.W1 = s_red[0]; rt.W2 = s_red[1]; rt.dpos1 = s_red[2]; rt.dpos2 = s_red[3];
+    ru.W1 = s_red[5]; ru.W2 = s_red[6];
+    const double Gt = s_red[4], Gu = s_red[7];                      // <dwpmarg, pbar> (OTlib.py:1144-1145)
+    rt.common = (int)__double_as_longlong(s_red[8]); ru.common = (int)__double_as_longlong(s_red[9]);
+    __syncthreads();                                                // s_red is re-used below
     if (tid == 0) {
         a.W[2 * (size_t)b] = (a.pmask & 1) ? rt.W1 : rt.W2;
         a.W[2 * (size_t)b + 1] = (a.pmask & 1) ? ru.W1 : ru.W2;

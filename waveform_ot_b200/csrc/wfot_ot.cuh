@@ -1,4 +1,4 @@
-// wfot_ot.cuh -- block-cooperative 1-D optimal transport (FP64):
+// wfot_ot.cuh -- 1-D optimal transport inside the fused path (FP64), one warp per problem:
 // OTpdf normalisation + CDF prefix scan (libs/OTlib.py:92-93,112-114), stable
 // rank-merge of the two monotone CDFs (libs/OTlib.py:668-673: append, argsort,
 // bisect_left), W_1 / W_2^2 and translation derivatives (:690-706), and the
@@ -168,14 +168,6 @@ __device__ __forceinline__ int lower_bound_d(const double* a, int n, double v) {
     }
     return lo;
 }
-__device__ __forceinline__ int upper_bound_d(const double* a, int n, double v) {   // bisect_right
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a[mid] <= v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
 
 // Shared-memory working set of one 1-D problem.
 struct OtScratch {
@@ -194,45 +186,131 @@ struct OtResult {
     int neg, common;
 };
 
-// cg/xg/xf may live in shared or global memory.  If dW1/dW2 != nullptr the
-// derivative vectors (length n) are written there (any address space).
-// merge_order (nullable, global): the reference's tkarg.
-__device__ __forceinline__ OtResult block_ot1d(const OtScratch& sc, int n, const double* cg, int m,
-                                               const double* xf, const double* xg, int pmask,
-                                               double* dW1, double* dW2, int32_t* merge_order) {
-    const int tid = threadIdx.x, T = blockDim.x;
-    OtResult r;
-    // -- OTpdf: sign check, normalise, CDF (libs/OTlib.py:91-93,112-114), canonical summation order
-    int neg = 0;
-    r.amp = canon_cdf(sc.cf, n, sc.red, &neg);
+// ------------------------------------------------------------------ one warp, no block barriers
+// The fused path solves two small problems per window (n = m = a grid axis, tens to a few hundred bins).  The
+// block-cooperative version of round 1 ended every phase in a block barrier or a block reduction, and a window paid
+// their latency, not the work: ~24 k cycles per problem whether it had 61 or 256 bins (29 % of a 79 x 61 window).
+// warp_ot1d() is the same algorithm run by ONE warp with warp-level synchronisation only - the two marginal problems
+// of a window run on two warps side by side when shared memory has room for two scratch sets - the rank searches are
+// branch-free with a fixed trip count and U elements of a lane are searched side by side, so their shared-memory
+// latencies overlap.
+// Same CDF (canonical order: the arithmetic of canon_cdf()); the sums over the merged knots are lane-strided + xor tree.
+
+// bisect_left (LEQ = false) / bisect_right (LEQ = true) of U values at once in a[0..n), n >= 1, warp-uniform trip count
+template <int U, bool LEQ>
+__device__ __forceinline__ void bisect_multi(const double* a, int n, const double (&v)[U], int (&lo)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) lo[u] = 0;
+    int len = n;
+    while (len > 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double x = a[lo[u] + half - 1];
+            lo[u] += (LEQ ? (x <= v[u]) : (x < v[u])) ? half : 0;
+        }
+        len -= half;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const double x = a[lo[u]];
+        lo[u] += (LEQ ? (x <= v[u]) : (x < v[u])) ? 1 : 0;
+    }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Called by all 32 lanes of one warp.  sc.cf: un-normalised source amplitudes (n) on entry, source CDF on return;
+// cg_g / xg_g: target CDF / abscissae in global memory (m = n entries); xf: source abscissae (shared); dW (shared, n
+// doubles): receives d W_p^p / d(un-normalised source amplitude) for the order(s) in pmask (the higher one last).
+// `marg` (shared, n): the normalised source density; the result carries G = <dW, marg> (OTlib.py:1144-1145).
+struct WarpOtResult { OtResult r; double G; };
+
+__device__ __forceinline__ WarpOtResult warp_ot1d(const OtScratch& sc, int n, const double* cg_g, const double* xf,
+                                                  const double* xg_g, int pmask, double* dW, const double* marg) {
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    const int m = n, K = 2 * n - 1;
+    WarpOtResult out;
+    double* const cf = sc.cf;
+    double* const cg = sc.E;      // target CDF staged for the searches (E is written after the merge) ...
+    double* const xg = dW;        // ... and its abscissae (dW likewise)
+    for (int j = lane; j < m; j += 32) { cg[j] = cg_g[j]; xg[j] = xg_g[j]; }
+    // -- OTpdf: sign check, normalise, CDF (libs/OTlib.py:91-93,112-114): the arithmetic and order of canon_cdf()
+    {
+        double v = 0.0;
+        int ng = 0;
+        for (int j = lane; j < n; j += 32) { const double x = cf[j]; v += x; ng += (x < 0.0); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, off);
+            ng += __shfl_xor_sync(0xffffffffu, ng, off);
+        }
+        out.r.amp = v; out.r.neg = ng;
+        for (int j = lane; j < n; j += 32) cf[j] = cf[j] / v;      // pdf / amp (:93)
+        __syncwarp();
+        if (lane == 0) {
+            double run = 0.0;
+            for (int j = 0; j < n; ++j) { run += cf[j]; cf[j] = run; }
+        }
+        __syncwarp();
+        const double last = cf[n - 1];
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) cf[j] = cf[j] / last;   // cdf / cdf[-1] (:114)
+        __syncwarp();
+    }
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
     // -- stable rank-merge of cf[:-1] and cg (:668-672)
-    const int K = n + m - 1;
     int common = 0;
-    for (int j = tid; j < n - 1; j += T) {
-        const double v = sc.cf[j];
-        const int lb = lower_bound_d(cg, m, v);
-        const int pos = j + lb;                       // source knots first on ties
-        const int a = lower_bound_d(sc.cf, n, v);     // bisect_left(cf, tk)
-        sc.tk[pos] = v;
-        sc.dx[pos] = xf[a] - xg[lb];
-        sc.posf[j] = pos;
-        if (lb < m - 1 && cg[lb] == v) ++common;      // np.intersect1d(cg[:-1], cf[:-1]) (:664)
-        if (merge_order) merge_order[pos] = j;
+    for (int j0 = lane; j0 < n - 1; j0 += 32 * U) {
+        double v[U];
+        int lb[U], a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (j0 + 32 * u < n - 1) ? cf[j0 + 32 * u] : kInf;
+        bisect_multi<U, false>(cg, m, v, lb);
+        bisect_multi<U, false>(cf, n, v, a);              // bisect_left(cf, tk)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + 32 * u;
+            if (j < n - 1) {
+                const int pos = j + lb[u];                // source knots first on ties
+                sc.tk[pos] = v[u];
+                sc.dx[pos] = xf[a[u]] - xg[lb[u]];
+                sc.posf[j] = pos;
+                if (lb[u] < m - 1 && cg[lb[u]] == v[u]) ++common;      // np.intersect1d(cg[:-1], cf[:-1]) (:664)
+            }
+        }
     }
-    for (int i = tid; i < m; i += T) {
-        const double v = cg[i];
-        const int ub = upper_bound_d(sc.cf, n - 1, v);
-        const int pos = i + ub;
-        const int a = lower_bound_d(sc.cf, n, v);
-        const int b = lower_bound_d(cg, m, v);
-        sc.tk[pos] = v;
-        sc.dx[pos] = xf[a] - xg[b];
-        if (merge_order) merge_order[pos] = n - 1 + i;
+    for (int i0 = lane; i0 < m; i0 += 32 * U) {
+        double v[U];
+        int ub[U], a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (i0 + 32 * u < m) ? cg[i0 + 32 * u] : kInf;
+        if (n > 1) bisect_multi<U, true>(cf, n - 1, v, ub);
+        else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) ub[u] = 0;
+        }
+        bisect_multi<U, false>(cf, n, v, a);
+        bisect_multi<U, false>(cg, m, v, b);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + 32 * u;
+            if (i < m) {
+                const int pos = i + ub[u];
+                sc.tk[pos] = v[u];
+                sc.dx[pos] = xf[a[u]] - xg[b[u]];
+            }
+        }
     }
-    __syncthreads();
+    __syncwarp();
     // -- W_p^p and translation derivatives (:673,690-706)
     double w1 = 0.0, w2 = 0.0, p1 = 0.0, p2 = 0.0;
-    for (int k = tid; k < K; k += T) {
+    for (int k = lane; k < K; k += 32) {
         const double dt = k ? sc.tk[k] - sc.tk[k - 1] : sc.tk[0];
         const double d = sc.dx[k];
         w1 += fabs(d) * dt;
@@ -240,18 +318,19 @@ __device__ __forceinline__ OtResult block_ot1d(const OtScratch& sc, int n, const
         p1 += (d > 0.0 ? dt : (d < 0.0 ? -dt : 0.0));
         p2 += 2.0 * d * dt;
     }
-    r.W1 = block_sum(w1, sc.red);
-    r.W2 = block_sum(w2, sc.red);
-    r.dpos1 = block_sum(p1, sc.red);
-    r.dpos2 = block_sum(p2, sc.red);
-    r.neg = neg;
-    r.common = (int)block_sum((double)common, sc.red);
+    out.r.W1 = warp_sum_d(w1);
+    out.r.W2 = warp_sum_d(w2);
+    out.r.dpos1 = warp_sum_d(p1);
+    out.r.dpos2 = warp_sum_d(p2);
+    out.r.common = __reduce_add_sync(0xffffffffu, common);
+    __syncwarp();                                     // cg (in E) and xg (in dW) are dead from here on
     // -- d/d(un-normalised source amplitude) (:682-686,694,704), O(n) form
+    const int chunk = (n + 31) >> 5;
+    const int beg = lane * chunk, end = min(beg + chunk, n);
     for (int p = 1; p <= 2; ++p) {
-        double* out = (p == 1) ? dW1 : dW2;
-        if (!(pmask & p) || out == nullptr) continue;
+        if (!(pmask & p)) continue;
         double z = 0.0;
-        for (int j = tid; j < n; j += T) {
+        for (int j = lane; j < n; j += 32) {
             double e = 0.0;
             if (j < n - 1) {
                 const int k = sc.posf[j];
@@ -262,14 +341,29 @@ __device__ __forceinline__ OtResult block_ot1d(const OtScratch& sc, int n, const
                 e = c0 - c1;
             }
             sc.E[j] = e;
-            z += sc.cf[j] * e;
+            z += cf[j] * e;
         }
-        const double Z = block_sum(z, sc.red);
-        block_scan(sc.E, n, true, sc.red);
-        for (int j = tid; j < n; j += T) out[j] = (sc.E[j] - Z) / r.amp;
-        __syncthreads();
+        const double Z = warp_sum_d(z);
+        __syncwarp();
+        // suffix sums of E: a lane owns a contiguous chunk (walked from the end), lane totals combined by a warp scan
+        double run = 0.0;
+        for (int i = beg; i < end; ++i) { const int j = n - 1 - i; run += sc.E[j]; sc.E[j] = run; }
+        double inc = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += o;
+        }
+        const double excl = inc - run;
+        for (int i = beg; i < end; ++i) sc.E[n - 1 - i] += excl;
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) dW[j] = (sc.E[j] - Z) / out.r.amp;
+        __syncwarp();
     }
-    return r;
+    double g = 0.0;
+    for (int j = lane; j < n; j += 32) g += marg[j] * dW[j];
+    out.G = warp_sum_d(g);
+    return out;
 }
 
 }  // namespace wfot

@@ -293,7 +293,15 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
     if (sms <= 0) return cuda_fail(cudaGetLastError(), "device query");
     FusedArgs as = a, ar = a;
     as.L = make_layout(a.nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax, kLayoutScan);
-    ar.L = make_layout(a.nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax, kLayoutResolve);
+    // resolve kernel shape: 128 registers x 2 CTAs per SM for long windows (deeper unrolled gradient assembly: its slab
+    // read-back is the latency sink of the kernel), 80 registers x 3 per SM for short ones; the layout gets the second
+    // OT scratch set (the two marginal problems on two warps) unless that costs a resident CTA
+    int rshape = dev_option(kOptResolveShape);
+    {
+        const int base = make_layout(a.nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax, kLayoutResolve).total;
+        if (rshape != 1 && rshape != 2 && rshape != 5) rshape = base > 48 * 1024 ? 1 : 2;
+        ar.L = make_layout_auto(a.nt, a.Spad, a.ntg_pad, a.nug_pad, a.nmax, kLayoutResolve, rshape == 1 ? 2 : rshape == 2 ? 3 : 6);
+    }
     const size_t smem_s = (size_t)as.L.total, smem_r = (size_t)ar.L.total;
     // overlap needs a helper stream; not while the caller's stream is being captured into a CUDA graph
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -304,10 +312,6 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
     const int scan_ctas = scan3 ? resident_ctas(k_scan<4, T, 3>, smem_s, &per_sm, 256)
                                 : resident_ctas(k_scan<4, T, 2>, smem_s, &per_sm, 256);
     if (scan_ctas < 1) return cuda_fail(cudaGetLastError(), "k_scan occupancy");
-    // resolve kernel: 128 registers x 2 CTAs per SM for long windows (deeper unrolled gradient assembly: its slab
-    // read-back is the latency sink of the kernel), 80 registers x 3 per SM for short ones
-    int rshape = dev_option(kOptResolveShape);
-    if (rshape != 1 && rshape != 2 && rshape != 5) rshape = smem_r > 48 * 1024 ? 1 : 2;
     const int rthreads = rshape == 5 ? 128 : 256;
     const int res_ctas = rshape == 1 ? resident_ctas(k_resolve<2, T, 256>, smem_r, &per_sm, 256)
                        : rshape == 2 ? resident_ctas(k_resolve<3, T, 256>, smem_r, &per_sm, 256)
