@@ -15,7 +15,7 @@ ec=$(ln $D "void eval_candidates("); rf=$(ln $D "bool resolve_pixel_flagged("); 
 foot=$(ln $D "^// -* warp footprints"); hot=$(ln $D "^// -* the hot loop"); prep=$(ln $D "window preparation"); epi=$(ln $D "per-pixel epilogue values")
 sp=$(ln $F "double store_pixel("); p2=$(ln $F "---------------- P2"); p3=$(ln $F "---------------- P3"); p4=$(ln $F "---------------- P4"); pe=$(ln $F "resident CTAs of a kernel")
 ks=$(ln $S "k_scan(FusedArgs a)"); kr=$(ln $S "k_resolve(FusedArgs a)"); hs=$(ln $S "^// -* host side")
-GR="tau32:wfot_device.cuh:$tau-$((e64-4)),eval64:wfot_device.cuh:$e64-$((hit-1)),tile_mask (packed FP32 re-evaluation):wfot_device.cuh:$((tm-1))-$((ec-6)),eval_candidates:wfot_device.cuh:$((ec-1))-$((rf-3)),resolve_pixel_flagged:wfot_device.cuh:$((rf-1))-$((rfull-1)),resolve_warp/full:wfot_device.cuh:$rfull-$((foot-1)),prep_window:wfot_device.cuh:$prep-$((epi-1)),store_pixel (density epilogue + slab):wfot_fused.cuh:$((sp-1))-$((sp+36)),P2 column/row sums:wfot_fused.cuh:$p2-$((p3-1)),P3 OT driver:wfot_fused.cuh:$p3-$((p4-1)),P4 gradient assembly:wfot_fused.cuh:$p4-$((pe-1)),block_ot1d + canon sums:wfot_ot.cuh:1-400,k_resolve body:wfot_split.cu:$kr-$((hs-1))"
+GR="tau32:wfot_device.cuh:$tau-$((e64-4)),eval64:wfot_device.cuh:$e64-$((hit-1)),tile_mask (packed FP32 re-evaluation):wfot_device.cuh:$((tm-1))-$((ec-6)),eval_candidates:wfot_device.cuh:$((ec-1))-$((rf-3)),resolve_pixel_flagged:wfot_device.cuh:$((rf-1))-$((rfull-1)),resolve_warp/full:wfot_device.cuh:$rfull-$((foot-1)),prep_window:wfot_device.cuh:$prep-$((epi-1)),store_pixel (density epilogue + slab):wfot_fused.cuh:$((sp-1))-$((sp+36)),P2 column/row sums:wfot_fused.cuh:$p2-$((p3-1)),P3 OT driver:wfot_fused.cuh:$p3-$((p4-1)),P4 gradient assembly:wfot_fused.cuh:$p4-$((pe-1)),warp_ot1d + canon sums:wfot_ot.cuh:1-400,k_resolve body:wfot_split.cu:$kr-$((hs-1))"
 GS="tau32:wfot_device.cuh:$tau-$((e64-4)),footmap/lane_block:wfot_device.cuh:$foot-$((hot-1)),scan_block:wfot_device.cuh:$hot-$((prep-1)),prep_window:wfot_device.cuh:$prep-$((epi-1)),k_scan body:wfot_split.cu:$ks-$((kr-12))"
 if [ -f gpurun_out/bench_final.json ]; then cp gpurun_out/bench_final.json profiles/r02_bench.json; fi
 if [ -f gpurun_out/launches_final.csv ]; then
