@@ -59,6 +59,8 @@ VARIANTS = [("two-kernel default", 0, 0, 0, 0),
             ("two-kernel, resolve 128 regs x2", 0, 1, 0, 0),
             ("two-kernel, resolve 80 regs x3", 0, 2, 0, 0),
             ("two-kernel, scan 128 regs x2", 0, 0, 0, 2),
+            ("two-kernel, scan 256 threads x3", 0, 0, 0, 3),
+            ("two-kernel, scan 128 threads x6", 0, 0, 0, 4),
             ("two-kernel, resolve 128 threads x6", 0, 5, 0, 0),
             ("two-kernel sequential one chunk", 1, 0, nb, 0),
             ("two-kernel chunk 32/SM", 0, 0, 4736, 0)]

@@ -12,7 +12,7 @@ enum DevOption {
     kOptTile = 4,          // argmin tile: 0 auto, 8 or 16 segments
     kOptSplitChunk = 5,    // windows per scan/resolve launch pair: 0 auto
     kOptOverlap = 6,       // two-kernel form: 0 auto (resolve of chunk c next to the scan of chunk c + 1), 1 sequential
-    kOptScanShape = 7,     // k_scan CTAs per SM: 0 auto (3, 80 registers), 2 = 2 per SM (128 registers)
+    kOptScanShape = 7,     // k_scan: 0 auto, 2 = 256 threads x 2 per SM (128 registers), 3 = 256 x 3 (80 registers), 4 = 128 threads x 6
     kOptSkipKernel = 8,    // two-kernel form, timing aid: 1 = do not launch k_resolve, 2 = do not launch k_scan (stale scan results)
     kOptCount = 12
 };

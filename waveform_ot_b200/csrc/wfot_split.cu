@@ -30,8 +30,8 @@
 namespace wfot {
 
 // ------------------------------------------------------------------ k_scan
-template <int R, int T, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_scan(FusedArgs a) {
+template <int R, int T, int MINB, int NT = 256>
+__global__ void __launch_bounds__(NT, MINB) k_scan(FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WFOT_SMEM_POINTERS(a.L);
     (void)s_margt; (void)s_margu; (void)s_Rt; (void)s_Ru; (void)s_xt; (void)s_xu; (void)s_cf; (void)s_E;
@@ -308,8 +308,15 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
     cudaStreamIsCapturing(stream, &cap);
     SideLane* lane = (overlap_enabled() && cap == cudaStreamCaptureStatusNone) ? side_lane(stream) : nullptr;
     int per_sm = 0;
-    const int scan3 = dev_option(kOptScanShape) != 2;             // default: 80 registers, 3 CTAs per SM (2: 128 x 2)
-    const int scan_ctas = scan3 ? resident_ctas(k_scan<4, T, 3>, smem_s, &per_sm, 256)
+    const int scan3 = dev_option(kOptScanShape) != 2;             // default: 80 registers, 3 CTAs per SM (2: 128 x 2; 4: 128 threads x 6)
+    // windows with fewer footprints than a 256-thread CTA has warps to spare (79 x 61 pixels: 20 footprints for 8 warps,
+    // and the barriers of the window preparation in between): 128-thread CTAs, six per SM
+    const int nfoot = max_footprints<4>(a.ntg, a.nug);
+    const int sshape = dev_option(kOptScanShape);
+    const bool scan128 = sshape == 4 || (sshape == 0 && nfoot <= 32);
+    const int sthreads = scan128 ? 128 : 256;
+    const int scan_ctas = scan128 ? resident_ctas(k_scan<4, T, 6, 128>, smem_s, &per_sm, 128)
+                        : scan3 ? resident_ctas(k_scan<4, T, 3>, smem_s, &per_sm, 256)
                                 : resident_ctas(k_scan<4, T, 2>, smem_s, &per_sm, 256);
     if (scan_ctas < 1) return cuda_fail(cudaGetLastError(), "k_scan occupancy");
     const int rthreads = rshape == 5 ? 128 : 256;
@@ -349,6 +356,7 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
             return cuda_fail(cudaGetLastError(), "cudaStreamWaitEvent");
         const int skip = dev_option(kOptSkipKernel);
         if (skip == 2) {}
+        else if (scan128) k_scan<4, T, 6, 128><<<scan_ctas < nb ? scan_ctas : nb, sthreads, smem_s, stream>>>(as);
         else if (scan3) k_scan<4, T, 3><<<scan_ctas < nb ? scan_ctas : nb, 256, smem_s, stream>>>(as);
         else k_scan<4, T, 2><<<scan_ctas < nb ? scan_ctas : nb, 256, smem_s, stream>>>(as);
         if (lane) {
