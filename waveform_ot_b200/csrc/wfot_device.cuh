@@ -562,22 +562,6 @@ __device__ __forceinline__ double load_sample(const void* p, int dtype, long lon
                              : (double)reinterpret_cast<const float*>(p)[i];
 }
 
-__device__ __forceinline__ double block_reduce_minmax(double v, bool is_max, double* red) {
-    // red: >= 32 doubles of shared memory; all threads of the block participate
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double o = __shfl_xor_sync(0xffffffffu, v, off);
-        v = is_max ? fmax(v, o) : fmin(v, o);
-    }
-    __syncthreads();
-    if (lane == 0) red[wid] = v;
-    __syncthreads();
-    double r = red[0];
-    for (int i = 1; i < nw; ++i) r = is_max ? fmax(r, red[i]) : fmin(r, red[i]);
-    return r;
-}
-
 // Destination buffers may live in shared or global memory.
 struct PrepOut {
     double2* pn;    // [nt]
@@ -620,10 +604,23 @@ __device__ __forceinline__ void prep_window(const void* t, const void* w, int dt
         mnx = fmin(mnx, p.x); mxx = fmax(mxx, p.x);
         mny = fmin(mny, p.y); mxy = fmax(mxy, p.y);
     }
-    mnx = block_reduce_minmax(mnx, false, red);
-    mxx = block_reduce_minmax(mxx, true, red);
-    mny = block_reduce_minmax(mny, false, red);
-    mxy = block_reduce_minmax(mxy, true, red);   // contains __syncthreads: o.pn visible below
+    {   // the four extrema through ONE pair of block barriers (exact whatever the order); o.pn visible below
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, off));
+            mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, off));
+            mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, off));
+            mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, off));
+        }
+        __syncthreads();
+        if (lane == 0) { red[wid] = mnx; red[8 + wid] = mxx; red[16 + wid] = mny; red[24 + wid] = mxy; }
+        __syncthreads();
+        mnx = red[0]; mxx = red[8]; mny = red[16]; mxy = red[24];
+        for (int i = 1; i < nw; ++i) {
+            mnx = fmin(mnx, red[i]); mxx = fmax(mxx, red[8 + i]); mny = fmin(mny, red[16 + i]); mxy = fmax(mxy, red[24 + i]);
+        }
+    }
     // pixel axes (:91, 95-106)
     double T0, Tl, U0, Ul;
     if (g.has_fpgrid) {
