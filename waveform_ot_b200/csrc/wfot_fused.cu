@@ -221,8 +221,8 @@ static int run_fused(FusedArgs a, void* workspace, size_t workspace_bytes, cudaS
     unsigned char* p = (unsigned char*)base;
     const size_t nslab = csize > 1 ? (size_t)(ctas / csize) : (size_t)ctas;
     a.s_pdf = (double*)p;   p += nslab * npix * 8;
-    a.s_wa = (double*)p;    p += nslab * npix * 8;
-    a.s_wbi = (unsigned long long*)p;
+    p = (unsigned char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    a.s_w = (ulonglong2*)p;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];

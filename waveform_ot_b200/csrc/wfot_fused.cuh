@@ -118,8 +118,9 @@ struct FusedArgs {
     int32_t* dbg_iray;
     unsigned long long* dbg_phase;   // measurement aid (wfot_dev.h): per-phase cycle counters of k_resolve
     // per-CTA scratch slabs
-    // s_wbi: weight of sample idx + 1 with idx in its 16 lowest mantissa bits (pack_wbi)
-    double* s_pdf; double* s_wa; unsigned long long* s_wbi;
+    // s_w: one 16-byte entry per pixel, {weight of sample idx, weight of sample idx + 1 with idx in its 16 lowest
+    // mantissa bits (pack_wbi)}
+    double* s_pdf; ulonglong2* s_w;
     int32_t* status;
     int* next_window;     // global work counters (zeroed by the launcher): [0] fused / scan, [16] resolve
     int cluster;          // > 1: launched as thread-block clusters of this many CTAs, one window per CLUSTER
@@ -230,8 +231,7 @@ __device__ __forceinline__ double store_pixel(const FusedArgs& a, const double2*
     const double wa = far ? wgt : (1.0 - hit.lam) * wgt, wb = far ? 0.0 : hit.lam * wgt;
     if (live) {                        // a shadow lane (row tail) computes and stores nothing
         if (STORE_PDF) a.s_pdf[k] = pdf;
-        a.s_wa[k] = wa;
-        a.s_wbi[k] = pack_wbi(wb, hit.s + (far ? 1 : 0));
+        a.s_w[k] = make_ulonglong2((unsigned long long)__double_as_longlong(wa), pack_wbi(wb, hit.s + (far ? 1 : 0)));
         if (dbg_iray) dbg_iray[(size_t)iu * a.ntg + it] = hit.s;
     }
     return pdf;
@@ -419,7 +419,8 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
 #pragma unroll
                 for (int j = 0; j < P4R; ++j) {      // P4R rows in flight (the slab comes back from DRAM)
                     const size_t k = slab + (size_t)min(iu0 + j, r_hi - 1) * a.ntg + c;
-                    wa[j] = __ldcg(a.s_wa + k); wbi[j] = __ldcg(a.s_wbi + k);
+                    const ulonglong2 e = __ldcg(a.s_w + k);
+                    wa[j] = __longlong_as_double((long long)e.x); wbi[j] = e.y;
                 }
 #pragma unroll
                 for (int j = 0; j < P4R; ++j) unpack_wbi(wbi[j], wb[j], idx[j]);

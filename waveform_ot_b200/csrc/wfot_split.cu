@@ -339,8 +339,7 @@ static int launch_split_t(FusedArgs a, unsigned char* ws, size_t ws_bytes, cudaS
     const int res_grid = (size_t)res_ctas > max_ctas ? (int)max_ctas : res_ctas;
     unsigned char* q = (unsigned char*)p;
     ar.s_pdf = nullptr;      // the resolve kernel sums the density on the fly
-    ar.s_wa = (double*)q;    q += (size_t)res_grid * npix * 8;
-    ar.s_wbi = (unsigned long long*)q;
+    ar.s_w = (ulonglong2*)q;
     as.cluster = ar.cluster = 1;
     int* const counters = a.next_window;             // 64 ints, zeroed by the caller on `stream`
     cudaStream_t rstream = lane ? lane->side : stream;
