@@ -427,17 +427,13 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
 #pragma unroll
                 for (int j = 0; j < P4R; ++j) {
                     if (iu0 + j >= r_hi) break;
-                    if (idx[j] != cur) {
-                        if (idx[j] == cur + 1) {
-                            flush(cur, t0, u0);
-                            t0 = t1; u0 = u1; t1 = 0.0; u1 = 0.0;
-                        } else if (idx[j] == cur - 1) {
-                            flush(cur + 1, t1, u1);
-                            t1 = t0; u1 = u0; t0 = 0.0; u0 = 0.0;
-                        } else {
-                            if (cur >= 0) { flush(cur, t0, u0); flush(cur + 1, t1, u1); }
-                            t0 = t1 = u0 = u1 = 0.0;
-                        }
+                    const int d = idx[j] - cur;
+                    if (d != 0) {      // one body for the three cases (lanes of a warp hit different ones in the same row)
+                        const bool up = d == 1, dn = d == -1;
+                        if (!dn) flush(cur, t0, u0);              // sample cur is complete unless the run moved down
+                        if (!up) flush(cur + 1, t1, u1);          // sample cur + 1 is complete unless it moved up
+                        const double c0 = up ? t1 : 0.0, c1 = up ? u1 : 0.0, c2 = dn ? t0 : 0.0, c3 = dn ? u0 : 0.0;
+                        t0 = c0; u0 = c1; t1 = c2; u1 = c3;
                         cur = idx[j];
                     }
                     const double cu = s_Ru[iu0 + j];
