@@ -335,11 +335,14 @@ def secondary_configs(dev):
     tsh, amp = np.linspace(-4, 4, 512), np.linspace(0.2, 4, 512)
     adapters.misfit_surface(tsh[:8], amp[:8], 1.0, tgt3, grid3, 0.03)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    adapters.misfit_surface(tsh, amp, 1.0, tgt3, grid3, 0.03)
-    dt3 = time.perf_counter() - t0
+    dt3 = 1e30
+    for _ in range(2):      # best of two (the first full-size call also pays the allocations)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        adapters.misfit_surface(tsh, amp, 1.0, tgt3, grid3, 0.03)
+        dt3 = min(dt3, time.perf_counter() - t0)
     out["cfg3_surface_512x512_W1_and_W2"] = {"models": 512 * 512, "seconds": dt3, "models_per_s": 512 * 512 / dt3,
-                                            "note": "wall clock incl. on-device forward model, 2 fused passes (W1, W2), D2H"}
+                                            "note": "wall clock incl. on-device forward model, 2 fused passes (W1, W2), D2H; best of 2 calls"}
     # cfg1 latency: ONE Ricker evaluation (misfit + gradient w.r.t. the 3 model parameters) through the adapter
     # a scipy.optimize loop would call, host in / host out, forward model included (ricker_util.optfunc)
     data = [tgt3, "W2", (-2.0, 2.0), grid3, 0.03, False, 0.5, 45.0]
