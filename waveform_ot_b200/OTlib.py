@@ -119,18 +119,64 @@ class OTpdf(object):
         self.calcmarg = True
         self.ProjNum = -1
 
+    @classmethod
+    def _from_device_marginal(cls, raw_dev, x):
+        """A 1-D OTpdf over a marginal that is already on the device (setMarginals): nothing is launched or copied
+        here.  wasser() feeds `_raw_dev` to the 1-D OT kernel, which normalises and builds the CDF itself; the
+        attributes of the reference object (amp, pdf, cdf: libs/OTlib.py:92-93,112-114) are produced by the same
+        kernel as in __init__ the first time one of them is read.  A marginal of a density that passed the sign
+        check (:91) has no negative entry, so there is nothing to raise here."""
+        self = cls.__new__(cls)
+        self.ndim = 1
+        self.nproj = 0
+        self._raw_dev = raw_dev
+        self.n = int(raw_dev.numel())
+        self.type = '1D'
+        if self.n != len(x):                                          # :109-110
+            raise PDFShapeError
+        self.x = x.copy()                                             # :94
+        self.calcproj = True
+        self.calcmarg = True
+        self.ProjNum = -1
+        return self
+
+    def _materialise_1d(self):
+        r = _B.otpdf1d_batch(self._raw_dev.reshape(1, -1))
+        _sync()
+        self.__dict__["amp"] = float(r["amp"][0])
+        self._pdf = r["pdf"][0].cpu().numpy()
+        self._cdf = r["cdf"][0].cpu().numpy()
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails: the lazily produced attributes of a device marginal
+        d = self.__dict__
+        if d.get("_raw_dev") is not None and d.get("type") == '1D':
+            if name == "_raw":
+                d["_raw"] = d["_raw_dev"].reshape(-1).cpu().numpy()
+                return d["_raw"]
+            if name == "amp":
+                self._materialise_1d()
+                return d["amp"]
+        raise AttributeError(name)
+
     @property
     def pdf(self):
-        if not hasattr(self, "_pdf"):
-            self._pdf = self._raw / self.amp                          # :93 (attribute shaping only)
+        if "_pdf" not in self.__dict__:
+            if self.type == '1D' and self.__dict__.get("_raw_dev") is not None:
+                self._materialise_1d()
+            else:
+                self._pdf = self._raw / self.amp                      # :93 (attribute shaping only)
         return self._pdf
 
     @property
     def cdf(self):
-        if not hasattr(self, "_cdf"):                                 # 2-D: flattened CDF nobody reads (:112-114)
-            r = _B.otpdf1d_batch(self._raw.reshape(1, -1))
-            _sync()
-            self._cdf = r["cdf"][0].cpu().numpy()
+        if "_cdf" not in self.__dict__:
+            if self.type == '1D' and self.__dict__.get("_raw_dev") is not None:
+                self._materialise_1d()
+            else:                                                     # 2-D: flattened CDF nobody reads (:112-114)
+                r = _B.otpdf1d_batch(self._raw.reshape(1, -1))
+                _sync()
+                self._cdf = r["cdf"][0].cpu().numpy()
         return self._cdf
 
     def setSliced(self, Nproj, org):
@@ -166,18 +212,29 @@ class OTpdf(object):
         if self.type != '2D':
             raise TargetSource2DShapeError
         self.nproj = 2
-        f0 = self._marg_dev[0][0].cpu().numpy()                       # :155 (sum over rows of pdf/amp)
-        f1 = self._marg_dev[1][0].cpu().numpy()                       # :156
-        self.marg = [OTpdf((f0, self.x[0, :, 0])), OTpdf((f1, self.x[:, 0, 1]))]   # :157-160
+        if self.__dict__.get("_marg_dev") is None:                    # un-pickled object: the device sums are gone
+            self._marg_dev = _marg_of(self._raw)
+        # :155-160: sums over rows / columns of pdf/amp, each wrapped as a 1-D OTpdf; the sums stay on the device
+        self.marg = [OTpdf._from_device_marginal(self._marg_dev[0][0], self.x[0, :, 0]),
+                     OTpdf._from_device_marginal(self._marg_dev[1][0], self.x[:, 0, 1])]
         self.angles = np.array([0.0, np.pi / 2.])
         self.calcmarg = False
 
     def __getstate__(self):
+        if self.__dict__.get("_raw_dev") is not None and self.type == '1D':
+            self._raw                                                 # host copy of a device marginal
+            self.pdf                                                  # amp, pdf, cdf
         st = dict(self.__dict__)
         st.pop("_marg_dev", None)
         st["_proj"] = None
         st["_raw_dev"] = None
         return st
+
+
+def _marg_of(f):
+    r = _B.marginals_batch(f)
+    _sync()
+    return (r["marg_t"], r["marg_u"])
 
 
 def _checkdistfunc(distfunc):
@@ -203,7 +260,9 @@ def wasser(source, target, distfunc='W12', proj=-1, returnplan=False, derivative
         raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,) "
                          % (source.n, target.n, source.n))
     name = 'W12' if (calcW1 and calcW2) else ('W1' if calcW1 else 'W2')
-    r = _B.ot1d_batch(source._raw, target._raw, source.x, target.x, name, derivatives=derivatives,
+    fsrc = source._raw_dev if source.__dict__.get("_raw_dev") is not None else source._raw
+    gtgt = target._raw_dev if target.__dict__.get("_raw_dev") is not None else target._raw
+    r = _B.ot1d_batch(fsrc, gtgt, source.x, target.x, name, derivatives=derivatives,
                       want_cdf=returnplan, want_merge=returnplan)
     _sync()
     st = r["status"].read()
