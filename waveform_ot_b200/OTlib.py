@@ -269,16 +269,17 @@ def wasser(source, target, distfunc='W12', proj=-1, returnplan=False, derivative
     if (derivatives or checkCommonCDF) and st[1] and not ignoreCommonCDFerror:      # :663-666
         cset = np.intersect1d(target.cdf[:-1], source.cdf[:-1])
         raise TargetSourceCDFError(cset)
-    W = r["W"][0].cpu().numpy()
+    Wd = r["W_dpos"].cpu().numpy()                                    # [W | dpos] of the one pair
+    W, dpos = Wd[0, 0], Wd[1, 0]
     out = []
     if calcW1:
         out += [W[0]]
         if derivatives:
-            out += [r["dW1"][0].cpu().numpy(), r["dpos"][0, 0].item()]
+            out += [r["dW1"][0].cpu().numpy(), float(dpos[0])]
     if calcW2:
         out += [W[1]]
         if derivatives:
-            out += [r["dW2"][0].cpu().numpy(), r["dpos"][0, 1].item()]
+            out += [r["dW2"][0].cpu().numpy(), float(dpos[1])]
     if returnplan:
         out += _transport_plan(r, source, target, derivatives)
     return out

@@ -20,13 +20,23 @@ GRID_DTYPE = np.dtype([("t0", "f8"), ("t1", "f8"), ("u0", "f8"), ("u1", "f8"),
 assert GRID_DTYPE.itemsize == ctypes.sizeof(C.wfot_grid)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)   # the handle without building a Stream object
+_cuda_checked = False
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device (what every C-ABI call is queued on)."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def _device():
-    if not torch.cuda.is_available():
-        raise RuntimeError("waveform_ot_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    global _cuda_checked
+    if not _cuda_checked:      # asked once per process: torch.cuda.is_available() costs microseconds on every call
+        if not torch.cuda.is_available():
+            raise RuntimeError("waveform_ot_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        _cuda_checked = True
     return torch.device("cuda", torch.cuda.current_device())
 
 
@@ -196,8 +206,9 @@ def ot1d_batch(f, g, xf, xg, distfunc="W12", derivatives=False, want_cdf=False, 
     xg = _as_device(xg, torch.float64)
     pmask = {"W1": C.W1, "W2": C.W2, "W12": C.W12}[distfunc]
     f64 = dict(dtype=torch.float64, device=dev)
-    W = torch.zeros((B, 2), **f64)
-    dpos = torch.zeros((B, 2), **f64) if derivatives else None
+    Wd = torch.zeros((2, B, 2), **f64)      # W and dpos side by side: one device -> host copy brings both
+    W = Wd[0]
+    dpos = Wd[1] if derivatives else None
     dW1 = torch.empty((B, n), **f64) if derivatives and pmask & 1 else None
     dW2 = torch.empty((B, n), **f64) if derivatives and pmask & 2 else None
     amp = torch.empty(B, **f64)
@@ -212,7 +223,7 @@ def ot1d_batch(f, g, xf, xg, distfunc="W12", derivatives=False, want_cdf=False, 
         C.ptr(W), C.ptr(dW1), C.ptr(dW2), C.ptr(dpos), C.ptr(amp), C.ptr(cdf_f), C.ptr(cdf_g),
         C.ptr(merge), C.ptr(st.t), _stream()), "wfot_ot1d_batch")
     return dict(W=W, dW1=dW1, dW2=dW2, dpos=dpos, amp=amp, cdf_f=cdf_f, cdf_g=cdf_g, merge_order=merge,
-                status=st, _keepalive=(f, g, xf, xg))
+                status=st, W_dpos=Wd, _keepalive=(f, g, xf, xg))
 
 
 def plan_batch(r, n, m, perm_f=None, perm_g=None, accumulate=False, derivatives=False):
