@@ -70,3 +70,43 @@ def test_unmodified_optfunc_raises_on_identical_windows(ref_over_shim, golden):
     ru.ricker_util_opt.init()
     with pytest.raises(OT.TargetSourceCDFError):
         ru.optfunc(np.array([0.0, 1.6, 1.0]), [tgt, "W2", [-2.0, 2.0], grid, lam, False, 0.5, 45.0])
+
+
+@pytest.mark.parametrize("transform", [False, True])
+def test_unmodified_fd_checkers_over_shim(ref_over_shim, transform):
+    """The reference's own finite-difference checkers (libs/ricker_util.py:554-606), unmodified, running over the shim:
+    the walk-through of Ricker_waveform_derivatives.ipynb (cells 7-15, 31-50).  Analytic derivatives -
+    MargWasserstein(derivatives, returnmargW) -> PDFderivMarg -> (arctan chain) -> dudm.dot - against central differences
+    of the misfit itself: a check that needs no oracle.  The notebook's own table agrees to ~7 digits for dW/du and
+    for the origin-time parameter, and to 3-4 digits for the amplitude marginal's dW/dm (its FD step is coarse)."""
+    ru, OT = ref_over_shim
+    trange = [-2.0, 2.0]
+    mstart = np.array([5.0, 3.0, 0.5])                                             # cell 7
+    tpred, wpred, dudm = ru.rickerwavelet(mstart[0], mstart[1], mstart[2], trange=trange, deriv=True)   # cell 44
+    tobs, wobs = ru.rickerwavelet(0.0, 1.6, 1.0, trange=trange)                    # noiseless observed wavelet
+    lam, theta = 0.03, 45.0                                                        # cell 12
+    grid = (trange[0], trange[1], -0.8, 1.8, 80, 512) if transform else (trange[0], trange[1], -2.0, 3.5, 80, 512)
+    wfobs, tgt = ru.BuildOTobjfromWaveform(tobs, wobs, grid, lambdav=lam, transform=transform, theta=theta)   # cell 15
+    wfpred, src = ru.BuildOTobjfromWaveform(tpred, wpred, grid, lambdav=lam, deriv=True, transform=transform, theta=theta)
+    w, dwdpbar, dwdt0 = OT.MargWasserstein(src, tgt, derivatives=True, distfunc="W2", returnmargW=True)   # cell 31
+    wfpred.PDFderivMarg(dwdpbar)                                                   # cell 38
+    gt, gu = wfpred.pdfdMarg[0].copy(), wfpred.pdfdMarg[1].copy()
+    if transform:
+        un, dundu = ru.arctan_trans(wpred, grid[2], grid[3], deriv=True)
+        gt, gu = gt * dundu, gu * dundu
+    # cell 41: d(Wt, Wu)/du at waveform points, 0.001 % central differences
+    scale_t, scale_u = np.abs(gt).max(), np.abs(gu).max()
+    for k in (23, 29, 44, 103, 177):
+        fdt, fdu = ru.check_dwduFD(k, tpred, wpred, 0.001, grid, lam, tgt, transform=transform, theta=theta)
+        assert fdt == pytest.approx(gt[k], rel=2e-5, abs=2e-7 * scale_t)
+        assert fdu == pytest.approx(gu[k], rel=2e-5, abs=2e-7 * scale_u)
+    # cells 48-50: d(Wt, Wu)/d(t0, A, f)
+    dwtdm, dwudm = dudm.dot(gt), dudm.dot(gu)
+    dwtdm[0] = dwdt0[0] / (wfpred.tant * (wfpred.tlim[1] - wfpred.tlim[0]))
+    dwudm[0] = dwdt0[1] / (wfpred.tant * (wfpred.tlim[1] - wfpred.tlim[0]))
+    fdt, fdu = ru.check_dwdmFD(0, tpred, wpred, 0.00001, mstart, grid, lam, tgt, trange, transform=transform, theta=theta)
+    assert fdt == pytest.approx(dwtdm[0], rel=1e-6)
+    assert abs(fdu) <= 1e-9 and dwudm[0] == 0.0
+    for k in (1, 2):
+        fdt, fdu = ru.check_dwdmFD(k, tpred, wpred, 0.00001, mstart, grid, lam, tgt, trange, transform=transform, theta=theta)
+        assert fdu == pytest.approx(dwudm[k], rel=5e-3)
