@@ -3,7 +3,8 @@ that has neither /root/reference nor matplotlib.
 
     python oracle/build_ref.py            # in the build container (needs /root/reference)
 
-copies libs/{__init__,FingerprintLib,OTlib,ricker_util,ricker_util_opt,myGP}.py byte for byte into the
+copies libs/{__init__,FingerprintLib,OTlib,ricker_util,ricker_util_opt,myGP,loc_cmt_util,loc_cmt_util_opt}.py byte
+for byte into the
 git-ignored oracle/_ref/libs/ (nothing is edited; `cmp` against the originals is part of the recipe) and
 writes inert stub packages for the plotting imports those modules make at module scope (matplotlib, pylab,
 mpl_toolkits: libs/FingerprintLib.py:15-18, libs/OTlib.py:18, libs/ricker_util.py:11-13).  oracle/_ref/ is
@@ -11,7 +12,8 @@ listed in .gitignore (reference sources never enter the history) but not in .gpu
 the GPU box with the snapshot like the built libwfot.so.
 
 Users: bench.py (`--impl reference` and the `cpu_baseline` leg: kind "reference") and
-tests/test_gpu_dropin.py (the unmodified libs.ricker_util.optfunc running over the B200 shim).  Like the rest
+tests/test_gpu_dropin.py (the unmodified libs.ricker_util.optfunc and libs.loc_cmt_util.optfunc_OT running over the
+B200 shim; loc_cmt_util imports the third-party pyprop8, absent from the image: oracle/pyprop8_stub.py).  Like the rest
 of oracle/ it is test / measurement infrastructure: the product never imports it.
 """
 import filecmp
@@ -22,7 +24,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
 DST = os.path.join(HERE, "_ref")
-MODULES = ["__init__.py", "FingerprintLib.py", "OTlib.py", "ricker_util.py", "ricker_util_opt.py", "myGP.py"]
+MODULES = ["__init__.py", "FingerprintLib.py", "OTlib.py", "ricker_util.py", "ricker_util_opt.py", "myGP.py",
+           "loc_cmt_util.py", "loc_cmt_util_opt.py"]
 
 STUB = '''"""Inert stand-in for a plotting package the reference imports at module scope (written by
 oracle/build_ref.py; never used by the hot path)."""
@@ -105,6 +108,20 @@ def import_reference():
     OT = importlib.import_module("libs.OTlib")
     ru = importlib.import_module("libs.ricker_util")
     return fp, OT, ru
+
+
+def import_cmt():
+    """-> the unmodified libs.loc_cmt_util of oracle/_ref, bound to whatever libs.FingerprintLib / libs.OTlib are
+    installed in sys.modules at this point (the reference's own after import_reference(), the B200 shim after
+    adapters.install("libs")).  pyprop8 (libs/loc_cmt_util.py:9,12) is replaced by oracle/pyprop8_stub.py if absent."""
+    import importlib
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import pyprop8_stub
+    pyprop8_stub.install()
+    for k in ("libs.loc_cmt_util", "libs.loc_cmt_util_opt"):
+        sys.modules.pop(k, None)
+    return importlib.import_module("libs.loc_cmt_util")
 
 
 if __name__ == "__main__":

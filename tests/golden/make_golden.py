@@ -219,3 +219,46 @@ def sliced_avgplan():
 
 if __name__ == "__main__" and (len(sys.argv) == 1 or sys.argv[1] == "avgplan"):
     sliced_avgplan()
+
+
+def cmt_optfunc():
+    """(9) the reference's CMT misfit function, UNMODIFIED (libs/loc_cmt_util.py:186-306 `optfunc_OT` with its
+    BuildOTobjfromWaveform / CalcWasserWaveform / arctan_trans / buildFingerprintwindows, :430-587), over the unmodified
+    FingerprintLib / OTlib: 4 stations x 3 components x 61 samples set up as the CMT notebook does
+    (oracle/cmt_scenario.py); pyprop8 is absent from the image, oracle/pyprop8_stub.py stands in for it.
+    Run on its own:  python tests/golden/make_golden.py cmt"""
+    import importlib
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import cmt_scenario, pyprop8_stub
+    pyprop8_stub.install()
+    cmt = importlib.import_module("libs.loc_cmt_util")
+    out = {}
+    for c in (False, True):
+        tag = "cmt" if c else "loc"
+        optdata, t = cmt_scenario.build_optdata(cmt, cmt=c)
+        models = cmt_scenario.trial_models(cmt, cmt=c)
+        out[tag + "_models"] = np.array(models)
+        out[tag + "_obs"] = optdata["prop8data"]["obs_seis"]
+        out[tag + "_grids"] = np.array(optdata["OTdata"]["obs_grids"], dtype=np.float64)
+        mis, dmis, seis, jac, drs = [], [], [], [], []
+        for m in models:
+            a, b, tt, s = cmt.optfunc_OT(m, optdata, returnseis=True)                 # Wopt = 'Wavg' (notebook cell 34)
+            mis.append(a); dmis.append(b); seis.append(s)
+            a2, b2, dxyz, dr = cmt.optfunc_OT(m, optdata, returnderiv=True)            # + d(seis)/d(model), dW/d(seis)
+            assert a2 == a
+            jac.append(dxyz.reshape(dxyz.shape[0], -1)); drs.append(dr)
+        out[tag + "_mis"], out[tag + "_dmis"], out[tag + "_seis"] = np.array(mis), np.array(dmis), np.array(seis)
+        out[tag + "_J"], out[tag + "_dr"] = np.array(jac), np.array(drs)               # (M, P, nr*nc*nt), (M, nr, nc, nt)
+        a, b = cmt.optfunc_OT(models[0], optdata, return2W=True)                       # both marginals
+        out[tag + "_mis2W"], out[tag + "_dmis2W"] = np.array(a), np.array(b)
+        for w in ("Wt", "Wu"):
+            optdata["OTdata"]["Wopt"] = w
+            a, b = cmt.optfunc_OT(models[1], optdata)
+            out[tag + "_mis" + w], out[tag + "_dmis" + w] = np.array(a), np.array(b)
+        optdata["OTdata"]["Wopt"] = "Wavg"
+    np.savez_compressed(os.path.join(HERE, "cmt_optfunc.npz"), **out)
+    print("cmt_optfunc", {k: np.shape(v) for k, v in out.items()})
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or sys.argv[1] == "cmt"):
+    cmt_optfunc()

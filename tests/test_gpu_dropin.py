@@ -110,3 +110,40 @@ def test_unmodified_fd_checkers_over_shim(ref_over_shim, transform):
     for k in (1, 2):
         fdt, fdu = ru.check_dwdmFD(k, tpred, wpred, 0.00001, mstart, grid, lam, tgt, trange, transform=transform, theta=theta)
         assert fdu == pytest.approx(dwudm[k], rel=5e-3)
+
+
+@pytest.mark.parametrize("cmt", [False, True])
+def test_unmodified_loc_cmt_util_optfunc_OT_over_shim(ref_over_shim, golden, cmt):
+    """The reference's CMT misfit function, UNMODIFIED (libs/loc_cmt_util.py:186-306 optfunc_OT with its own
+    BuildOTobjfromWaveform / CalcWasserWaveform / arctan_trans / buildFingerprintwindows, :430-587), running over the
+    shim: 4 stations x 3 components x 61 samples, 79 x 61 grids, arctan transform, source location only (3 parameters)
+    and location + moment tensor (9), Wopt = Wavg / Wt / Wu and both marginals.  Expected values:
+    tests/golden/cmt_optfunc.npz, produced by the same calls on the unmodified reference end to end
+    (make_golden.py cmt).  pyprop8 is absent from the image: oracle/pyprop8_stub.py generates the seismograms and
+    Jacobians on both sides (the fixture holds them too, as a check that both sides saw the same input)."""
+    ru, OT = ref_over_shim
+    from oracle import build_ref, cmt_scenario
+    cmtu = build_ref.import_cmt()
+    assert cmtu.OT is OT and os.path.realpath(cmtu.__file__).startswith(os.path.realpath(os.path.join(ROOT, "oracle", "_ref")))
+    g = golden("cmt_optfunc")
+    tag = "cmt" if cmt else "loc"
+    optdata, t = cmt_scenario.build_optdata(cmtu, cmt=cmt)
+    np.testing.assert_allclose(optdata["prop8data"]["obs_seis"], g[tag + "_obs"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(np.array(optdata["OTdata"]["obs_grids"], dtype=np.float64), g[tag + "_grids"], rtol=1e-12)
+    models = cmt_scenario.trial_models(cmtu, cmt=cmt)
+    np.testing.assert_allclose(np.array(models), g[tag + "_models"], rtol=1e-14)
+    for i, m in enumerate(models):
+        mis, dmis, tt, seis = cmtu.optfunc_OT(m, optdata, returnseis=True)
+        np.testing.assert_allclose(seis, g[tag + "_seis"][i], rtol=1e-12, atol=1e-15)
+        assert mis == pytest.approx(float(g[tag + "_mis"][i]), rel=1e-9)
+        scale = np.abs(g[tag + "_dmis"][i]).max()
+        np.testing.assert_allclose(dmis, g[tag + "_dmis"][i], rtol=1e-6, atol=1e-8 * scale)
+    mis, dmis = cmtu.optfunc_OT(models[0], optdata, return2W=True)
+    np.testing.assert_allclose(mis, g[tag + "_mis2W"], rtol=1e-9)
+    np.testing.assert_allclose(np.array(dmis), g[tag + "_dmis2W"], rtol=1e-6, atol=1e-8 * np.abs(g[tag + "_dmis2W"]).max())
+    for w in ("Wt", "Wu"):
+        optdata["OTdata"]["Wopt"] = w
+        mis, dmis = cmtu.optfunc_OT(models[1], optdata)
+        assert mis == pytest.approx(float(g[tag + "_mis" + w]), rel=1e-9)
+        np.testing.assert_allclose(dmis, g[tag + "_dmis" + w], rtol=1e-6, atol=1e-8 * np.abs(g[tag + "_dmis" + w]).max())
+    assert len(cmtu.loc_cmt_util_opt.opt_history_data) == len(models) + 3          # the reference's history side effect

@@ -158,6 +158,34 @@ def test_cmt_models_adapter(mods):
         np.testing.assert_allclose(dmis[m], J[m].dot(drm.reshape(-1)), rtol=1e-5, atol=1e-7 * np.abs(dmis[m]).max())
 
 
+@pytest.mark.parametrize("tag", ["loc", "cmt"])
+def test_cmt_models_adapter_vs_reference_golden(mods, golden, tag):
+    """The batched CMT loop (one fused launch for all models x stations x components, in-kernel arctan transform,
+    Jacobian chain) against what the UNMODIFIED libs/loc_cmt_util.optfunc_OT (:186-306) returned on the unmodified
+    reference for the same seismograms and Jacobians (tests/golden/cmt_optfunc.npz, make_golden.py cmt):
+    misfit, d(misfit)/d(model) for 3 (location) and 9 (location + moment tensor) parameters, d(misfit)/d(seismogram)."""
+    fp, OT, adapters = mods
+    g = golden("cmt_optfunc")
+    seis, J, obs = g[tag + "_seis"], g[tag + "_J"], g[tag + "_obs"]
+    M, nr, nc, nt = seis.shape
+    t = np.arange(float(nt))
+    grids = [[list(g[tag + "_grids"][i, j][:4]) + [int(g[tag + "_grids"][i, j][4]), int(g[tag + "_grids"][i, j][5])]
+              for j in range(nc)] for i in range(nr)]
+    assert grids == [[list(x) for x in row] for row in adapters.buildFingerprintwindows(t, obs)]      # :430-446
+    lam = 0.04
+    targets = adapters.make_targets_models(t, obs, grids, lam)                                       # :237-249,576-587
+    mis, dmis, dr = adapters.misfit_grad_models(t, seis, grids, targets, lam, J=J)
+    np.testing.assert_allclose(mis, g[tag + "_mis"], rtol=1e-9)
+    for m in range(M):
+        np.testing.assert_allclose(dr[m].reshape(nr, nc, nt), g[tag + "_dr"][m], rtol=1e-6,
+                                   atol=1e-8 * np.abs(g[tag + "_dr"][m]).max())
+        np.testing.assert_allclose(dmis[m], g[tag + "_dmis"][m], rtol=1e-6, atol=1e-8 * np.abs(g[tag + "_dmis"][m]).max())
+    for w in ("Wt", "Wu"):
+        mis, dmis, _ = adapters.misfit_grad_models(t, seis[1:2], grids, targets, lam, J=J[1:2], Wopt=w)
+        assert mis[0] == pytest.approx(float(g[tag + "_mis" + w]), rel=1e-9)
+        np.testing.assert_allclose(dmis[0], g[tag + "_dmis" + w], rtol=1e-6, atol=1e-8 * np.abs(g[tag + "_dmis" + w]).max())
+
+
 def test_ricker_forward_batch_golden(mods, golden):
     """wfot_ricker_batch against the reference's rickerwavelet(..., deriv=True) (libs/ricker_util.py:38-89):
     sample times bit-exact, amplitudes / derivatives to a few ulp (CUDA exp vs libm exp)."""

@@ -171,3 +171,26 @@ def test_sliced_wasserstein_and_plan_fixture(golden):
                  returnplan=True)
     np.testing.assert_allclose(w[3], g["plan_H"], atol=1e-15)
     np.testing.assert_allclose(w[4], g["plan_dH"], atol=1e-14)
+
+
+@pytest.mark.parametrize("tag,m", [("loc", 0), ("cmt", 2)])
+def test_cmt_optfunc_fixture(golden, tag, m):
+    """The oracle's CMT adapter composition (arctan window per station/component -> fingerprint -> marginal W2 -> chain
+    to the seismogram and on to the model parameters) against what the UNMODIFIED libs/loc_cmt_util.optfunc_OT
+    (:186-306) returned on the unmodified reference: tests/golden/cmt_optfunc.npz (make_golden.py cmt)."""
+    g = golden("cmt_optfunc")
+    seis, J, obs, grids = g[tag + "_seis"][m], g[tag + "_J"][m], g[tag + "_obs"], g[tag + "_grids"]
+    nr, nc, nt = seis.shape
+    t = np.arange(float(nt))
+    tot, dr = 0.0, np.zeros((nr, nc, nt))
+    for i in range(nr):
+        for j in range(nc):
+            grid = tuple(grids[i, j][:4]) + (int(grids[i, j][4]), int(grids[i, j][5]))
+            assert list(grid) == list(O.build_fingerprint_window(t, obs[i, j]))                    # :430-446
+            _, tgt = O.build_ot_from_waveform(t, obs[i, j], grid, lambdav=0.04, transform=True)
+            W, d, dg, _, _ = O.misfit_grad_window(t, seis[i, j], grid, tgt, lambdav=0.04, transform=True, adapter="cmt")
+            tot += 0.5 * (W[0] + W[1])                                                             # Wopt = 'Wavg'
+            dr[i, j] = 0.5 * (d[0] + d[1])
+    assert tot == pytest.approx(float(g[tag + "_mis"][m]), rel=1e-12)
+    np.testing.assert_allclose(dr, g[tag + "_dr"][m], rtol=1e-9, atol=1e-12 * np.abs(dr).max())
+    np.testing.assert_allclose(J.dot(dr.reshape(-1)), g[tag + "_dmis"][m], rtol=1e-9, atol=1e-12 * np.abs(g[tag + "_dmis"][m]).max())
