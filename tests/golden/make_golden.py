@@ -262,3 +262,29 @@ def cmt_optfunc():
 
 if __name__ == "__main__" and (len(sys.argv) == 1 or sys.argv[1] == "cmt"):
     cmt_optfunc()
+
+
+def fd_checkers():
+    """(10) the finite-difference checkers the derivative notebook calls directly on the two modules:
+    fp.check_FDderiv (libs/FingerprintLib.py:516-572, Ricker_waveform_derivatives.ipynb cell 31) and
+    OT._checkderivMarg (libs/OTlib.py:330-393, cell 36), on the notebook's noiseless Ricker pair.
+    Run on its own:  python tests/golden/make_golden.py fd"""
+    trange = [-2.0, 2.0]
+    tp, wp = ru.rickerwavelet(5.0, 3.0, 0.5, trange=trange)                       # cell 7
+    to, wo = ru.rickerwavelet(0.0, 1.6, 1.0, trange=trange)
+    grid, lam = (-2.0, 2.0, -2.0, 3.5, 80, 512), 0.03                             # cell 12
+    wfo, tgt = ru.BuildOTobjfromWaveform(to, wo, grid, lambdav=lam)
+    wfp, src = ru.BuildOTobjfromWaveform(tp, wp, grid, lambdav=lam, deriv=True)
+    ks = np.array([6302, 11236, 14513, 22195, 30191, 34237, 39605])               # grid points of the notebook's table
+    fd = np.array([fp.check_FDderiv(wfp, int(k)) for k in ks])                    # (segment, d/du_i, d/du_i+1)
+    marg = np.array([OT._checkderivMarg(src, tgt, 0.5, distfunc='W2', percent=True, ind=[int(k)], returnmargW=True)
+                     for k in ks], dtype=np.float64)
+    avg = np.array([OT._checkderivMarg(src, tgt, 0.5, distfunc='W2', percent=True, ind=[int(k)]) for k in ks[:3]],
+                   dtype=np.float64)
+    np.savez(os.path.join(HERE, "fd_checkers.npz"), tp=tp, wp=wp, to=to, wo=wo, grid=np.array(grid, dtype=np.float64),
+             lam=lam, ks=ks, fd=fd, dddy=wfp.dddy[ks], marg=marg, avg=avg)
+    print("fd_checkers", fd, marg, avg, sep="\n")
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or sys.argv[1] == "fd"):
+    fd_checkers()

@@ -394,3 +394,33 @@ def test_fused_adapters_raise_reference_exceptions(mods, golden):
     wf = fp.waveformFP(t, w, gz)
     with pytest.warns(RuntimeWarning, match="zero distance"):
         wf.calcpdf(lambdav=0.1, deriv=True)
+
+
+def test_fd_checkers_golden(mods, golden):
+    """The finite-difference checkers the derivative notebook calls on the two modules themselves
+    (Ricker_waveform_derivatives.ipynb cells 31, 36): fp.check_FDderiv (libs/FingerprintLib.py:516-572) and
+    OT._checkderivMarg (libs/OTlib.py:330-393), against what the unmodified reference returned for the same grid
+    points (tests/golden/fd_checkers.npz, make_golden.py fd) and against the analytic derivatives."""
+    fp, OT, adapters = mods
+    g = golden("fd_checkers")
+    grid, lam = _grid(g), float(g["lam"])
+    wfo = fp.waveformFP(g["to"], g["wo"], grid); wfo.calcpdf(lambdav=lam)
+    tgt = OT.OTpdf((wfo.pdf, wfo.pos))
+    wfp = fp.waveformFP(g["tp"], g["wp"], grid); wfp.calcpdf(lambdav=lam, deriv=True)
+    src = OT.OTpdf((wfp.pdf, wfp.pos))
+    w, dwdpbar, dwdt0 = OT.MargWasserstein(src, tgt, derivatives=True, distfunc='W2', returnmargW=True)
+    for n, k in enumerate(g["ks"]):
+        i, d0, d1 = fp.check_FDderiv(wfp, int(k))
+        assert i == int(g["fd"][n, 0])
+        np.testing.assert_allclose([d0, d1], g["fd"][n, 1:], rtol=1e-7, atol=1e-11)
+        np.testing.assert_allclose(wfp.dddy[int(k)], g["dddy"][n], rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose([d0, d1], wfp.dddy[int(k)], rtol=2e-2, atol=1e-5)          # FD vs analytic (cell 31; the
+        #                                                                                        reference's own step gives ~1 %)
+        f0, f1 = OT._checkderivMarg(src, tgt, 0.5, distfunc='W2', percent=True, ind=[int(k)], returnmargW=True)
+        np.testing.assert_allclose([f0, f1], g["marg"][n], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose([f0, f1], [dwdpbar[0].flatten()[int(k)], dwdpbar[1].flatten()[int(k)]],
+                                   rtol=1e-4, atol=1e-9)                                      # FD vs analytic (cell 36)
+    for n, k in enumerate(g["ks"][:3]):
+        fa = OT._checkderivMarg(src, tgt, 0.5, distfunc='W2', percent=True, ind=[int(k)])
+        assert fa == pytest.approx(float(g["avg"][n]), rel=1e-6)
+    assert OT._checkderivMarg(src, tgt, 0.5, ind=[0], dffloor=10.0, returnmargW=True) == (None, None)   # :393

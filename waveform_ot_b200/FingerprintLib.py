@@ -9,7 +9,8 @@ can be stored in the adapters' history lists and pickled like the reference's.
 
 Out of scope (raise NotImplementedError): method='FMM' / 'NNsearch'
 (libs/FingerprintLib.py:139-152,160-164; marked obsolete by the reference,
-unused by every notebook), plotting helpers and finite-difference checkers.
+unused by every notebook) and the plotting helpers.  The finite-difference checker the derivative notebook calls
+(check_FDderiv, libs/FingerprintLib.py:516-572) is provided on top of the GPU distance field.
 """
 from __future__ import annotations
 
@@ -218,3 +219,31 @@ class waveformFP(object):
 
     def __setstate__(self, st):
         self.__dict__.update(st)
+
+
+def check_FDderiv(wf, k, du=0.001, verbose=False):
+    """libs/FingerprintLib.py:516-572 (Ricker_waveform_derivatives.ipynb cell 31): central finite differences of the
+    distance at grid point k with respect to the amplitudes of the two samples that bound its nearest segment.
+    Returns (segment, d d[k]/d u_segment, d d[k]/d u_segment+1).  Each of the four perturbed windows is one call of
+    the distance-field kernel (the reference evaluates all grid points too, wavedistv :456-474, and reads point k);
+    like the reference, the perturbed objects are built on (tlim, ulim) without the fpgrid of `wf`."""
+    t, RF = wf.p.T[0], wf.p.T[1]
+    u0, u1 = wf.ulim
+    t0, t1 = wf.tlim
+    i = int(wf.irays[k])
+    dups = du * np.abs(RF[i])                                        # :527
+
+    def dist_at_k(j, sign):
+        RFq = np.copy(RF)
+        RFq[j] += sign * dups
+        wq = waveformFP(t, RFq, (t0, t1, u0, u1, wf.nug, wf.ntg), tantheta=wf.tant)
+        wq.wdist()
+        return wq.dfield.reshape(-1)[k], int(wq.irays[k])
+
+    (dp0, ip0), (dm0, im0) = dist_at_k(i, +1.0), dist_at_k(i, -1.0)
+    (dp1, ip1), (dm1, im1) = dist_at_k(i + 1, +1.0), dist_at_k(i + 1, -1.0)
+    dddy0fd = (dp0 - dm0) / (2 * dups)                               # :544
+    dddy1fd = (dp1 - dm1) / (2 * dups)                               # :560
+    if verbose:
+        print('\n segments after FD perturbation : ', ' pos 0 ', ip0, ' minus 0', im0, 'pos 1 ', ip1, ' minus 1', im1)
+    return i, dddy0fd, dddy1fd

@@ -296,6 +296,47 @@ def _transport_plan(r, source, target, derivatives):
     return out
 
 
+def _checkderivMarg(source, target, df, distfunc='W2', verbose=False, memory=False, percent=False, ind=None,
+                    returnmargW=False, dffloor=None):
+    """libs/OTlib.py:330-393 (Ricker_waveform_derivatives.ipynb cell 36): central finite difference of the marginal
+    Wasserstein distance(s) with respect to ONE un-normalised amplitude of the 2-D source density - the first index
+    of `ind` (default: all indices) whose amplitude exceeds `dffloor` (default 1e-4 of the maximum).  Returns
+    (dWt/df, dWu/df) with returnmargW, else d(mean)/df; (None, None) if no index qualified.  `df` is the step, or a
+    percentage of the amplitude with percent=True."""
+    f = source.pdf.reshape(source.n) * source.amp                     # :331
+    fx = source.x
+    out = MargWasserstein(source, target, derivatives=True, distfunc=distfunc, memory=memory, returnmargW=returnmargW)
+    Wpm, dWm = out[0], out[1]                                         # :337 (raises what the reference raises)
+    if verbose:
+        print('\n W2 from average marginal : ', np.sqrt(Wpm))
+        print('\n Compare analytical and finite difference derivatives from Marginal Wasserstein: \n')
+        print('I                     d(W2)/df            Finite Diff \n')
+    if dffloor is None:
+        dffloor = 0.0001 * np.max(f)                                  # :345
+    for i in (range(source.n) if ind is None else ind):
+        step = np.abs(f[i]) * df / 100. if percent else df            # :354
+        if not np.abs(f[i]) > dffloor:                                # :355
+            continue
+        w = []
+        for sgn in (-1.0, +1.0):
+            fq = np.copy(f)
+            fq[i] = f[i] + sgn * step
+            sq = OTpdf((fq.reshape((source.nx, source.ny)), fx))
+            w.append(MargWasserstein(sq, target, distfunc=distfunc, memory=memory, returnmargW=returnmargW)[0])
+        if returnmargW:
+            wfd0 = (w[1][0] - w[0][0]) / (2 * step)                   # :366-367
+            wfd1 = (w[1][1] - w[0][1]) / (2 * step)
+            if verbose:
+                print(i, ' :     Marg t   ', dWm[0].flatten()[i], ' ', wfd0)
+                print(i, ' :     Marg u   ', dWm[1].flatten()[i], ' ', wfd1)
+            return wfd0, wfd1
+        wfd = (w[1] - w[0]) / (2 * step)                              # :388
+        if verbose:
+            print(i, ' :     avg   ', dWm.flatten()[i], ' ', wfd)
+        return wfd
+    return None, None                                                 # :393
+
+
 def _point_distances(source, target, distfunc):
     """libs/OTlib.py:187-217 for distfunc 'W1' / 'W2' between the 2-D point positions: |dx| + |dy| or dx^2 + dy^2."""
     fx = source.x.reshape((source.n, 2))
