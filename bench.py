@@ -388,8 +388,9 @@ def secondary_configs(dev):
         "models": M4, "windows": M4 * nr4 * nc4, "seconds": dt4, "models_per_s": M4 / dt4,
         "h2d_bytes": int(pred4_pin.numel() * 8 + J4_pin.numel() * 8),
         "note": "adapters.misfit_grad_models: pinned host tensors in (seismograms 60 MB, Jacobians 540 MB) streamed in "
-                "chunks of 512 models under the kernels, fused kernel with in-kernel arctan transform, Jacobian chain, "
-                "results (misfit, 9 derivatives, d/d(seismogram) 60 MB) back on the host as NumPy; wall clock, best of 3 calls"}
+                "chunks of 1024 models (the first one 256) under the kernels, fused kernel with in-kernel arctan transform, "
+                "Jacobian chain, results (misfit, 9 derivatives, d/d(seismogram) 60 MB) back in pinned host memory as NumPy "
+                "views; wall clock, best of 3 calls"}
     # the Jacobian chain alone (k_chain, HBM bound: J is read once, 8 P L bytes per model)
     Jd = J4_pin[:2048].to(dev)
     drd = torch.randn((2048, nr4 * nc4 * nt4), dtype=torch.float64, device=dev)

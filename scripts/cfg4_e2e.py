@@ -23,9 +23,9 @@ pred4_pin = torch.from_numpy(pred4).pin_memory()
 J4_pin = torch.randn((M4, 9, nr4 * nc4 * nt4), dtype=torch.float64).pin_memory()
 grids4 = adapters.buildFingerprintwindows(t4, obs4)
 tg4 = adapters.make_targets_models(t4, obs4, grids4, 0.04)
-for pipeline in (1, 0):
+for pipeline in (0,):
     C.lib.wfot_dev_set_option(C.OPT_PIPELINE, pipeline)
-    for cm in (512, 1024, 2048):
+    for cm in (512, 768, 1024, 1366, 2048):
         adapters.misfit_grad_models(t4, pred4_pin[:64], grids4, tg4, 0.04, J=J4_pin[:64])
         torch.cuda.synchronize()
         best = 1e9

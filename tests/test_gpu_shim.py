@@ -158,6 +158,37 @@ def test_cmt_models_adapter(mods):
         np.testing.assert_allclose(dmis[m], J[m].dot(drm.reshape(-1)), rtol=1e-5, atol=1e-7 * np.abs(dmis[m]).max())
 
 
+def test_cmt_models_adapter_chunking(mods):
+    """misfit_grad_models streams the models through in chunks (a short first one, then `chunk_models` each): the
+    results do not depend on where the chunks are cut (37 models: one chunk, 2 + 8 + ..., one model at a time), with
+    NumPy, pinned-tensor and device-tensor inputs."""
+    fp, OT, adapters = mods
+    rng = np.random.default_rng(3)
+    M, nr, nc, nt = 37, 2, 3, 61
+    t = np.arange(float(nt))
+    base = np.stack([[np.exp(-0.5 * ((t - 20 - 3 * i - 2 * j) / 4.0) ** 2) * np.sin(0.4 * (t - 20 - 3 * i))
+                      for j in range(nc)] for i in range(nr)]) * 1e-3
+    obs = base + 2e-5 * rng.standard_normal(base.shape)
+    pred = np.stack([np.roll(base, m % 5 + 1, axis=-1) * (1 + 0.01 * m) + 1e-5 * rng.standard_normal(base.shape)
+                     for m in range(M)])
+    J = rng.standard_normal((M, 9, nr * nc * nt))
+    grids = adapters.buildFingerprintwindows(t, obs)
+    tg = adapters.make_targets_models(t, obs, grids, 0.04)
+    ref = adapters.misfit_grad_models(t, pred, grids, tg, 0.04, J=J, chunk_models=64)
+    assert ref[0].shape == (M,) and ref[1].shape == (M, 9) and ref[2].shape == (M, nr, nc, nt)
+    variants = [dict(seis=pred, J=J, cm=8), dict(seis=pred, J=J, cm=1),
+                dict(seis=torch.from_numpy(pred).pin_memory(), J=torch.from_numpy(J).pin_memory(), cm=8),
+                dict(seis=torch.from_numpy(pred).cuda(), J=torch.from_numpy(J).cuda(), cm=16)]
+    for v in variants:
+        out = adapters.misfit_grad_models(t, v["seis"], grids, tg, 0.04, J=v["J"], chunk_models=v["cm"])
+        np.testing.assert_array_equal(out[0], ref[0])                      # misfits: fixed summation orders
+        for a, b in zip(out[1:], ref[1:]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-12 * np.abs(b).max())
+    mis, dmis, dr = adapters.misfit_grad_models(t, pred, grids, tg, 0.04)  # no Jacobian
+    assert dmis is None
+    np.testing.assert_array_equal(mis, ref[0])
+
+
 @pytest.mark.parametrize("tag", ["loc", "cmt"])
 def test_cmt_models_adapter_vs_reference_golden(mods, golden, tag):
     """The batched CMT loop (one fused launch for all models x stations x components, in-kernel arctan transform,
