@@ -193,7 +193,10 @@ int wfot_ricker_batch(const double* params, int M, double t0, double t1,
  * Outputs: W (B, 2) = [W^t, W^u]; grad (B, 2, nt) = [dW^t/dw, dW^u/dw] (NULL =
  * misfit only); dwg (B,) = dW^t/d(translation) in normalised time units
  * (divide by tan(theta)*(t1-t0) as libs/ricker_util.py:333).
- * pmask is WFOT_W1 or WFOT_W2.  If transform != 0 the arctan amplitude
+ * pmask is WFOT_W1 or WFOT_W2; misfit-only calls (grad == NULL) also take WFOT_W12: both orders
+ * from one fingerprint (the misfit surfaces of Ricker_Figs_1_7.ipynb cells 34/38 want W1 and W2 of
+ * the same windows), W then (B, 4) = [W1^t, W1^u, W2^t, W2^u] and dwg (B, 2) = [of W1^t, of W2^t].
+ * If transform != 0 the arctan amplitude
  * transform of libs/ricker_util.py:270-275 is applied in-kernel with each
  * grid's (u0,u1) and the gradient is multiplied by d(un)/du (:393-397).
  * Reproducibility: W and dwg are bit-identical from run to run (fixed summation orders).  The

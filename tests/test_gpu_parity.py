@@ -228,6 +228,39 @@ def test_fused_batch_vs_oracle_and_unfused(B):
                                        atol=1e-10 * np.abs(dr[i]).max())
 
 
+@pytest.mark.parametrize("nb,nt,nug,ntg", [(5, 200, 48, 64), (700, 61, 79, 61)])
+def test_fused_both_orders_misfit_only(B, nb, nt, nug, ntg):
+    """Misfit-only mode with both orders from one fingerprint (pmask = WFOT_W12, include/wfot.h): W (B, 4) and dwg (B, 2)
+    equal the W1 and the W2 call's results bit for bit (one-kernel form and, for the larger batch, scan + resolve), W12
+    with a gradient is refused, and the values agree with the oracle's wasser('W12') on the marginals."""
+    lam = 0.04
+    w = O.random_walk_windows(nb + 1, nt, seed=11).astype(np.float64)
+    t = np.linspace(0, 1, nt)
+    grid = (0.0, 1.0, -1.3, 1.3, nug, ntg)
+    tg = B.Target.from_waveform(t, w[0], grid, nug, ntg, lam)
+    r12 = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg, distfunc="W12", want_grad=False)
+    r1 = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg, distfunc="W1", want_grad=False)
+    r2 = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg, distfunc="W2", want_grad=False)
+    r2g = B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg, distfunc="W2")
+    torch.cuda.synchronize()
+    W12, d12 = r12["W"].cpu().numpy(), r12["dwg"].cpu().numpy()
+    assert W12.shape == (nb, 4) and d12.shape == (nb, 2)
+    np.testing.assert_array_equal(W12[:, 0:2], r1["W"].cpu().numpy())
+    np.testing.assert_array_equal(W12[:, 2:4], r2["W"].cpu().numpy())
+    np.testing.assert_array_equal(d12[:, 0], r1["dwg"].cpu().numpy())
+    np.testing.assert_array_equal(d12[:, 1], r2["dwg"].cpu().numpy())
+    np.testing.assert_array_equal(r2["W"].cpu().numpy(), r2g["W"].cpu().numpy())       # with and without the gradient
+    with pytest.raises(ValueError):
+        B.misfit_grad_batch(t, w[1:], grid, nug, ntg, lam, tg, distfunc="W12")
+    wino, tgt = O.build_ot_from_waveform(t, w[0], grid, lambdav=lam)
+    for b in range(min(nb, 3)):
+        win, src = O.build_ot_from_waveform(t, w[1 + b], grid, lambdav=lam)
+        O.set_marginals(src); O.set_marginals(tgt)
+        for i in range(2):
+            out = O.wasser(src.marg[i], tgt.marg[i], distfunc="W12")
+            np.testing.assert_allclose([W12[b, i], W12[b, 2 + i]], out, rtol=1e-10)
+
+
 def test_fused_transform_vs_oracle(B):
     """In-kernel arctan amplitude transform (libs/ricker_util.py:241-244, 393-397)."""
     nt, nug, ntg, lam = 61, 79, 61, 0.04

@@ -228,19 +228,20 @@ def misfit_surface(tshifts, amps, f, target, grid, lambdav, trange=(-2.0, 2.0), 
     tant = 1.0 if theta == 45.0 else float(np.tan(np.pi * theta / 180.0))
     ts, am = np.meshgrid(np.asarray(tshifts, dtype=np.float64), np.asarray(amps, dtype=np.float64), indexing="ij")
     P = np.stack([ts.ravel(), am.ravel(), np.full(ts.size, float(f))], axis=1)
-    out = {"W1": [], "W2": []}
+    out = []
     g = _B.pack_grids((t0, t1, u0, u1, Nu, Nt), tant)
     status = _B.Status()
     for a in range(0, P.shape[0], chunk):
         fw = _B.ricker_batch(P[a:a + chunk], trange)
-        for d in ("W1", "W2"):
-            r = _B.misfit_grad_batch(fw["t"], fw["w"], g, int(Nu), int(Nt), lambdav, target, distfunc=d,
-                                     want_grad=False, status=status)
-            out[d].append(r["W"])
+        # both orders from ONE fingerprint pass (W (B, 4) = [W1^t, W1^u, W2^t, W2^u]): the nearest-segment search is
+        # the cost of a window and does not depend on the order
+        r = _B.misfit_grad_batch(fw["t"], fw["w"], g, int(Nu), int(Nt), lambdav, target, distfunc="W12",
+                                 want_grad=False, status=status)
+        out.append(r["W"])
     torch.cuda.current_stream().synchronize()
     status.raise_for_reference(derivatives=False, what="misfit_surface")
-    shp = (len(tshifts), len(amps), 2)
-    return torch.cat(out["W1"]).cpu().numpy().reshape(shp), torch.cat(out["W2"]).cpu().numpy().reshape(shp)
+    W = torch.cat(out).cpu().numpy().reshape(len(tshifts), len(amps), 2, 2)
+    return np.ascontiguousarray(W[:, :, 0]), np.ascontiguousarray(W[:, :, 1])
 
 
 class RickerGraphEvaluator:

@@ -368,6 +368,8 @@ def misfit_grad_batch(t, w, grids, nug, ntg, lambdav, target: Target, distfunc="
                       workspace=None, out=None):
     """Fused evaluation of B windows: returns W (B,2) [W^t, W^u], grad (B,2,nt), dwg (B,)
     (dW^t/d(translation) in normalised time units).  Inputs may already be device tensors.
+    distfunc "W12" (misfit only, want_grad=False): both orders from one fingerprint, W (B,4) =
+    [W1^t, W1^u, W2^t, W2^u], dwg (B,2).
     `workspace` / `out` (a previous result dict) let a caller that streams batches of one shape
     through the library re-use the scratch and result buffers instead of allocating per call."""
     dev = _device()
@@ -378,15 +380,19 @@ def misfit_grad_batch(t, w, grids, nug, ntg, lambdav, target: Target, distfunc="
     t = _as_device(t, w.dtype)
     t_stride = 0 if t.dim() == 1 else nt
     g = grids if isinstance(grids, torch.Tensor) else pack_grids(grids, tantheta, fpgrids)
-    pmask = {"W1": C.W1, "W2": C.W2}[distfunc]
+    pmask = {"W1": C.W1, "W2": C.W2, "W12": C.W12}[distfunc]
+    if pmask == C.W12 and want_grad:
+        raise ValueError("distfunc 'W12' is a misfit-only mode of the fused path (want_grad=False); "
+                         "MargWasserstein itself rejects 'W12' (libs/OTlib.py:1090-1091)")
+    nW = 4 if pmask == C.W12 else 2
     f64 = dict(dtype=torch.float64, device=dev)
-    if out is not None and out["W"].shape == (B, 2) and (not want_grad or (out.get("grad") is not None
-                                                                          and out["grad"].shape == (B, 2, nt))):
+    if out is not None and out["W"].shape == (B, nW) and (not want_grad or (out.get("grad") is not None
+                                                                           and out["grad"].shape == (B, 2, nt))):
         W, grad, dwg = out["W"], (out["grad"] if want_grad else None), out["dwg"]
     else:
-        W = torch.empty((B, 2), **f64)
+        W = torch.empty((B, nW), **f64)
         grad = torch.empty((B, 2, nt), **f64) if want_grad else None
-        dwg = torch.empty(B, **f64)
+        dwg = torch.empty((B, 2) if pmask == C.W12 else B, **f64)
     wsb = C.lib.wfot_misfit_grad_workspace_bytes(B, nt, nug, ntg)
     ws = workspace if workspace is not None and workspace.numel() >= wsb else \
         torch.empty(wsb, dtype=torch.uint8, device=dev)

@@ -283,7 +283,7 @@ int wfot_misfit_grad_batch(const void* t, const void* w, int in_dtype, long long
                            int32_t* status, void* stream_) {
     if (!t || !w || !grids || !W || !workspace || !tgt_cdf_t || !tgt_x_t || !tgt_cdf_u || !tgt_x_u ||
         B <= 0 || nt < 2 || nug < 1 || ntg < 1 || n_grids < 1 || tgt_rows < 1 ||
-        (q != 0 && q != 2) || (pmask != WFOT_W1 && pmask != WFOT_W2) || !(lambda > 0.0) ||
+        (q != 0 && q != 2) || (pmask != WFOT_W1 && pmask != WFOT_W2 && !(pmask == WFOT_W12 && grad == nullptr)) || !(lambda > 0.0) ||
         (in_dtype != WFOT_F32 && in_dtype != WFOT_F64))
         return WFOT_ERR_INVALID_ARG;
     FusedArgs a;

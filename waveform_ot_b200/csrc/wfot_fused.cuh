@@ -316,13 +316,14 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
     // ---------------- P3: both marginal problems by warp 0, without block barriers (warp_ot1d)
     const size_t trow = (size_t)(b % a.tgt_rows);
     OtScratch sc{s_cf, s_tk, s_dx, s_E, s_posf, s_red};
+    const int dmask = a.grad ? a.pmask : 0;      // amplitude derivatives of the 1-D problems only when a gradient is assembled
     for (int c = tid; c < a.ntg; c += NT) s_cf[c] = s_margt[c];
     __syncthreads();
     if (a.L.cf2) {       // one warp per marginal
         double* const s_cf2 = reinterpret_cast<double*>(smem_raw + a.L.cf2);
         if (warp == 0) {
             const WarpOtResult ot = warp_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, s_xt, a.tgt_x_t + trow * a.ntg,
-                                              a.pmask, s_Rt, s_margt);
+                                              dmask, s_Rt, s_margt);
             if (lane == 0) {
                 s_red[0] = ot.r.W1; s_red[1] = ot.r.W2; s_red[2] = ot.r.dpos1; s_red[3] = ot.r.dpos2; s_red[4] = ot.G;
                 s_red[8] = __longlong_as_double((long long)ot.r.common);
@@ -334,7 +335,7 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
             for (int c = lane; c < a.nug; c += 32) s_cf2[c] = s_margu[c];
             __syncwarp();
             const WarpOtResult ou = warp_ot1d(sc2, a.nug, a.tgt_cdf_u + trow * a.nug, s_xu, a.tgt_x_u + trow * a.nug,
-                                              a.pmask, s_Ru, s_margu);
+                                              dmask, s_Ru, s_margu);
             if (lane == 0) {
                 s_red[5] = ou.r.W1; s_red[6] = ou.r.W2; s_red[7] = ou.G;
                 s_red[9] = __longlong_as_double((long long)ou.r.common);
@@ -342,12 +343,12 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
         }
     } else if (warp == 0) {
         const WarpOtResult ot = warp_ot1d(sc, a.ntg, a.tgt_cdf_t + trow * a.ntg, s_xt, a.tgt_x_t + trow * a.ntg,
-                                          a.pmask, s_Rt, s_margt);
+                                          dmask, s_Rt, s_margt);
         __syncwarp();
         for (int c = lane; c < a.nug; c += 32) s_cf[c] = s_margu[c];
         __syncwarp();
         const WarpOtResult ou = warp_ot1d(sc, a.nug, a.tgt_cdf_u + trow * a.nug, s_xu, a.tgt_x_u + trow * a.nug,
-                                          a.pmask, s_Ru, s_margu);
+                                          dmask, s_Ru, s_margu);
         if (lane == 0) {
             s_red[0] = ot.r.W1; s_red[1] = ot.r.W2; s_red[2] = ot.r.dpos1; s_red[3] = ot.r.dpos2; s_red[4] = ot.G;
             s_red[5] = ou.r.W1; s_red[6] = ou.r.W2; s_red[7] = ou.G;
@@ -363,9 +364,15 @@ __device__ __forceinline__ int window_tail(const FusedArgs& a, unsigned char* sm
     rt.common = (int)__double_as_longlong(s_red[8]); ru.common = (int)__double_as_longlong(s_red[9]);
     __syncthreads();                                                // s_red is re-used below
     if (tid == 0) {
-        a.W[2 * (size_t)b] = (a.pmask & 1) ? rt.W1 : rt.W2;
-        a.W[2 * (size_t)b + 1] = (a.pmask & 1) ? ru.W1 : ru.W2;
-        if (a.dwg) a.dwg[b] = (a.pmask & 1) ? rt.dpos1 : rt.dpos2;  // OTlib.py:1121
+        if (a.pmask == 3) {   // both orders from one fingerprint (misfit only): [W1^t, W1^u, W2^t, W2^u], dwg [W1, W2]
+            double* const w4 = a.W + 4 * (size_t)b;
+            w4[0] = rt.W1; w4[1] = ru.W1; w4[2] = rt.W2; w4[3] = ru.W2;
+            if (a.dwg) { a.dwg[2 * (size_t)b] = rt.dpos1; a.dwg[2 * (size_t)b + 1] = rt.dpos2; }
+        } else {
+            a.W[2 * (size_t)b] = (a.pmask & 1) ? rt.W1 : rt.W2;
+            a.W[2 * (size_t)b + 1] = (a.pmask & 1) ? ru.W1 : ru.W2;
+            if (a.dwg) a.dwg[b] = (a.pmask & 1) ? rt.dpos1 : rt.dpos2;  // OTlib.py:1121
+        }
     }
 
     // ---------------- P4
