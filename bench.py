@@ -342,7 +342,7 @@ def secondary_configs(dev):
         adapters.misfit_surface(tsh, amp, 1.0, tgt3, grid3, 0.03)
         dt3 = min(dt3, time.perf_counter() - t0)
     out["cfg3_surface_512x512_W1_and_W2"] = {"models": 512 * 512, "seconds": dt3, "models_per_s": 512 * 512 / dt3,
-                                            "note": "wall clock incl. on-device forward model, 2 fused passes (W1, W2), D2H; best of 2 calls"}
+                                            "note": "wall clock incl. on-device forward model, one fused misfit-only pass giving W1 and W2 of both marginals (WFOT_W12), D2H; best of 2 calls"}
     # cfg1 latency: ONE Ricker evaluation (misfit + gradient w.r.t. the 3 model parameters) through the adapter
     # a scipy.optimize loop would call, host in / host out, forward model included (ricker_util.optfunc)
     data = [tgt3, "W2", (-2.0, 2.0), grid3, 0.03, False, 0.5, 45.0]
