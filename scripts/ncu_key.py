@@ -1,6 +1,8 @@
-"""Key per-kernel counters of an .ncu-rep (raw page): usage ncu_key.py report.ncu-rep"""
-import csv, subprocess, sys, io
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+"""Key per-kernel counters of an .ncu-rep (raw page): usage ncu_key.py report.ncu-rep
+NCU_SKIP=<n>: leave out the first n launches of the report (warm-up / set-up launches of the same kernels)."""
+import csv, os, subprocess, sys, io
+skip = ["--launch-skip", os.environ["NCU_SKIP"]] if os.environ.get("NCU_SKIP") else []
+out = subprocess.run(["ncu", "-i", sys.argv[1]] + skip + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',

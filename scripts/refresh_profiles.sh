@@ -4,7 +4,9 @@
 #   launches_final.csv               ncu --metrics gpu__time_duration.sum on a short bench run  (launch list)
 #   prof_split_<tag>.ncu-rep         ncu --set full, python scripts/prof_split.py 592 cfg5      (k_scan + k_resolve)
 #   prof_split_cfg4_<tag>.ncu-rep    ncu --set full, python scripts/prof_split.py 9472 cfg4
-# usage: scripts/refresh_profiles.sh <tag> "<build note>"
+# The captures hold every k_scan / k_resolve launch of prof_split.py (observed-window set-up, warm-up call, profiled call):
+# NCU_SKIP=4 keeps the last pair.
+# usage: NCU_SKIP=4 scripts/refresh_profiles.sh <tag> "<build note>"
 set -e
 cd "$(dirname "$0")/.."
 TAG=${1:?tag}; NOTE=${2:-}
@@ -26,7 +28,7 @@ for cfg in cfg5 cfg4; do
   if [ $cfg = cfg5 ]; then rep=gpurun_out/prof_split_$TAG.ncu-rep; out=profiles/r02_split_ncu_summary.txt; what="cfg5 shape (nt=1024, 256x256 grid), 592 windows"; cmd="python scripts/prof_split.py 592 cfg5"
   else rep=gpurun_out/prof_split_cfg4_$TAG.ncu-rep; out=profiles/r02_split_cfg4_ncu_summary.txt; what="cfg4 shape (nt=61, 79x61 grid), 9472 windows"; cmd="python scripts/prof_split.py 9472 cfg4"; fi
   [ -f $rep ] || continue
-  ncu -i $rep --page source --csv --print-source cuda,sass > gpurun_out/src_split_$cfg.csv 2>/dev/null
+  ncu -i $rep ${NCU_SKIP:+--launch-skip $NCU_SKIP} --page source --csv --print-source cuda,sass > gpurun_out/src_split_$cfg.csv 2>/dev/null
   { echo "ncu --set full --clock-control none --import-source on, k_scan + k_resolve (two-kernel form of the fused path), $what; $NOTE"
     echo "command: $cmd   (report: $rep, not tracked)"; echo
     python scripts/ncu_key.py $rep 2>/dev/null; echo
@@ -38,7 +40,9 @@ done
 python - "$TAG" <<'PY'
 import csv, io, json, subprocess, sys
 rep = "gpurun_out/prof_split_%s.ncu-rep" % sys.argv[1]
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+import os
+skip = ["--launch-skip", os.environ["NCU_SKIP"]] if os.environ.get("NCU_SKIP") else []
+out = subprocess.run(["ncu", "-i", rep] + skip + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
