@@ -138,3 +138,16 @@ def test_sharded_empty_shard_contributes_zeros(monkeypatch):
     w = torch.zeros((2, 16))
     out = wd.misfit_grad_sharded(torch.linspace(0, 1, 16), w, None, 4, 4, 0.04, None)
     assert out.shape == (3 + 2 * 16,) and float(out.abs().sum()) == 0.0
+
+
+def test_model_chunk_bounds():
+    """adapters._chunk_bounds: every model in exactly one chunk, no chunk larger than asked, a short first chunk."""
+    from waveform_ot_b200 import adapters
+    for M in (1, 2, 3, 5, 37, 255, 256, 257, 1024, 1025, 4096, 5000):
+        for cm in (1, 2, 8, 64, 512, 1024, 10 ** 6):
+            b = adapters._chunk_bounds(M, cm)
+            assert b[0] == 0 and b[-1] == M and all(x < y for x, y in zip(b, b[1:]))
+            assert max(y - x for x, y in zip(b, b[1:])) <= max(1, min(cm, M))
+            if M > cm >= 4:
+                assert b[1] == cm // 4
+    assert adapters._chunk_bounds(4096, 1024) == [0, 256, 1280, 2304, 3328, 4096]

@@ -95,6 +95,14 @@ def optfunc_ricker(x, data, forward):
     return w2, deriv
 
 
+def _chunk_bounds(M, chunk):
+    """Cut M models into chunks of at most `chunk`: a short first chunk (a quarter; its upload is the only one that no
+    kernel hides), full chunks after it.  Returns the ascending bounds [0, ..., M]."""
+    chunk = max(1, min(int(chunk), M))
+    first = chunk if M <= chunk else max(1, chunk // 4)
+    return [0, first] + list(range(first + chunk, M, chunk)) + ([M] if first < M else [])
+
+
 def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfunc="W2", Wopt="Wavg",
                        chunk_models=1024):
     """Batched libs/loc_cmt_util.py:251-296.  seis_pred (M, nr, nc, nt) predicted seismograms of M
@@ -132,9 +140,7 @@ def misfit_grad_models(t, seis_pred, obs_grids, targets, lambdav, J=None, distfu
     h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     h2d.wait_stream(main)
     cm = max(1, min(int(chunk_models), M))
-    # chunk bounds: a short first chunk (its upload is the only one nothing hides), full chunks after it
-    first = cm if M <= cm else max(1, cm // 4)
-    bounds = [0, first] + list(range(first + cm, M, cm)) + ([M] if first < M else [])
+    bounds = _chunk_bounds(M, cm)
     nxt = {bounds[i]: bounds[i + 1] for i in range(len(bounds) - 1)}
     ws = torch.empty(_B.C.lib.wfot_misfit_grad_workspace_bytes(cm * nw, nt, Nu, Nt), dtype=torch.uint8, device=dev)
     staged, finished = {}, {}
