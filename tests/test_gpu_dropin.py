@@ -149,3 +149,27 @@ def test_unmodified_loc_cmt_util_optfunc_OT_over_shim(ref_over_shim, golden, cmt
         assert mis == pytest.approx(float(g[tag + "_mis" + w]), rel=1e-9)
         np.testing.assert_allclose(dmis, g[tag + "_dmis" + w], rtol=1e-6, atol=1e-8 * np.abs(g[tag + "_dmis" + w]).max())
     assert len(cmtu.loc_cmt_util_opt.opt_history_data) == len(models) + 3          # the reference's history side effect
+
+
+def test_out_of_scope_names_are_served_by_the_reference(ref_over_shim, golden):
+    """With the shim installed over the reference package, names outside the accelerated path resolve to the
+    reference's own functions (adapters.reference_attr) and work on shim objects through the attribute protocol:
+    the reference's host-side evaluator fp.wavedistv (libs/FingerprintLib.py:456-474) applied to a shim waveformFP
+    reproduces the GPU distance field, nearest segments and ray parameters bit for bit."""
+    ru, OT = ref_over_shim
+    fp = ru.fp
+    assert fp.wavedistv.__module__ == "libs._reference_FingerprintLib"
+    assert OT.wasserNumInt.__module__ == "libs._reference_OTlib"
+    assert not hasattr(OT, "no_such_name")
+    g = golden("ricker_forward")
+    grid = tuple(g["grid"][:4]) + (int(g["grid"][4]), int(g["grid"][5]))
+    wf = fp.waveformFP(g["to"], g["wo"], grid)
+    wf.calcpdf(lambdav=float(g["lam"]))
+    Xn, Yn = np.meshgrid(np.linspace(wf.tlimnfp[0], wf.tlimnfp[1], wf.ntg), np.linspace(wf.ulimnfp[0], wf.ulimnfp[1], wf.nug))
+    points = np.vstack((Xn.flatten(), Yn.flatten())).T
+    ks = np.random.default_rng(0).choice(points.shape[0], 4000, replace=False)
+    d, irays, xrays, lrays = fp.wavedistv(points[ks], wf)            # the reference's NumPy evaluator, shim geometry
+    np.testing.assert_array_equal(irays, wf.irays[ks])
+    np.testing.assert_array_equal(d, wf.dfield.reshape(-1)[ks])
+    np.testing.assert_array_equal(lrays, wf.lrays[ks])
+    np.testing.assert_array_equal(xrays, wf.xrays[ks])

@@ -151,3 +151,38 @@ def test_model_chunk_bounds():
             if M > cm >= 4:
                 assert b[1] == cm // 4
     assert adapters._chunk_bounds(4096, 1024) == [0, 256, 1280, 2304, 3328, 4096]
+
+
+def test_out_of_scope_names_delegate_to_installed_reference():
+    """Module __getattr__ of the shim: a clear AttributeError for names outside the path, and - once installed over a
+    reference package - the reference's own function (no GPU needed: nothing is called)."""
+    import importlib
+    import sys
+    from oracle import build_ref
+    from waveform_ot_b200 import FingerprintLib, OTlib, adapters
+    saved_prefix = adapters._installed_prefix
+    adapters._installed_prefix = None
+    try:
+        with pytest.raises(AttributeError, match="outside the accelerated path"):
+            OTlib.plotWasser
+        with pytest.raises(AttributeError, match="has no attribute"):
+            OTlib.no_such_name
+        assert not hasattr(FingerprintLib, "plot_LS")
+        if not build_ref.available():
+            pytest.skip("oracle/_ref not built")
+        saved = {k: v for k, v in sys.modules.items() if k == "libs" or k.startswith("libs.")}
+        try:
+            build_ref.import_reference()
+            for k in [k for k in sys.modules if k == "libs" or k.startswith("libs.")]:
+                del sys.modules[k]
+            importlib.import_module("libs")
+            adapters.install("libs")
+            assert OTlib.wasserNumInt.__module__ == "libs._reference_OTlib"
+            assert FingerprintLib.wavedistv.__module__ == "libs._reference_FingerprintLib"
+            assert not hasattr(OTlib, "no_such_name")
+        finally:
+            for k in [k for k in sys.modules if k == "libs" or k.startswith("libs.")]:
+                del sys.modules[k]
+            sys.modules.update(saved)
+    finally:
+        adapters._installed_prefix = saved_prefix

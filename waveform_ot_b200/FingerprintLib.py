@@ -247,3 +247,24 @@ def check_FDderiv(wf, k, du=0.001, verbose=False):
     if verbose:
         print('\n segments after FD perturbation : ', ' pos 0 ', ip0, ' minus 0', im0, 'pos 1 ', ip1, ' minus 1', im1)
     return i, dddy0fd, dddy1fd
+
+
+# Names of libs/FingerprintLib.py that are outside the hot path (plotting, the obsolete FMM / nearest-neighbour methods,
+# point-wise host evaluators): with the shim installed over the reference package they are served by
+# the reference's own module (adapters.reference_attr); otherwise asking for one says so instead of a bare AttributeError.
+_OUT_OF_SCOPE = ("NNsearch", "wavedist", "wavedistv", "wavederiv", "check_FDchain", "wPDFderiv", "plot_RF_SDF",
+                 "plotPDFsurface", "plot_phi", "plot_rays_discrete", "plot_rays", "plot_LS", "plot_2LS", "plotMarginals",
+                 "calcFMM_dist_deriv", "find_raystart_point_with_gradient")
+
+
+def __getattr__(name):
+    if name in _OUT_OF_SCOPE:
+        try:   # installed over the reference package (adapters.install): the reference's own function serves the call
+            from . import adapters
+            return adapters.reference_attr("FingerprintLib", name)
+        except AttributeError:
+            pass
+        raise AttributeError("waveform_ot_b200.FingerprintLib: %r of libs/FingerprintLib.py is outside the accelerated "
+                             "path (plotting, FMM / NNsearch, host-side point evaluators); use the reference module "
+                             "for it" % name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -493,3 +493,24 @@ def MargWasserstein(source, target, distfunc='W2', derivatives=False, verbose=Fa
     if returnmargW:
         return outMarg
     return out
+
+
+# Names of libs/OTlib.py that are outside the hot path (plotting, LP / Sinkhorn / POT cross-checks,
+# barycentres, diagnostics that only print): with the shim installed over the reference package they are served by
+# the reference's own module (adapters.reference_attr); otherwise asking for one says so instead of a bare AttributeError.
+_OUT_OF_SCOPE = ("_calc_distArray", "_checkderiv", "_checkderivSliced", "_normalise", "_optimaltransport", "BuildLinProg",
+                 "Wasser_LinProg", "plotWasser", "distfunction", "barypath_pointmass", "barypath", "wasserNumInt",
+                 "wasser_find_optplan", "wasserPOT", "filter", "SinkhornAB", "Sinkhorn", "Sinkhorn_MS", "sinkhornPOT",
+                 "trim_axs", "plot_optimal_transform_frames", "plotOT1D", "POTlibraryError")
+
+
+def __getattr__(name):
+    if name in _OUT_OF_SCOPE:
+        try:   # installed over the reference package (adapters.install): the reference's own function serves the call
+            from . import adapters
+            return adapters.reference_attr("OTlib", name)
+        except AttributeError:
+            pass
+        raise AttributeError("waveform_ot_b200.OTlib: %r of libs/OTlib.py is outside the accelerated path (plotting, "
+                             "LP / Sinkhorn / POT cross-checks, barycentres); use the reference module for it" % name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

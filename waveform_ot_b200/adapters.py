@@ -19,8 +19,15 @@ import numpy as np
 from . import batch as _B
 
 
+_installed_prefix = None
+
+
 def install(module_prefix="libs"):
-    """Make `from libs import FingerprintLib, OTlib` resolve to the B200 implementation."""
+    """Make `from libs import FingerprintLib, OTlib` resolve to the B200 implementation.  Names of the two reference
+    modules that are outside the accelerated path (plotting helpers, LP / Sinkhorn cross-checks, host-side point
+    evaluators, ...) keep working: they are served on first use by the reference's own source files of the package the
+    shim was installed over (reference_attr), operating on the shim objects through the attribute protocol."""
+    global _installed_prefix
     from . import FingerprintLib, OTlib
     sys.modules[module_prefix + ".FingerprintLib"] = FingerprintLib
     sys.modules[module_prefix + ".OTlib"] = OTlib
@@ -28,7 +35,33 @@ def install(module_prefix="libs"):
     if pkg is not None:
         pkg.FingerprintLib = FingerprintLib
         pkg.OTlib = OTlib
+    _installed_prefix = module_prefix
     return FingerprintLib, OTlib
+
+
+def reference_attr(basename, name):
+    """`name` from the reference's own <package>/<basename>.py, loaded (once, lazily) under a private module name next
+    to the installed shim.  Raises AttributeError if the shim is not installed over an importable reference package."""
+    import importlib
+    import importlib.util
+    import os
+    if _installed_prefix is None:
+        raise AttributeError(name)
+    modname = "%s._reference_%s" % (_installed_prefix, basename)
+    mod = sys.modules.get(modname)
+    if mod is None:
+        try:
+            pkg = importlib.import_module(_installed_prefix)
+            path = os.path.join(list(pkg.__path__)[0], basename + ".py")
+            spec = importlib.util.spec_from_file_location(modname, path)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[modname] = mod
+            spec.loader.exec_module(mod)
+        except Exception as ex:
+            sys.modules.pop(modname, None)
+            raise AttributeError("%s (the reference's %s.py could not be loaded: %s: %s)"
+                                 % (name, basename, type(ex).__name__, ex))
+    return getattr(mod, name)
 
 
 def arctan_trans(u, u0, u1, deriv=False):
