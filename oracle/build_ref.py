@@ -27,6 +27,9 @@ DST = os.path.join(HERE, "_ref")
 MODULES = ["__init__.py", "FingerprintLib.py", "OTlib.py", "ricker_util.py", "ricker_util_opt.py", "myGP.py",
            "loc_cmt_util.py", "loc_cmt_util_opt.py"]
 
+# notebooks whose code cells tests/test_gpu_dropin.py executes over the shim (copied unmodified, like the modules)
+NOTEBOOKS = ["Point_mass_demo_Fig_5.ipynb", "Ricker_waveform_derivatives.ipynb"]
+
 STUB = '''"""Inert stand-in for a plotting package the reference imports at module scope (written by
 oracle/build_ref.py; never used by the hot path)."""
 import sys as _sys
@@ -76,6 +79,10 @@ def build(verbose=True):
     for m in MODULES:
         shutil.copyfile(os.path.join(src, m), os.path.join(DST, "libs", m))
         assert filecmp.cmp(os.path.join(src, m), os.path.join(DST, "libs", m), shallow=False), m
+    os.makedirs(os.path.join(DST, "notebooks"), exist_ok=True)
+    for nb in NOTEBOOKS:
+        shutil.copyfile(os.path.join(REF, nb), os.path.join(DST, "notebooks", nb))
+        assert filecmp.cmp(os.path.join(REF, nb), os.path.join(DST, "notebooks", nb), shallow=False), nb
     with open(os.path.join(DST, "_plot_stubs.py"), "w") as f:
         f.write(STUB)
     if verbose:
