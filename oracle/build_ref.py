@@ -28,7 +28,7 @@ MODULES = ["__init__.py", "FingerprintLib.py", "OTlib.py", "ricker_util.py", "ri
            "loc_cmt_util.py", "loc_cmt_util_opt.py"]
 
 # notebooks whose code cells tests/test_gpu_dropin.py executes over the shim (copied unmodified, like the modules)
-NOTEBOOKS = ["Point_mass_demo_Fig_5.ipynb", "Ricker_waveform_derivatives.ipynb"]
+NOTEBOOKS = ["Point_mass_demo_Fig_5.ipynb", "Ricker_waveform_derivatives.ipynb", "Ricker_Figs_3_8.ipynb"]
 
 STUB = '''"""Inert stand-in for a plotting package the reference imports at module scope (written by
 oracle/build_ref.py; never used by the hot path)."""

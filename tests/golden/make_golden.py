@@ -288,3 +288,22 @@ def fd_checkers():
 
 if __name__ == "__main__" and (len(sys.argv) == 1 or sys.argv[1] == "fd"):
     fd_checkers()
+
+
+def inversion_notebook():
+    """(11) Ricker_Figs_3_8.ipynb run as it is on the unmodified reference (tests/test_gpu_dropin._run_notebook: every
+    code cell but the ones that draw): the L-BFGS-B inversion of cell 32.  The observed waveform carries Gaussian-process
+    noise whose draw depends on the installed scikit-learn; the fixture stores it so that the GPU test knows whether it
+    is looking at the same problem.  Run on its own:  python tests/golden/make_golden.py inversion"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_gpu_dropin import _run_notebook
+    ns = {}
+    _run_notebook("Ricker_Figs_3_8.ipynb", ns)
+    o = ns["opt1"]
+    np.savez(os.path.join(HERE, "inversion_notebook.npz"), wobs=ns["wobs"], x=o.x, fun=o.fun, nfev=o.nfev, nit=o.nit,
+             its=np.array(ns["ricker_util_opt"].Wits), was=np.array(ns["was"], dtype=np.float64))
+    print("inversion_notebook", o.x, o.fun, o.nfev, o.nit)
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or sys.argv[1] == "inversion"):
+    inversion_notebook()

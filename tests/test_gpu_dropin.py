@@ -245,3 +245,29 @@ def test_ricker_derivatives_notebook_runs_unchanged(ref_over_shim):
     assert fd_t0 == pytest.approx(an_t0, rel=1e-6) and abs(an_t0) > 0.1
     assert float(rows50[1][-3]) == pytest.approx(float(rows50[1][-1]), rel=5e-3)   # amplitude parameter, dWu/dm
     assert float(rows50[2][-3]) == pytest.approx(float(rows50[2][-1]), rel=5e-3)   # frequency parameter, dWu/dm
+
+
+def test_ricker_inversion_notebook_runs_unchanged(ref_over_shim, golden):
+    """Ricker_Figs_3_8.ipynb, code cells as they are, over the shim: the notebook's L-BFGS-B inversion
+    `minimize(ru.optfunc, mstart, data, jac=True, ...)` (cell 32) of the double Ricker wavelet's (time offset, amplitude,
+    frequency factor) from a noisy observation - the inversion loop this library exists to drop into.  The Gaussian-process
+    noise draw depends on the installed scikit-learn, so the notebook's stored digits are not reproducible; the run must
+    converge from the notebook's start (5.0, 3.0, 0.5) to its true model (0, 1.6, 1) within the noise."""
+    ns = {}
+    out = _run_notebook("Ricker_Figs_3_8.ipynb", ns)
+    opt1, mtrue, mstart = ns["opt1"], ns["mtrue"], ns["mstart"]
+    assert opt1.nfev >= 5 and len(ns["ricker_util_opt"].Wdata) == opt1.nfev      # every evaluation went through ru.optfunc
+    w0, _ = ns["ru"].optfunc(mstart, ns["data"])
+    assert opt1.fun < 1e-2 * w0                                                  # the misfit dropped by orders of magnitude
+    np.testing.assert_allclose(opt1.x, mtrue, atol=0.2)
+    assert len(ns["was"]) == len(ns["ls"]) >= 3                                  # cells 36-38: the per-iteration history
+    # the same notebook run on the unmodified reference in the build container (make_golden.py inversion): if this box
+    # drew the same noise, the optimiser must walk the same path to the same point
+    g = golden("inversion_notebook")
+    same = ns["wobs"].shape == g["wobs"].shape and np.allclose(ns["wobs"], g["wobs"], rtol=1e-12, atol=1e-14)
+    print("inversion notebook: same noise draw as in the build container:", same, "x =", opt1.x, "nfev =", opt1.nfev)
+    if same:
+        assert opt1.nfev == int(g["nfev"]) and opt1.nit == int(g["nit"])
+        np.testing.assert_allclose(opt1.x, g["x"], rtol=1e-6, atol=1e-8)
+        assert opt1.fun == pytest.approx(float(g["fun"]), rel=1e-6)
+        np.testing.assert_allclose(np.array(ns["ricker_util_opt"].Wits), g["its"], rtol=1e-6, atol=1e-8)
