@@ -194,3 +194,22 @@ def test_cmt_optfunc_fixture(golden, tag, m):
     assert tot == pytest.approx(float(g[tag + "_mis"][m]), rel=1e-12)
     np.testing.assert_allclose(dr, g[tag + "_dr"][m], rtol=1e-9, atol=1e-12 * np.abs(dr).max())
     np.testing.assert_allclose(J.dot(dr.reshape(-1)), g[tag + "_dmis"][m], rtol=1e-9, atol=1e-12 * np.abs(g[tag + "_dmis"][m]).max())
+
+
+def test_inversion_notebook_fixture(golden):
+    """The oracle's optfunc composition inside the notebook's own optimiser call (Ricker_Figs_3_8.ipynb cells 11-32:
+    L-BFGS-B from (5, 3, 0.5), jac=True, tol 1e-8) walks the path the unmodified reference walked on the same noisy
+    observation: tests/golden/inversion_notebook.npz (make_golden.py inversion)."""
+    from scipy.optimize import minimize
+    g = golden("inversion_notebook")
+    trange, lam, alpha = [-2.0, 2.0], 0.03, 0.5
+    grid = (trange[0], trange[1], -2.0, 3.5, 80, 512)                              # cells 14, 17
+    tobs, _ = O.rickerwavelet(0.0, 1.6, 1.0, trange=trange)                         # the time axis; the amplitudes (with the
+    _, tgt = O.build_ot_from_waveform(tobs, g["wobs"], grid, lambdav=lam)           # reference's noise) come from the fixture
+    its = [[5.0, 3.0, 0.5]]
+    opt = minimize(lambda x: O.ricker_optfunc(x, tgt, "W2", trange, grid, lam, alpha=alpha), np.array(its[0]),
+                   jac=True, tol=1e-8, method="L-BFGS-B", options={"maxiter": 500}, callback=lambda x: its.append(x.tolist()))
+    assert opt.nfev == int(g["nfev"]) and opt.nit == int(g["nit"])
+    np.testing.assert_allclose(opt.x, g["x"], rtol=1e-6, atol=1e-8)
+    assert opt.fun == pytest.approx(float(g["fun"]), rel=1e-6)
+    np.testing.assert_allclose(np.array(its), g["its"], rtol=1e-6, atol=1e-8)
