@@ -213,3 +213,21 @@ def test_inversion_notebook_fixture(golden):
     np.testing.assert_allclose(opt.x, g["x"], rtol=1e-6, atol=1e-8)
     assert opt.fun == pytest.approx(float(g["fun"]), rel=1e-6)
     np.testing.assert_allclose(np.array(its), g["its"], rtol=1e-6, atol=1e-8)
+
+
+def test_fd_checkers_fixture(golden):
+    """The oracle's analytic derivatives against the finite differences the reference's own checkers produced
+    (fp.check_FDderiv, OT._checkderivMarg: tests/golden/fd_checkers.npz, make_golden.py fd) and against the
+    reference's analytic dddy at the same grid points."""
+    g = golden("fd_checkers")
+    grid = tuple(g["grid"][:4]) + (int(g["grid"][4]), int(g["grid"][5]))
+    lam = float(g["lam"])
+    _, tgt = O.build_ot_from_waveform(g["to"], g["wo"], grid, lambdav=lam)
+    win, src = O.build_ot_from_waveform(g["tp"], g["wp"], grid, lambdav=lam, deriv=True)
+    ks = g["ks"].astype(int)
+    np.testing.assert_array_equal(win.irays[ks], g["fd"][:, 0].astype(int))
+    np.testing.assert_allclose(win.dddy[ks], g["dddy"], rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(win.dddy[ks], g["fd"][:, 1:], rtol=2e-2, atol=1e-5)        # the reference's FD step: ~1 %
+    out = O.marg_wasserstein(src, tgt, distfunc="W2", derivatives=True, returnmargW=True)
+    dWt, dWu = out[1]
+    np.testing.assert_allclose(np.stack([dWt.reshape(-1)[ks], dWu.reshape(-1)[ks]], axis=1), g["marg"], rtol=1e-4, atol=1e-9)
