@@ -1,7 +1,9 @@
 """Key per-kernel counters of an .ncu-rep (raw page): usage ncu_key.py report.ncu-rep
-NCU_SKIP=<n>: leave out the first n launches of the report (warm-up / set-up launches of the same kernels)."""
+NCU_SKIP=<n>: leave out the first n launches of the report (warm-up / set-up launches of the same kernels);
+NCU_COUNT=<n>: read n launches."""
 import csv, os, subprocess, sys, io
-skip = ["--launch-skip", os.environ["NCU_SKIP"]] if os.environ.get("NCU_SKIP") else []
+skip = (["--launch-skip", os.environ["NCU_SKIP"]] if os.environ.get("NCU_SKIP") else []) + \
+       (["--launch-count", os.environ["NCU_COUNT"]] if os.environ.get("NCU_COUNT") else [])
 out = subprocess.run(["ncu", "-i", sys.argv[1]] + skip + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]

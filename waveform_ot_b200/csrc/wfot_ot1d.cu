@@ -473,6 +473,23 @@ __device__ __forceinline__ int merge_split(const double* cf, const double* cg, i
     return lo;
 }
 
+// the splits of a lane's two chains side by side: two independent chains of dependent shared-memory loads per lane
+// instead of one after the other (the bisection is pure load latency)
+__device__ __forceinline__ void merge_split2(const double* cf, const double* cg, int n, int m, int dA, int dB,
+                                             int& ia, int& ib) {
+    int loA = max(0, dA - m), hiA = min(dA, n - 1);
+    int loB = max(0, dB - m), hiB = min(dB, n - 1);
+    while (loA < hiA || loB < hiB) {
+        const int mA = (loA + hiA) >> 1, mB = (loB + hiB) >> 1;
+        const bool actA = loA < hiA, actB = loB < hiB;
+        const double fa = cf[mA], ga = cg[min(max(dA - 1 - mA, 0), m - 1)];    // in range whenever the search is active
+        const double fb = cf[mB], gb = cg[min(max(dB - 1 - mB, 0), m - 1)];
+        if (actA) { if (fa <= ga) loA = mA + 1; else hiA = mA; }
+        if (actB) { if (fb <= gb) loB = mB + 1; else hiB = mB; }
+    }
+    ia = loA; ib = loB;
+}
+
 template <bool STRICT, int PM, int EM, bool MO>
 __device__ __forceinline__ void warp_merge(const double* cf, const double* xf, int npad,
                                            double* e1s, double* e2s, int32_t* mo, int n, int m, int lane, Acc& acc) {
@@ -480,8 +497,8 @@ __device__ __forceinline__ void warp_merge(const double* cf, const double* xf, i
     const int K = n - 1 + m;
     const int per = (K + 63) >> 6;                // knots per chain (64 chains per warp)
     const int dA = min(2 * lane * per, K), dB = min(dA + per, K), dE = min(dB + per, K);
-    const int iaA = merge_split(cf, cg, n, m, dA);
-    const int iaB = merge_split(cf, cg, n, m, dB);
+    int iaA, iaB;
+    merge_split2(cf, cg, n, m, dA, dB, iaA, iaB);
     int iaE = __shfl_down_sync(kFull, iaA, 1);    // the next lane's first chain starts where this lane's second ends
     if (lane == 31) iaE = n - 1;
     constexpr bool E1 = (EM & 1) != 0, E2 = (EM & 2) != 0;
